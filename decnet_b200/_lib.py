@@ -1,0 +1,64 @@
+"""ctypes binding of libdecnet_b200.so (the C ABI declared in include/decnet_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("DECNET_B200_LIB", _PKG / "libdecnet_b200.so"))
+
+_f32p = C.c_void_p
+_i = C.c_int
+
+# name -> (restype, argtypes); mirrors include/decnet_b200.h one to one.
+SIGNATURES = {
+    "decnet_abi_version": (_i, []),
+    "decnet_last_error": (C.c_char_p, []),
+    "decnet_device_info": (_i, [C.POINTER(_i)] * 3),
+    "decnet_launch_count": (C.c_int64, []),
+    "decnet_reset_launch_count": (None, []),
+    "decnet_spamat_fwd": (_i, [_f32p] * 7 + [_i] * 5 + [C.c_void_p]),
+    "decnet_spavar_fwd": (_i, [_f32p] * 8 + [_i] * 5 + [C.c_void_p]),
+    "decnet_spamat_spavar_fwd": (_i, [_f32p] * 8 + [_i] * 5 + [C.c_void_p]),
+    "decnet_spamat_bwd": (_i, [_f32p] * 10 + [_i] * 5 + [C.c_void_p]),
+    "decnet_spavar_bwd": (_i, [_f32p] * 12 + [_i] * 5 + [C.c_void_p]),
+    "decnet_candidate_signature": (_i, [_f32p] * 4 + [_i] * 4 + [C.c_void_p]),
+    "decnet_last_sparse_path": (_i, []),
+    "decnet_set_sparse_path": (None, [_i]),
+}
+
+
+class DecnetError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly if it is absent."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise DecnetError(
+                f"{LIB_PATH} not found: build it with `python -m decnet_b200.build` "
+                "(there is no CPU or PyTorch fallback for these ops)")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if handle.decnet_abi_version() != 1:
+            raise DecnetError("libdecnet_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().decnet_last_error().decode("utf-8", "replace")
+        raise DecnetError(f"{what} failed with status {status}: {msg}")

@@ -1,0 +1,411 @@
+// decnet_b200/csrc/sparse_match.cu -- SparseMatching / SparseVar for sm_100a.
+//
+// Replaces the reference's SM_kernel.cu / SV_kernel.cu.
+// Design (not a translation; the reference is thread-per-pixel with every cost
+// recomputed by four separate kernels):
+//
+//   * Both ops are ROW-LOCAL: pixel (b,h,w) only touches row (b,h) of the two
+//     feature maps, and C*W is the same at every pyramid level.  One CTA owns one
+//     row: the [C,W] slabs of L and R are staged in shared memory once
+//     (cp.async 128-bit here, TMA in sparse_match_tma.cu) and every cost of the
+//     row is evaluated from shared memory.
+//   * Mask compaction: per 32-column chunk one __ballot_sync gives the mask bits,
+//     __popc the chunk count, a warp scan over chunk counts the offsets; the
+//     sorted list of valid right columns makes the candidate set of pixel w the
+//     CONTIGUOUS list range [prefix(max(0,w-D+1)), prefix(w+1)) -- bit-exact with
+//     the reference's `tar_mask[w-d] != 0` scan, and work is proportional to
+//     density^2 instead of D.
+//   * A group of G lanes (G picked per row from the candidate density) owns one
+//     masked pixel; lanes own candidates; the channel dot product is the same
+//     sequential FMA chain as the reference (bit-identical costs); max / sum
+//     reductions are warp shuffles; SpaVar reuses the exp() of SpaMat and is
+//     evaluated against the FINAL mean (two-phase, no moment expansion).
+//   * All outputs of a row are assembled in shared memory and written with
+//     coalesced 128-bit stores, zeros included.
+#include "common.cuh"
+#include "sparse_core.cuh"
+
+namespace decnet {
+namespace sparse {
+
+// -------------------------------------------------------------------------------------
+// Row kernel, cp.async staging.  grid = B*H rows, block = kThreads.
+// -------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+sparse_row_cpasync_kernel(const float *__restrict__ L, const float *__restrict__ R,
+                          const float *__restrict__ lmask, const float *__restrict__ rmask,
+                          const float *__restrict__ disp_in,
+                          float *__restrict__ out_a,   // MAT: out   VAR: var   FUSED: out
+                          float *__restrict__ out_b,   // FUSED: var, else unused
+                          float *__restrict__ sum_sim, float *__restrict__ max_cost,
+                          int C, int H, int W, int D, int vec_ok)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x;
+    const int b = row / H, h = row - b * H;
+    const int Wp = (W + 3) & ~3;
+    RowSmem s = carve_row_smem(smem_raw, C, W);
+
+    const size_t plane = (size_t)H * W;
+    const float *Lrow = L + (size_t)b * C * plane + (size_t)h * W;
+    const float *Rrow = R + (size_t)b * C * plane + (size_t)h * W;
+
+    // 1. put the whole [C,W] slabs of both views in flight
+    if (vec_ok) {
+        const int w4n = W >> 2;
+        const int total = C * w4n;
+        for (int i = tid; i < total; i += kThreads) {
+            const int c = i / w4n, w4 = i - c * w4n;
+            cp_async_16(s.Ls + c * Wp + 4 * w4, Lrow + (size_t)c * plane + 4 * w4);
+            cp_async_16(s.Rs + c * Wp + 4 * w4, Rrow + (size_t)c * plane + 4 * w4);
+        }
+    } else {
+        const int total = C * W;
+        for (int i = tid; i < total; i += kThreads) {
+            const int c = i / W, w = i - c * W;
+            cp_async_4(s.Ls + c * Wp + w, Lrow + (size_t)c * plane + w);
+            cp_async_4(s.Rs + c * Wp + w, Rrow + (size_t)c * plane + w);
+        }
+    }
+    cp_async_commit();
+
+    // 2. while they fly: compact both masks of this row, clear the output rows
+    const size_t m0 = (size_t)row * W;
+    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads);
+    for (int w = tid; w < Wp; w += kThreads) {
+        s.o_a[w] = 0.f; s.o_b[w] = 0.f; s.o_ssim[w] = 0.f; s.o_max[w] = 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // 3. costs / softmax regression / variance for every masked pixel of the row
+    const int G = pick_group_size(s.counts[1], W, D);
+    process_row<MODE>(s, s.Ls, s.Rs, /*chan_stride=*/Wp, C, W, D,
+                      MODE == MODE_VAR ? disp_in + m0 : nullptr, G, tid, kThreads);
+    __syncthreads();
+
+    // 4. coalesced row stores (every element, zeros included)
+    store_row(out_a + m0, s.o_a, W, vec_ok, tid, kThreads);
+    if (MODE == MODE_FUSED) store_row(out_b + m0, s.o_b, W, vec_ok, tid, kThreads);
+    store_row(sum_sim + m0, s.o_ssim, W, vec_ok, tid, kThreads);
+    store_row(max_cost + m0, s.o_max, W, vec_ok, tid, kThreads);
+}
+
+// -------------------------------------------------------------------------------------
+// Candidate signature (test hook): same compaction + prefix code, no features.
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+candidate_signature_kernel(const float *__restrict__ lmask, const float *__restrict__ rmask,
+                           int32_t *__restrict__ count, unsigned long long *__restrict__ hash,
+                           int W, int D)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const size_t m0 = (size_t)blockIdx.x * W;
+    RowSmem s = carve_row_smem(smem_raw, /*C=*/0, W);
+    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads);
+    __syncthreads();
+    for (int w = tid; w < W; w += kThreads) { count[m0 + w] = 0; hash[m0 + w] = 0ull; }
+    __syncthreads();
+    const int nL = s.counts[0];
+    for (int i = tid; i < nL; i += kThreads) {
+        const int w = (int)(s.llist[i] & 0xffffu);
+        const int x0 = max(0, w - D + 1);
+        const int lo = row_prefix(s, x0), hi = row_prefix(s, w + 1);
+        unsigned long long hs = 0ull;
+        for (int j = lo; j < hi; ++j) {
+            const int d = w - (int)(s.rlist[j] & 0xffffu);
+            unsigned long long x = (unsigned long long)(d + 1) * 0x9E3779B97F4A7C15ull;
+            x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+            hs += x;
+        }
+        count[m0 + w] = max(hi - lo, 0);
+        hash[m0 + w] = hs;
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// Backward (API parity with SM_kernel.cu:143-195,300-355 and SV_kernel.cu:142-325).
+// One CTA per row, one warp per masked pixel; the per-candidate weight
+//   p_d = e_d * q_d   (q = d - out   or   (d-disp)^2 - var)
+// is computed once per (pixel, candidate) instead of once per channel thread.
+// Gradients arrive zero-filled; only masked positions are written (reference contract).
+// -------------------------------------------------------------------------------------
+template <int VARMODE>
+__global__ void __launch_bounds__(kThreads)
+sparse_row_backward_kernel(const float *__restrict__ L, const float *__restrict__ R,
+                           const float *__restrict__ lmask, const float *__restrict__ rmask,
+                           const float *__restrict__ disp, const float *__restrict__ outv,
+                           const float *__restrict__ sum_sim, const float *__restrict__ max_cost,
+                           const float *__restrict__ gout,
+                           float *__restrict__ dL, float *__restrict__ dR, float *__restrict__ ddisp,
+                           int C, int H, int W, int D, int vec_ok)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nWarps = kThreads / 32;
+    const int row = blockIdx.x;
+    const int b = row / H, h = row - b * H;
+    const int Wp = (W + 3) & ~3;
+    RowSmem s = carve_row_smem(smem_raw, C, W);
+    const size_t plane = (size_t)H * W;
+    const size_t f0 = (size_t)b * C * plane + (size_t)h * W;
+    const float *Lrow = L + f0, *Rrow = R + f0;
+    if (vec_ok) {
+        const int w4n = W >> 2, total = C * w4n;
+        for (int i = tid; i < total; i += kThreads) {
+            const int c = i / w4n, w4 = i - c * w4n;
+            cp_async_16(s.Ls + c * Wp + 4 * w4, Lrow + (size_t)c * plane + 4 * w4);
+            cp_async_16(s.Rs + c * Wp + 4 * w4, Rrow + (size_t)c * plane + 4 * w4);
+        }
+    } else {
+        const int total = C * W;
+        for (int i = tid; i < total; i += kThreads) {
+            const int c = i / W, w = i - c * W;
+            cp_async_4(s.Ls + c * Wp + w, Lrow + (size_t)c * plane + w);
+            cp_async_4(s.Rs + c * Wp + w, Rrow + (size_t)c * plane + w);
+        }
+    }
+    cp_async_commit();
+    const size_t m0 = (size_t)row * W;
+    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads);
+    // per-pixel scalars of the row -> shared (o_a: out/var, o_b: disp, o_ssim, o_max)
+    for (int w = tid; w < W; w += kThreads) {
+        s.o_a[w] = outv[m0 + w];
+        s.o_b[w] = VARMODE ? disp[m0 + w] : 0.f;
+        s.o_ssim[w] = sum_sim[m0 + w];
+        s.o_max[w] = max_cost[m0 + w];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int nL = s.counts[0], nR = s.counts[1];
+
+    // ---- left gradient (and SpaVar's disparity gradient): warp per masked left pixel.
+    // Lanes own candidates in ascending d (descending list index); the first KB*32
+    // candidate weights p = e*q stay in registers, the (rare) remainder is recomputed.
+    constexpr int KB = 8;
+    for (int i = warp; i < nL; i += nWarps) {
+        const int w = (int)(s.llist[i] & 0xffffu);
+        const int lo = row_prefix(s, max(0, w - D + 1)), hi = row_prefix(s, w + 1);
+        const float mx = s.o_max[w], ov = s.o_a[w], mu = s.o_b[w];
+        const float gw = gout[m0 + w], ss = s.o_ssim[w];
+        auto weight = [&](int col, float &dpart) -> float {
+            float cost = 0.f;
+            for (int cc = 0; cc < C; ++cc) cost = fmaf(s.Ls[cc * Wp + w], s.Rs[cc * Wp + col], cost);
+            const float e = expf(cost - mx);
+            const float df = (float)(w - col);
+            if (VARMODE) { const float dd = df - mu; dpart = e * dd; return e * (dd * dd - ov); }
+            dpart = 0.f;
+            return e * (df - ov);
+        };
+        float p[KB]; int ro[KB];
+        float dacc = 0.f;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const int j = hi - 1 - (k * 32 + lane);
+            p[k] = 0.f; ro[k] = 0;
+            if (j >= lo) {
+                ro[k] = (int)(s.rlist[j] & 0xffffu);
+                float dp; p[k] = weight(ro[k], dp); dacc += dp;
+            }
+        }
+        for (int j = hi - 1 - (KB * 32 + lane); j >= lo; j -= 32) {
+            float dp; (void)weight((int)(s.rlist[j] & 0xffffu), dp); dacc += dp;
+        }
+        for (int c = 0; c < C; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < KB; ++k) acc += p[k] * s.Rs[c * Wp + ro[k]];
+            for (int j = hi - 1 - (KB * 32 + lane); j >= lo; j -= 32) {
+                const int col = (int)(s.rlist[j] & 0xffffu);
+                float dp; acc += weight(col, dp) * s.Rs[c * Wp + col];
+            }
+            acc = group_sum(acc, 32);
+            if (lane == 0) dL[f0 + (size_t)c * plane + w] = gw * acc / ss;
+        }
+        if (VARMODE) {
+            dacc = group_sum(dacc, 32);
+            if (lane == 0) ddisp[m0 + w] = -2 * gw * dacc / ss;
+        }
+    }
+    // ---- right gradient: warp per masked right pixel, gather over masked left pixels
+    // wl = w + d, d in [0, min(D, W - w))  (SM_kernel.cu:327-346)
+    for (int i = warp; i < nR; i += nWarps) {
+        const int w = (int)(s.rlist[i] & 0xffffu);
+        const int lo = left_prefix(s, w), hi = left_prefix(s, min(W, w + D));
+        auto weight = [&](int wl) -> float {
+            float cost = 0.f;
+            for (int cc = 0; cc < C; ++cc) cost = fmaf(s.Ls[cc * Wp + wl], s.Rs[cc * Wp + w], cost);
+            const float e = expf(cost - s.o_max[wl]);
+            const float df = (float)(wl - w);
+            float q;
+            if (VARMODE) { const float dd = df - s.o_b[wl]; q = dd * dd - s.o_a[wl]; }
+            else q = df - s.o_a[wl];
+            return gout[m0 + wl] * e * q / s.o_ssim[wl];
+        };
+        float p[KB]; int ro[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const int j = lo + k * 32 + lane;
+            p[k] = 0.f; ro[k] = 0;
+            if (j < hi) { ro[k] = (int)(s.llist[j] & 0xffffu); p[k] = weight(ro[k]); }
+        }
+        for (int c = 0; c < C; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < KB; ++k) acc += p[k] * s.Ls[c * Wp + ro[k]];
+            for (int j = lo + KB * 32 + lane; j < hi; j += 32) {
+                const int wl = (int)(s.llist[j] & 0xffffu);
+                acc += weight(wl) * s.Ls[c * Wp + wl];
+            }
+            acc = group_sum(acc, 32);
+            if (lane == 0) dR[f0 + (size_t)c * plane + w] = acc;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------
+static thread_local int g_last_path = 0;
+static thread_local int g_forced_path = 0;
+
+static int validate_common(const void *L, const void *R, const void *ml, const void *mr,
+                           int B, int C, int H, int W)
+{
+    DECNET_REQUIRE(L && R && ml && mr, "null input pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size B=%d C=%d H=%d W=%d", B, C, H, W);
+    DECNET_REQUIRE((long long)B * H < (1ll << 31), "B*H too large");
+    if (W > 65535) { set_error("W=%d exceeds 65535 columns", W); return DECNET_ERR_UNSUPPORTED; }
+    return 0;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int tma_forward(int mode, const float *L, const float *R, const float *ml, const float *mr,
+                const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
+                int B, int C, int H, int W, int D, cudaStream_t st, bool *handled);
+
+template <int MODE>
+static int launch_cpasync(const float *L, const float *R, const float *ml, const float *mr,
+                          const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
+                          int B, int C, int H, int W, int D, cudaStream_t st)
+{
+    const size_t smem = row_smem_bytes(C, W);
+    if (smem > kMaxSmem) {
+        set_error("row slab needs %zu B of shared memory (> %d): C*W=%d too large", smem, (int)kMaxSmem, C * W);
+        return DECNET_ERR_UNSUPPORTED;
+    }
+    auto kern = sparse_row_cpasync_kernel<MODE>;
+    DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int vec_ok = (W % 4 == 0) && aligned16(L) && aligned16(R) && aligned16(out_a) && aligned16(ssim) &&
+                       aligned16(mx) && (MODE != MODE_FUSED || aligned16(out_b));
+    kern<<<B * H, kThreads, smem, st>>>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, C, H, W, D, vec_ok);
+    return after_launch("sparse_row_cpasync_kernel");
+}
+
+static int forward_dispatch(int mode, const float *L, const float *R, const float *ml, const float *mr,
+                            const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
+                            int B, int C, int H, int W, int D, void *stream)
+{
+    int st_ = validate_common(L, R, ml, mr, B, C, H, W);
+    if (st_) return st_;
+    DECNET_REQUIRE(out_a && ssim && mx, "null output pointer");
+    DECNET_REQUIRE(mode != MODE_VAR || disp, "null disparity pointer");
+    DECNET_REQUIRE(mode != MODE_FUSED || out_b, "null variance output pointer");
+    if (D < 0) D = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g_forced_path != 1) {
+        bool handled = false;
+        int rc = tma_forward(mode, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st, &handled);
+        if (handled) { g_last_path = 2; return rc; }
+        if (g_forced_path == 2) {
+            set_error("TMA path forced but shape/alignment not eligible (W=%d)", W);
+            return DECNET_ERR_UNSUPPORTED;
+        }
+    }
+    g_last_path = 1;
+    switch (mode) {
+        case MODE_MAT: return launch_cpasync<MODE_MAT>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st);
+        case MODE_VAR: return launch_cpasync<MODE_VAR>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st);
+        default:       return launch_cpasync<MODE_FUSED>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st);
+    }
+}
+
+template <int VARMODE>
+static int backward_dispatch(const float *L, const float *R, const float *ml, const float *mr,
+                             const float *disp, const float *outv, const float *ssim, const float *mx,
+                             const float *g, float *dL, float *dR, float *ddisp,
+                             int B, int C, int H, int W, int D, void *stream)
+{
+    int st_ = validate_common(L, R, ml, mr, B, C, H, W);
+    if (st_) return st_;
+    DECNET_REQUIRE(outv && ssim && mx && g && dL && dR, "null pointer in backward");
+    DECNET_REQUIRE(!VARMODE || (disp && ddisp), "null disparity pointer in backward");
+    if (D < 0) D = 0;
+    const size_t smem = row_smem_bytes(C, W);
+    if (smem > kMaxSmem) {
+        set_error("row slab needs %zu B of shared memory (> %d)", smem, (int)kMaxSmem);
+        return DECNET_ERR_UNSUPPORTED;
+    }
+    auto kern = sparse_row_backward_kernel<VARMODE>;
+    DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int vec_ok = (W % 4 == 0) && aligned16(L) && aligned16(R);
+    kern<<<B * H, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        L, R, ml, mr, disp, outv, ssim, mx, g, dL, dR, ddisp, C, H, W, D, vec_ok);
+    return after_launch("sparse_row_backward_kernel");
+}
+
+}  // namespace sparse
+}  // namespace decnet
+
+using namespace decnet::sparse;
+
+extern "C" {
+
+int decnet_spamat_fwd(const float *L, const float *R, const float *ml, const float *mr,
+                      float *out, float *ssim, float *mx, int B, int C, int H, int W, int D, void *stream) {
+    return forward_dispatch(MODE_MAT, L, R, ml, mr, nullptr, out, nullptr, ssim, mx, B, C, H, W, D, stream);
+}
+
+int decnet_spavar_fwd(const float *L, const float *R, const float *ml, const float *mr, const float *disp,
+                      float *var, float *ssim, float *mx, int B, int C, int H, int W, int D, void *stream) {
+    return forward_dispatch(MODE_VAR, L, R, ml, mr, disp, var, nullptr, ssim, mx, B, C, H, W, D, stream);
+}
+
+int decnet_spamat_spavar_fwd(const float *L, const float *R, const float *ml, const float *mr,
+                             float *out, float *var, float *ssim, float *mx,
+                             int B, int C, int H, int W, int D, void *stream) {
+    return forward_dispatch(MODE_FUSED, L, R, ml, mr, nullptr, out, var, ssim, mx, B, C, H, W, D, stream);
+}
+
+int decnet_spamat_bwd(const float *L, const float *R, const float *ml, const float *mr, const float *out,
+                      const float *ssim, const float *mx, const float *g, float *dL, float *dR,
+                      int B, int C, int H, int W, int D, void *stream) {
+    return backward_dispatch<0>(L, R, ml, mr, nullptr, out, ssim, mx, g, dL, dR, nullptr, B, C, H, W, D, stream);
+}
+
+int decnet_spavar_bwd(const float *L, const float *R, const float *ml, const float *mr, const float *disp,
+                      const float *var, const float *ssim, const float *mx, const float *g,
+                      float *dL, float *dR, float *ddisp, int B, int C, int H, int W, int D, void *stream) {
+    return backward_dispatch<1>(L, R, ml, mr, disp, var, ssim, mx, g, dL, dR, ddisp, B, C, H, W, D, stream);
+}
+
+int decnet_candidate_signature(const float *ml, const float *mr, int32_t *count, uint64_t *hash,
+                               int B, int H, int W, int D, void *stream) {
+    DECNET_REQUIRE(ml && mr && count && hash, "null pointer");
+    DECNET_REQUIRE(B > 0 && H > 0 && W > 0 && W <= 65535, "bad size B=%d H=%d W=%d", B, H, W);
+    if (D < 0) D = 0;
+    const size_t smem = row_smem_bytes(0, W);
+    DECNET_CUDA(cudaFuncSetAttribute(candidate_signature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    candidate_signature_kernel<<<B * H, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        ml, mr, count, reinterpret_cast<unsigned long long *>(hash), W, D);
+    return decnet::after_launch("candidate_signature_kernel");
+}
+
+int decnet_last_sparse_path(void) { return g_last_path; }
+void decnet_set_sparse_path(int path) { g_forced_path = path; }
+
+}  // extern "C"

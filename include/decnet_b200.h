@@ -1,0 +1,120 @@
+/*
+ * decnet_b200.h -- C ABI of libdecnet_b200.so (sm_100a).
+ *
+ * Drop-in boundary for DecNet's decomposed-matching hot path.  Every entry point
+ * takes raw DEVICE pointers, explicit sizes and an explicit CUDA stream (passed
+ * as void* == cudaStream_t; NULL is the legacy default stream), returns 0 on
+ * success or a non-zero code (DECNET_ERR_* or a cudaError_t value offset by
+ * DECNET_ERR_CUDA_BASE) and records a message readable through
+ * decnet_last_error() (thread-local).  No torch / pybind types appear here.
+ *
+ * Unless stated otherwise tensors are fp32, contiguous, NCHW ("feats":
+ * [B,C,H,W]) or [B,H,W] ("planes"), exactly what the reference's extension
+ * receives (reference: modules/SparseMatching/src/SM_kernel.cu:359-376 reads
+ * sizes from ref_feas.size(0..3) and data_ptr<float>()).
+ *
+ * Ownership: the caller allocates every output; the library never allocates
+ * user-visible memory and retains no pointer after the call returns (work is
+ * only enqueued on `stream`).  The forward entry points write EVERY element of
+ * their [B,H,W] outputs (zeros where the left mask is 0), so outputs need not be
+ * zero-filled (the reference requires zero-filled outputs:
+ * modules/SparseMatching/functions/SpaMat.py:25-27).  The backward entry points
+ * keep the reference contract: gradients must arrive zero-filled
+ * (functions/SpaMat.py:42-43) and only masked positions are written.
+ *
+ * Thread safety: no global mutable state except per-device caches guarded by a
+ * mutex; safe to call from one host thread per device (the reference is driven
+ * by nn.DataParallel worker threads, eval.py:145-146).
+ */
+#ifndef DECNET_B200_H
+#define DECNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DECNET_ABI_VERSION 1
+
+#define DECNET_OK 0
+#define DECNET_ERR_INVALID 1      /* bad argument (null pointer, non-positive size, ...) */
+#define DECNET_ERR_UNSUPPORTED 2  /* shape outside what the kernels support          */
+#define DECNET_ERR_CUDA_BASE 1000 /* 1000 + cudaError_t                              */
+
+int decnet_abi_version(void);
+const char *decnet_last_error(void);
+/* Number of SMs / compute capability of the current device (for host-side sizing). */
+int decnet_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* Kernel launches issued by this library on the calling thread since the last reset. */
+int64_t decnet_launch_count(void);
+void decnet_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Sparse matching.
+ *
+ * Candidate set of pixel (b,h,w) with lmask != 0:
+ *     { d : 0 <= d < min(max_disp, w+1), rmask[b,h,w-d] != 0 }
+ *   cost_d   = sum_c L[b,c,h,w] * R[b,c,h,w-d]      (sequential FMA chain over c)
+ *   max_cost = max(1e-6, max_d cost_d)
+ *   e_d      = expf(cost_d - max_cost);  sum_sim = 1e-6 + sum_d e_d
+ *   out      = (1e-6 + sum_d e_d * d) / sum_sim                    (SpaMat)
+ *   var      = (1e-6 + sum_d e_d * (d - disp)^2) / sum_sim         (SpaVar)
+ * Replaces: sparse_matching_cuda_forward  (modules/SparseMatching/src/SM_cuda.cpp:7-15,
+ *           kernels SM_kernel.cu:22-125), sparse_var_cuda_forward
+ *           (modules/SparseVar/src/SV_cuda.cpp:7-16, kernels SV_kernel.cu:22-124).
+ * ------------------------------------------------------------------------- */
+int decnet_spamat_fwd(const float *ref_feas, const float *tar_feas,
+                      const float *ref_mask, const float *tar_mask,
+                      float *output, float *sum_similarities, float *max_cost,
+                      int B, int C, int H, int W, int max_disp, void *stream);
+
+int decnet_spavar_fwd(const float *ref_feas, const float *tar_feas,
+                      const float *ref_mask, const float *tar_mask,
+                      const float *disparity,
+                      float *output, float *sum_similarities, float *max_cost,
+                      int B, int C, int H, int W, int max_disp, void *stream);
+
+/* SpaMat followed by SpaVar(disparity = SpaMat output) in ONE pass over the
+ * feature rows (what the model does back to back:
+ * modules/SparseDenseNetRefinementMask.py:183-192). */
+int decnet_spamat_spavar_fwd(const float *ref_feas, const float *tar_feas,
+                             const float *ref_mask, const float *tar_mask,
+                             float *disp_out, float *var_out,
+                             float *sum_similarities, float *max_cost,
+                             int B, int C, int H, int W, int max_disp, void *stream);
+
+/* Replaces sparse_matching_cuda_backward (SM_cuda.cpp:17-27, SM_kernel.cu:143-195,300-355). */
+int decnet_spamat_bwd(const float *ref_feas, const float *tar_feas,
+                      const float *ref_mask, const float *tar_mask,
+                      const float *output, const float *sum_similarities,
+                      const float *max_cost, const float *grad_output,
+                      float *grad_ref_feas, float *grad_tar_feas,
+                      int B, int C, int H, int W, int max_disp, void *stream);
+
+/* Replaces sparse_var_cuda_backward (SV_cuda.cpp:18-30, SV_kernel.cu:142-325). */
+int decnet_spavar_bwd(const float *ref_feas, const float *tar_feas,
+                      const float *ref_mask, const float *tar_mask,
+                      const float *disparity, const float *output,
+                      const float *sum_similarities, const float *max_cost,
+                      const float *grad_output,
+                      float *grad_ref_feas, float *grad_tar_feas, float *grad_disparity,
+                      int B, int C, int H, int W, int max_disp, void *stream);
+
+/* Per-pixel candidate count and order-independent 64-bit hash of the candidate
+ * set, produced by the SAME compaction code the matching kernels use.  Test hook
+ * for the "candidate indices bit-exact" gate. */
+int decnet_candidate_signature(const float *ref_mask, const float *tar_mask,
+                               int32_t *count, uint64_t *hash,
+                               int B, int H, int W, int max_disp, void *stream);
+
+/* Which row kernel the last spamat/spavar forward on this thread used:
+ * 0 = none, 1 = cp.async row kernel (any W / alignment), 2 = TMA persistent kernel. */
+int decnet_last_sparse_path(void);
+/* Force a path for the forward ops on this thread: 0 = auto, 1 = cp.async, 2 = TMA. */
+void decnet_set_sparse_path(int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECNET_B200_H */
