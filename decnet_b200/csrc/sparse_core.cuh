@@ -1,8 +1,7 @@
 // decnet_b200/csrc/sparse_core.cuh -- row-level building blocks shared by the cp.async and
 // TMA sparse-matching kernels: shared-memory carve-up, ballot/popc mask compaction,
-// candidate-range lookup, the per-pixel cost / softmax-regression / variance evaluation,
-// and coalesced row stores.  Semantics: SURVEY.md appendix A (reference
-// SM_kernel.cu:22-125, SV_kernel.cu:76-124).
+// candidate-range lookup and the per-pixel cost / softmax-regression / variance evaluation.
+// Semantics: SURVEY.md appendix A (reference SM_kernel.cu:22-125, SV_kernel.cu:76-124).
 #pragma once
 #include "common.cuh"
 #include <math_constants.h>
@@ -11,15 +10,13 @@ namespace decnet {
 namespace sparse {
 
 constexpr int kThreads = 256;          // threads that evaluate a row
-constexpr int KU = 4;                  // candidates per lane per round (held in registers)
+constexpr int KU = 4;                  // candidates per lane evaluated together (independent FMA chains)
 constexpr size_t kMaxSmem = 227 * 1024;
 constexpr float kEps6 = 0.000001f;     // SM_kernel.cu:45,104
 
 enum { MODE_MAT = 0, MODE_VAR = 1, MODE_FUSED = 2 };
 
 struct RowSmem {
-    float *Ls, *Rs;                    // [C][Wp] slabs (cp.async layout)
-    float *o_a, *o_b, *o_ssim, *o_max; // output rows
     uint32_t *rlist, *llist;           // compacted columns: (smem_offset << 16) | column
     uint32_t *rbits, *lbits;           // mask bits per 32-column chunk (+1 sentinel)
     int *roff, *loff;                  // exclusive chunk offsets (+1 total)
@@ -28,25 +25,14 @@ struct RowSmem {
 
 __host__ __device__ inline size_t list_smem_bytes(int W) {
     const size_t Wp = (size_t)((W + 3) & ~3);
-    const size_t nch = (size_t)((W + 31) / 32) + 1;
-    return 4 * Wp * 4        // 4 output rows
-           + 2 * Wp * 4      // rlist, llist
-           + 4 * ((nch + 3) & ~(size_t)3) * 4   // rbits lbits roff loff
-           + 16;             // counts
-}
-__host__ __device__ inline size_t row_smem_bytes(int C, int W) {
-    const size_t Wp = (size_t)((W + 3) & ~3);
-    return 2 * (size_t)C * Wp * 4 + list_smem_bytes(W);
+    const size_t nch = (((size_t)((W + 31) / 32) + 1) + 3) & ~(size_t)3;
+    return 2 * Wp * 4 + 4 * nch * 4 + 16;
 }
 
-// lists / outputs carved from `p` (16-byte aligned)
+// lists carved from `p` (16-byte aligned)
 __device__ inline unsigned char *carve_lists(RowSmem &s, unsigned char *p, int W) {
     const size_t Wp = (size_t)((W + 3) & ~3);
     const size_t nch = (((size_t)((W + 31) / 32) + 1) + 3) & ~(size_t)3;
-    s.o_a = reinterpret_cast<float *>(p);    p += Wp * 4;
-    s.o_b = reinterpret_cast<float *>(p);    p += Wp * 4;
-    s.o_ssim = reinterpret_cast<float *>(p); p += Wp * 4;
-    s.o_max = reinterpret_cast<float *>(p);  p += Wp * 4;
     s.rlist = reinterpret_cast<uint32_t *>(p); p += Wp * 4;
     s.llist = reinterpret_cast<uint32_t *>(p); p += Wp * 4;
     s.rbits = reinterpret_cast<uint32_t *>(p); p += nch * 4;
@@ -55,15 +41,6 @@ __device__ inline unsigned char *carve_lists(RowSmem &s, unsigned char *p, int W
     s.loff = reinterpret_cast<int *>(p);       p += nch * 4;
     s.counts = reinterpret_cast<int *>(p);     p += 16;
     return p;
-}
-
-__device__ inline RowSmem carve_row_smem(unsigned char *p, int C, int W) {
-    RowSmem s;
-    const size_t Wp = (size_t)((W + 3) & ~3);
-    s.Ls = reinterpret_cast<float *>(p); p += (size_t)C * Wp * 4;
-    s.Rs = reinterpret_cast<float *>(p); p += (size_t)C * Wp * 4;
-    carve_lists(s, p, W);
-    return s;
 }
 
 // number of valid right columns strictly below x, x in [0, W]
@@ -82,26 +59,23 @@ __device__ __forceinline__ int left_prefix(const RowSmem &s, int x) {
 //   tile_bw  > 0 : TMA box layout [chunk][C][bw]  -> (w / bw) * chunk_stride + w % bw
 // Mask test is `!= 0` on fp32 exactly as the reference's `== 0` early-outs
 // (SM_kernel.cu:33,49): -0.0 is unmasked, NaN is masked.
-__device__ inline void compact_row_masks(RowSmem &s, const float *lmask_row, const float *rmask_row,
+__device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ lmask_row,
+                                         const float *__restrict__ rmask_row,
                                          int W, int tid, int nthreads,
-                                         int tile_bw = 0, int chunk_stride = 0, int bar_id = 0)
+                                         int tile_bw = 0, int chunk_stride = 0)
 {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int nch = (W + 31) >> 5;
-    auto sync = [&]() {
-        if (bar_id == 0) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
-    };
     for (int k = warp; k < nch; k += nwarps) {
         const int w = (k << 5) + lane;
-        const bool lv = (w < W) && (lmask_row[w] != 0.f);
-        const bool rv = (w < W) && (rmask_row[w] != 0.f);
+        const bool lv = (w < W) && (__ldg(lmask_row + w) != 0.f);
+        const bool rv = (w < W) && (__ldg(rmask_row + w) != 0.f);
         const uint32_t lb = __ballot_sync(0xffffffffu, lv);
         const uint32_t rb = __ballot_sync(0xffffffffu, rv);
         if (lane == 0) { s.lbits[k] = lb; s.rbits[k] = rb; }
     }
     if (tid == 0) { s.lbits[nch] = 0u; s.rbits[nch] = 0u; }
-    sync();
+    __syncthreads();
     if (warp == 0) {
         int carryL = 0, carryR = 0;
         for (int base = 0; base < nch; base += 32) {
@@ -121,7 +95,7 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *lmask_row, con
         }
         if (lane == 0) { s.loff[nch] = carryL; s.roff[nch] = carryR; s.counts[0] = carryL; s.counts[1] = carryR; }
     }
-    sync();
+    __syncthreads();
     for (int k = warp; k < nch; k += nwarps) {
         const int w = (k << 5) + lane;
         const uint32_t lb = s.lbits[k], rb = s.rbits[k];
@@ -132,32 +106,62 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *lmask_row, con
         if ((lb >> lane) & 1u) s.llist[s.loff[k] + __popc(lb & below)] = packed;
         if ((rb >> lane) & 1u) s.rlist[s.roff[k] + __popc(rb & below)] = packed;
     }
-    sync();
+    __syncthreads();
 }
 
-// lanes per masked pixel, from the expected number of candidates per pixel of this row
-__device__ __forceinline__ int pick_group_size(int nR, int W, int D) {
-    const float avg = 1.25f * (float)nR * (float)min(D, W) / (float)W;
-    int G = 1;
-    while (G < 32 && (float)(G * KU) < avg) G <<= 1;
-    return G;
+// Lanes per masked pixel.  Tiny cost model (warp instructions for the row) evaluated for
+// G = 1..32: waves(G) * (chunks(G) * per_chunk + per_pixel + per_shuffle_step * log2 G).
+__device__ __forceinline__ int pick_group_log2(int nL, int nR, int W, int D, int C, int nthreads) {
+    const float avg = (float)nR * (float)min(D, W) / (float)W;
+    const float hi = avg + 2.f * sqrtf(avg) + 1.f;        // ~max candidates over the lanes of a warp
+    const float per_chunk = (float)(KU * (2 * C + 28));
+    int best = 0; float best_cost = 3.0e38f;
+#pragma unroll
+    for (int lg = 0; lg <= 5; ++lg) {
+        const int G = 1 << lg;
+        const float waves = ceilf((float)nL * (float)G / (float)nthreads);
+        const float chunks = ceilf(hi / (float)(KU * G));
+        const float cost = waves * (chunks * per_chunk + 160.f + 45.f * (float)lg);
+        if (cost < best_cost) { best_cost = cost; best = lg; }
+    }
+    return best;
 }
 
-// Evaluate every masked pixel of the row.  `tid` in [0, nthreads), nthreads % 32 == 0;
-// all threads of every participating warp must call (warp shuffles inside).
-//   Ls/Rs  : staged slabs, element (c, col) at  c*cs + offset(col)
-//   MODE_MAT   o_a = out
-//   MODE_VAR   o_a = var around disp_row[w]
-//   MODE_FUSED o_a = out, o_b = var around out
-template <int MODE>
-__device__ inline void process_row(RowSmem &s, const float *__restrict__ Ls, const float *__restrict__ Rs,
-                                   int cs, int C, int W, int D, const float *disp_row,
-                                   int G, int tid, int nthreads)
+template <int G> __device__ __forceinline__ float gmax(float v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int G> __device__ __forceinline__ double gsum(double v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Evaluate every masked pixel of the row and store the results straight to global memory
+// (the rows were zero-filled earlier by the same CTA, ordered by a __syncthreads()).
+//
+// Single pass per candidate ("online softmax"): running maximum m (starts at the 1e-6
+// floor of SM_kernel.cu:45), sums rescaled by exp(m_old - m_new) when m grows.  The three
+// moments S0 = sum e, S1 = sum e*d, S2 = sum e*d^2 are kept in fp64 so that
+//     var = (1e-6 + S2 - 2*mu*S1 + mu^2*S0) / (1e-6 + S0)
+// (identical to sum e*(d-mu)^2 around the FINAL mean) has no fp32 cancellation.
+//   Ls/Rs : staged slabs, element (c, col) at  c*cs + offset(col)
+//   MODE_MAT   g_a = out
+//   MODE_VAR   g_a = var around disp_row[w]
+//   MODE_FUSED g_a = out, g_b = var around out
+template <int MODE, int G>
+__device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__restrict__ Ls,
+                                              const float *__restrict__ Rs, int cs, int C, int D,
+                                              const float *__restrict__ disp_row,
+                                              float *__restrict__ g_a, float *__restrict__ g_b,
+                                              float *__restrict__ g_ssim, float *__restrict__ g_max,
+                                              int tid, int nthreads)
 {
+    constexpr int LG = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
     const int t = tid & (G - 1);
-    const int gid = tid / G, nG = nthreads / G;
+    const int gid = tid >> LG, nG = nthreads >> LG;
     const int nL = s.counts[0];
-    const int slots = G * KU;
 
     for (int i0 = 0; i0 < nL; i0 += nG) {
         const int i = i0 + gid;
@@ -169,115 +173,98 @@ __device__ inline void process_row(RowSmem &s, const float *__restrict__ Ls, con
             lo = row_prefix(s, max(0, w - D + 1));
             hi = row_prefix(s, w + 1);
         }
-        const int cnt = max(hi - lo, 0);
-        const int nrounds = (cnt + slots - 1) / slots;
+        float m = kEps6;
+        double S0 = 0.0, S1 = 0.0, S2 = 0.0;
+        const float *lp = Ls + lw;
 
-        // costs of one round: slot k of lane t is list entry jbase + k*G + t
-        auto round_costs = [&](int jbase, float (&cost)[KU], float (&df)[KU], bool (&val)[KU]) {
-            int ro[KU];
-            const int kcnt = min(KU, (hi - jbase + G - 1) / G);   // group-uniform
+        for (int jb = lo + t; jb < hi; jb += KU * G) {
+            int ro[KU], dk[KU];
+            float cost[KU];
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
-                const int j = jbase + k * G + t;
-                val[k] = j < hi;
-                const uint32_t e = val[k] ? s.rlist[j] : 0u;
+                const int j = jb + k * G;
+                const uint32_t e = (j < hi) ? s.rlist[j] : 0u;
                 ro[k] = (int)(e >> 16);
-                df[k] = (float)(w - (int)(e & 0xffffu));
+                dk[k] = w - (int)(e & 0xffffu);
                 cost[k] = 0.f;
             }
-            const float *lp = Ls + lw;
+            // the reference's sequential FMA chain over channels, KU independent chains
 #pragma unroll 4
             for (int c = 0; c < C; ++c) {
                 const float l = lp[c * cs];
+                const float *rp = Rs + c * cs;
 #pragma unroll
-                for (int k = 0; k < KU; ++k)
-                    if (k < kcnt) cost[k] = fmaf(l, Rs[c * cs + ro[k]], cost[k]);
+                for (int k = 0; k < KU; ++k) cost[k] = fmaf(l, rp[ro[k]], cost[k]);
             }
-        };
-
-        // ---- pass 1: maximum cost (floor 1e-6, SM_kernel.cu:45-59)
-        float cost0[KU], df0[KU]; bool v0[KU];
-#pragma unroll
-        for (int k = 0; k < KU; ++k) { cost0[k] = 0.f; df0[k] = 0.f; v0[k] = false; }
-        float mx = -CUDART_INF_F;
-        if (nrounds > 0) {
-            round_costs(lo, cost0, df0, v0);
-#pragma unroll
-            for (int k = 0; k < KU; ++k) if (v0[k]) mx = fmaxf(mx, cost0[k]);
-        }
-        for (int r = 1; r < nrounds; ++r) {
-            float cr[KU], dr[KU]; bool vr[KU];
-            round_costs(lo + r * slots, cr, dr, vr);
-#pragma unroll
-            for (int k = 0; k < KU; ++k) if (vr[k]) mx = fmaxf(mx, cr[k]);
-        }
-        mx = fmaxf(group_max(mx, G), kEps6);
-
-        // ---- pass 2: softmax sums
-        const float mu_in = (MODE == MODE_VAR && act) ? disp_row[w] : 0.f;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        float e0[KU];
-#pragma unroll
-        for (int k = 0; k < KU; ++k) {
-            e0[k] = v0[k] ? expf(cost0[k] - mx) : 0.f;
-            s0 += e0[k];
-            if (MODE == MODE_VAR) { const float dd = df0[k] - mu_in; s2 += e0[k] * dd * dd; }
-            else s1 += e0[k] * df0[k];
-        }
-        for (int r = 1; r < nrounds; ++r) {
-            float cr[KU], dr[KU]; bool vr[KU];
-            round_costs(lo + r * slots, cr, dr, vr);
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
-                const float e = vr[k] ? expf(cr[k] - mx) : 0.f;
-                s0 += e;
-                if (MODE == MODE_VAR) { const float dd = dr[k] - mu_in; s2 += e * dd * dd; }
-                else s1 += e * dr[k];
-            }
-        }
-        s0 = group_sum(s0, G);
-        const float ssim = kEps6 + s0;
-        float outv = 0.f;
-        if (MODE != MODE_VAR) { s1 = group_sum(s1, G); outv = (kEps6 + s1) / ssim; }
-
-        // ---- pass 3 (fused): variance around the FINAL mean, exp() of round 0 reused
-        if (MODE == MODE_FUSED) {
-#pragma unroll
-            for (int k = 0; k < KU; ++k) { const float dd = df0[k] - outv; s2 += e0[k] * dd * dd; }
-            for (int r = 1; r < nrounds; ++r) {
-                float cr[KU], dr[KU]; bool vr[KU];
-                round_costs(lo + r * slots, cr, dr, vr);
-#pragma unroll
-                for (int k = 0; k < KU; ++k) {
-                    const float e = vr[k] ? expf(cr[k] - mx) : 0.f;
-                    const float dd = dr[k] - outv;
-                    s2 += e * dd * dd;
+                if (jb + k * G < hi) {
+                    if (cost[k] > m) {
+                        const double sc = (double)expf(m - cost[k]);
+                        S0 *= sc; S1 *= sc; if (MODE != MODE_MAT) S2 *= sc;
+                        m = cost[k];
+                    }
+                    const double e = (double)expf(cost[k] - m);
+                    const double dd = (double)dk[k];
+                    S0 += e;
+                    const double ed = e * dd;
+                    S1 += ed;
+                    if (MODE != MODE_MAT) S2 = fma(ed, dd, S2);
                 }
             }
         }
-        float varv = 0.f;
-        if (MODE != MODE_MAT) { s2 = group_sum(s2, G); varv = (kEps6 + s2) / ssim; }
-
+        // merge the G lanes of the group
+        if (G > 1) {
+            const float mg = gmax<G>(m);
+            const double sc = (double)expf(m - mg);
+            S0 = gsum<G>(S0 * sc);
+            S1 = gsum<G>(S1 * sc);
+            if (MODE != MODE_MAT) S2 = gsum<G>(S2 * sc);
+            m = mg;
+        }
         if (act && t == 0) {
-            s.o_ssim[w] = ssim;
-            s.o_max[w] = mx;
-            if (MODE == MODE_MAT) s.o_a[w] = outv;
-            else if (MODE == MODE_VAR) s.o_a[w] = varv;
-            else { s.o_a[w] = outv; s.o_b[w] = varv; }
+            const double den = (double)kEps6 + S0;
+            const float ssim = (float)den;
+            const float outv = (float)(((double)kEps6 + S1) / den);
+            g_ssim[w] = ssim;
+            g_max[w] = m;
+            if (MODE == MODE_MAT) {
+                g_a[w] = outv;
+            } else {
+                const double mu = (MODE == MODE_VAR) ? (double)disp_row[w] : (double)outv;
+                const double cen = fma(mu, fma(mu, S0, -2.0 * S1), S2);   // sum e*(d-mu)^2
+                const float varv = (float)(((double)kEps6 + cen) / den);
+                if (MODE == MODE_VAR) g_a[w] = varv;
+                else { g_a[w] = outv; g_b[w] = varv; }
+            }
         }
     }
 }
 
-__device__ __forceinline__ void store_row(float *__restrict__ dst, const float *src, int W, int vec_ok,
-                                          int tid, int nthreads)
+template <int MODE>
+__device__ inline void process_row(const RowSmem &s, const float *Ls, const float *Rs, int cs, int C,
+                                   int W, int D, const float *disp_row, float *g_a, float *g_b,
+                                   float *g_ssim, float *g_max, int tid, int nthreads)
 {
+    const int lg = pick_group_log2(s.counts[0], s.counts[1], W, D, C, nthreads);
+    switch (lg) {
+        case 0: process_row_g<MODE, 1>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
+        case 1: process_row_g<MODE, 2>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
+        case 2: process_row_g<MODE, 4>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
+        case 3: process_row_g<MODE, 8>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
+        case 4: process_row_g<MODE, 16>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
+        default: process_row_g<MODE, 32>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
+    }
+}
+
+// coalesced zero fill of one output row
+__device__ __forceinline__ void zero_row(float *__restrict__ dst, int W, int vec_ok, int tid, int nthreads) {
     if (vec_ok) {
-        const int n4 = W >> 2;
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
         float4 *d4 = reinterpret_cast<float4 *>(dst);
-        for (int i = tid; i < n4; i += nthreads) __stcs(d4 + i, s4[i]);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < (W >> 2); i += nthreads) d4[i] = z;
     } else {
-        for (int i = tid; i < W; i += nthreads) dst[i] = src[i];
+        for (int i = tid; i < W; i += nthreads) dst[i] = 0.f;
     }
 }
 

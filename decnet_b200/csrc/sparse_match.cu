@@ -24,73 +24,98 @@
 //     coalesced 128-bit stores, zeros included.
 #include "common.cuh"
 #include "sparse_core.cuh"
+#include "tma_utils.cuh"
+#include <cstring>
 
 namespace decnet {
 namespace sparse {
 
 // -------------------------------------------------------------------------------------
-// Row kernel, cp.async staging.  grid = B*H rows, block = kThreads.
+// Forward row kernel.  grid = B*H rows, block = kThreads, 3 CTAs/SM at the SceneFlow
+// shapes (62 KB of slabs + 8 KB of lists per CTA) so that while one CTA evaluates its row
+// two more have their slabs in flight.
+//   USE_TMA = true : each operand's [C, W] slab arrives as ceil(W/256) TMA boxes
+//                    {bw, 1, C} of the 3-D view (W, H, B*C); one elected thread issues them
+//                    and the CTA waits on a single mbarrier (complete_tx::bytes).
+//   USE_TMA = false: cp.async (16 B when W % 4 == 0 and pointers are 16-B aligned, else
+//                    4 B) for shapes TMA cannot describe (e.g. KITTI's odd widths).
 // -------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(kThreads)
-sparse_row_cpasync_kernel(const float *__restrict__ L, const float *__restrict__ R,
-                          const float *__restrict__ lmask, const float *__restrict__ rmask,
-                          const float *__restrict__ disp_in,
-                          float *__restrict__ out_a,   // MAT: out   VAR: var   FUSED: out
-                          float *__restrict__ out_b,   // FUSED: var, else unused
-                          float *__restrict__ sum_sim, float *__restrict__ max_cost,
-                          int C, int H, int W, int D, int vec_ok)
+template <int MODE, bool USE_TMA>
+__global__ void __launch_bounds__(kThreads, 3)
+sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+                  const float *__restrict__ L, const float *__restrict__ R,
+                  const float *__restrict__ lmask, const float *__restrict__ rmask,
+                  const float *__restrict__ disp_in,
+                  float *__restrict__ out_a,   // MAT: out   VAR: var   FUSED: out
+                  float *__restrict__ out_b,   // FUSED: var, else unused
+                  float *__restrict__ sum_sim, float *__restrict__ max_cost,
+                  int C, int H, int W, int D, int vec_ok, int bw, int nchunks, int chunk_stride)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
     const int tid = threadIdx.x;
     const int row = blockIdx.x;
     const int b = row / H, h = row - b * H;
     const int Wp = (W + 3) & ~3;
-    RowSmem s = carve_row_smem(smem_raw, C, W);
-
-    const size_t plane = (size_t)H * W;
-    const float *Lrow = L + (size_t)b * C * plane + (size_t)h * W;
-    const float *Rrow = R + (size_t)b * C * plane + (size_t)h * W;
+    unsigned char *base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int tile_floats = USE_TMA ? nchunks * chunk_stride : C * Wp;
+    float *Ls = reinterpret_cast<float *>(base);
+    float *Rs = Ls + tile_floats;
+    RowSmem s;
+    carve_lists(s, reinterpret_cast<unsigned char *>(Rs + tile_floats), W);
 
     // 1. put the whole [C,W] slabs of both views in flight
-    if (vec_ok) {
-        const int w4n = W >> 2;
-        const int total = C * w4n;
-        for (int i = tid; i < total; i += kThreads) {
-            const int c = i / w4n, w4 = i - c * w4n;
-            cp_async_16(s.Ls + c * Wp + 4 * w4, Lrow + (size_t)c * plane + 4 * w4);
-            cp_async_16(s.Rs + c * Wp + 4 * w4, Rrow + (size_t)c * plane + 4 * w4);
+    if (USE_TMA) {
+        if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&mbar, (uint32_t)(2 * nchunks * C * bw * 4));
+            for (int ch = 0; ch < nchunks; ++ch) {
+                tma_load_3d(Ls + ch * chunk_stride, &tmL, ch * bw, h, b * C, &mbar);
+                tma_load_3d(Rs + ch * chunk_stride, &tmR, ch * bw, h, b * C, &mbar);
+            }
         }
     } else {
-        const int total = C * W;
-        for (int i = tid; i < total; i += kThreads) {
-            const int c = i / W, w = i - c * W;
-            cp_async_4(s.Ls + c * Wp + w, Lrow + (size_t)c * plane + w);
-            cp_async_4(s.Rs + c * Wp + w, Rrow + (size_t)c * plane + w);
+        const int lane = tid & 31, warp = tid >> 5;
+        const size_t plane = (size_t)H * W;
+        const float *Lrow = L + (size_t)b * C * plane + (size_t)h * W;
+        const float *Rrow = R + (size_t)b * C * plane + (size_t)h * W;
+        if (vec_ok) {
+            const int w4n = W >> 2;
+            for (int c = warp; c < C; c += kThreads / 32) {
+                const float *ls = Lrow + (size_t)c * plane, *rs = Rrow + (size_t)c * plane;
+                float *ld = Ls + c * Wp, *rd = Rs + c * Wp;
+                for (int w4 = lane; w4 < w4n; w4 += 32) {
+                    cp_async_16(ld + 4 * w4, ls + 4 * w4);
+                    cp_async_16(rd + 4 * w4, rs + 4 * w4);
+                }
+            }
+        } else {
+            for (int c = warp; c < C; c += kThreads / 32) {
+                const float *ls = Lrow + (size_t)c * plane, *rs = Rrow + (size_t)c * plane;
+                float *ld = Ls + c * Wp, *rd = Rs + c * Wp;
+                for (int w = lane; w < W; w += 32) { cp_async_4(ld + w, ls + w); cp_async_4(rd + w, rs + w); }
+            }
         }
+        cp_async_commit();
     }
-    cp_async_commit();
 
-    // 2. while they fly: compact both masks of this row, clear the output rows
+    // 2. while they fly: zero the output rows in global memory, compact both masks
     const size_t m0 = (size_t)row * W;
-    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads);
-    for (int w = tid; w < Wp; w += kThreads) {
-        s.o_a[w] = 0.f; s.o_b[w] = 0.f; s.o_ssim[w] = 0.f; s.o_max[w] = 0.f;
-    }
-    cp_async_wait_all();
-    __syncthreads();
+    zero_row(out_a + m0, W, vec_ok, tid, kThreads);
+    if (MODE == MODE_FUSED) zero_row(out_b + m0, W, vec_ok, tid, kThreads);
+    zero_row(sum_sim + m0, W, vec_ok, tid, kThreads);
+    zero_row(max_cost + m0, W, vec_ok, tid, kThreads);
+    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads, USE_TMA ? bw : 0, chunk_stride);
+    if (s.counts[0] == 0) return;          // no masked pixel in this row: zeros are the answer
+    if (USE_TMA) mbar_wait(&mbar, 0);
+    else cp_async_wait_all();
+    __syncthreads();   // slabs visible to all; also orders the zero fill before the result stores
 
-    // 3. costs / softmax regression / variance for every masked pixel of the row
-    const int G = pick_group_size(s.counts[1], W, D);
-    process_row<MODE>(s, s.Ls, s.Rs, /*chan_stride=*/Wp, C, W, D,
-                      MODE == MODE_VAR ? disp_in + m0 : nullptr, G, tid, kThreads);
-    __syncthreads();
-
-    // 4. coalesced row stores (every element, zeros included)
-    store_row(out_a + m0, s.o_a, W, vec_ok, tid, kThreads);
-    if (MODE == MODE_FUSED) store_row(out_b + m0, s.o_b, W, vec_ok, tid, kThreads);
-    store_row(sum_sim + m0, s.o_ssim, W, vec_ok, tid, kThreads);
-    store_row(max_cost + m0, s.o_max, W, vec_ok, tid, kThreads);
+    // 3. costs / softmax regression / variance for every masked pixel, stored straight to global
+    process_row<MODE>(s, Ls, Rs, USE_TMA ? bw : Wp, C, W, D, MODE == MODE_VAR ? disp_in + m0 : nullptr,
+                      out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
 }
 
 // -------------------------------------------------------------------------------------
@@ -104,9 +129,9 @@ candidate_signature_kernel(const float *__restrict__ lmask, const float *__restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const size_t m0 = (size_t)blockIdx.x * W;
-    RowSmem s = carve_row_smem(smem_raw, /*C=*/0, W);
+    RowSmem s;
+    carve_lists(s, smem_raw, W);
     compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads);
-    __syncthreads();
     for (int w = tid; w < W; w += kThreads) { count[m0 + w] = 0; hash[m0 + w] = 0ull; }
     __syncthreads();
     const int nL = s.counts[0];
@@ -149,37 +174,37 @@ sparse_row_backward_kernel(const float *__restrict__ L, const float *__restrict_
     const int row = blockIdx.x;
     const int b = row / H, h = row - b * H;
     const int Wp = (W + 3) & ~3;
-    RowSmem s = carve_row_smem(smem_raw, C, W);
+    float *Ls = reinterpret_cast<float *>(smem_raw);
+    float *Rs = Ls + C * Wp;
+    RowSmem s;
+    carve_lists(s, reinterpret_cast<unsigned char *>(Rs + C * Wp), W);
     const size_t plane = (size_t)H * W;
     const size_t f0 = (size_t)b * C * plane + (size_t)h * W;
     const float *Lrow = L + f0, *Rrow = R + f0;
     if (vec_ok) {
-        const int w4n = W >> 2, total = C * w4n;
-        for (int i = tid; i < total; i += kThreads) {
-            const int c = i / w4n, w4 = i - c * w4n;
-            cp_async_16(s.Ls + c * Wp + 4 * w4, Lrow + (size_t)c * plane + 4 * w4);
-            cp_async_16(s.Rs + c * Wp + 4 * w4, Rrow + (size_t)c * plane + 4 * w4);
+        const int w4n = W >> 2;
+        for (int c = warp; c < C; c += nWarps) {
+            for (int w4 = lane; w4 < w4n; w4 += 32) {
+                cp_async_16(Ls + c * Wp + 4 * w4, Lrow + (size_t)c * plane + 4 * w4);
+                cp_async_16(Rs + c * Wp + 4 * w4, Rrow + (size_t)c * plane + 4 * w4);
+            }
         }
     } else {
-        const int total = C * W;
-        for (int i = tid; i < total; i += kThreads) {
-            const int c = i / W, w = i - c * W;
-            cp_async_4(s.Ls + c * Wp + w, Lrow + (size_t)c * plane + w);
-            cp_async_4(s.Rs + c * Wp + w, Rrow + (size_t)c * plane + w);
+        for (int c = warp; c < C; c += nWarps) {
+            for (int w = lane; w < W; w += 32) {
+                cp_async_4(Ls + c * Wp + w, Lrow + (size_t)c * plane + w);
+                cp_async_4(Rs + c * Wp + w, Rrow + (size_t)c * plane + w);
+            }
         }
     }
     cp_async_commit();
     const size_t m0 = (size_t)row * W;
     compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads);
-    // per-pixel scalars of the row -> shared (o_a: out/var, o_b: disp, o_ssim, o_max)
-    for (int w = tid; w < W; w += kThreads) {
-        s.o_a[w] = outv[m0 + w];
-        s.o_b[w] = VARMODE ? disp[m0 + w] : 0.f;
-        s.o_ssim[w] = sum_sim[m0 + w];
-        s.o_max[w] = max_cost[m0 + w];
-    }
     cp_async_wait_all();
     __syncthreads();
+    // per-pixel scalars of the row come straight from global memory
+    const float *o_a = outv + m0, *o_b = VARMODE ? disp + m0 : outv + m0;
+    const float *o_ssim = sum_sim + m0, *o_max = max_cost + m0;
     const int nL = s.counts[0], nR = s.counts[1];
 
     // ---- left gradient (and SpaVar's disparity gradient): warp per masked left pixel.
@@ -189,11 +214,11 @@ sparse_row_backward_kernel(const float *__restrict__ L, const float *__restrict_
     for (int i = warp; i < nL; i += nWarps) {
         const int w = (int)(s.llist[i] & 0xffffu);
         const int lo = row_prefix(s, max(0, w - D + 1)), hi = row_prefix(s, w + 1);
-        const float mx = s.o_max[w], ov = s.o_a[w], mu = s.o_b[w];
-        const float gw = gout[m0 + w], ss = s.o_ssim[w];
+        const float mx = o_max[w], ov = o_a[w], mu = o_b[w];
+        const float gw = gout[m0 + w], ss = o_ssim[w];
         auto weight = [&](int col, float &dpart) -> float {
             float cost = 0.f;
-            for (int cc = 0; cc < C; ++cc) cost = fmaf(s.Ls[cc * Wp + w], s.Rs[cc * Wp + col], cost);
+            for (int cc = 0; cc < C; ++cc) cost = fmaf(Ls[cc * Wp + w], Rs[cc * Wp + col], cost);
             const float e = expf(cost - mx);
             const float df = (float)(w - col);
             if (VARMODE) { const float dd = df - mu; dpart = e * dd; return e * (dd * dd - ov); }
@@ -217,10 +242,10 @@ sparse_row_backward_kernel(const float *__restrict__ L, const float *__restrict_
         for (int c = 0; c < C; ++c) {
             float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < KB; ++k) acc += p[k] * s.Rs[c * Wp + ro[k]];
+            for (int k = 0; k < KB; ++k) acc += p[k] * Rs[c * Wp + ro[k]];
             for (int j = hi - 1 - (KB * 32 + lane); j >= lo; j -= 32) {
                 const int col = (int)(s.rlist[j] & 0xffffu);
-                float dp; acc += weight(col, dp) * s.Rs[c * Wp + col];
+                float dp; acc += weight(col, dp) * Rs[c * Wp + col];
             }
             acc = group_sum(acc, 32);
             if (lane == 0) dL[f0 + (size_t)c * plane + w] = gw * acc / ss;
@@ -237,13 +262,13 @@ sparse_row_backward_kernel(const float *__restrict__ L, const float *__restrict_
         const int lo = left_prefix(s, w), hi = left_prefix(s, min(W, w + D));
         auto weight = [&](int wl) -> float {
             float cost = 0.f;
-            for (int cc = 0; cc < C; ++cc) cost = fmaf(s.Ls[cc * Wp + wl], s.Rs[cc * Wp + w], cost);
-            const float e = expf(cost - s.o_max[wl]);
+            for (int cc = 0; cc < C; ++cc) cost = fmaf(Ls[cc * Wp + wl], Rs[cc * Wp + w], cost);
+            const float e = expf(cost - o_max[wl]);
             const float df = (float)(wl - w);
             float q;
-            if (VARMODE) { const float dd = df - s.o_b[wl]; q = dd * dd - s.o_a[wl]; }
-            else q = df - s.o_a[wl];
-            return gout[m0 + wl] * e * q / s.o_ssim[wl];
+            if (VARMODE) { const float dd = df - o_b[wl]; q = dd * dd - o_a[wl]; }
+            else q = df - o_a[wl];
+            return gout[m0 + wl] * e * q / o_ssim[wl];
         };
         float p[KB]; int ro[KB];
 #pragma unroll
@@ -255,10 +280,10 @@ sparse_row_backward_kernel(const float *__restrict__ L, const float *__restrict_
         for (int c = 0; c < C; ++c) {
             float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < KB; ++k) acc += p[k] * s.Ls[c * Wp + ro[k]];
+            for (int k = 0; k < KB; ++k) acc += p[k] * Ls[c * Wp + ro[k]];
             for (int j = lo + KB * 32 + lane; j < hi; j += 32) {
                 const int wl = (int)(s.llist[j] & 0xffffu);
-                acc += weight(wl) * s.Ls[c * Wp + wl];
+                acc += weight(wl) * Ls[c * Wp + wl];
             }
             acc = group_sum(acc, 32);
             if (lane == 0) dR[f0 + (size_t)c * plane + w] = acc;
@@ -284,26 +309,56 @@ static int validate_common(const void *L, const void *R, const void *ml, const v
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int tma_forward(int mode, const float *L, const float *R, const float *ml, const float *mr,
-                const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
-                int B, int C, int H, int W, int D, cudaStream_t st, bool *handled);
+struct TileGeom { int use_tma, bw, nchunks, chunk_stride; size_t smem; };
 
-template <int MODE>
-static int launch_cpasync(const float *L, const float *R, const float *ml, const float *mr,
+// TMA needs 16-B aligned rows (W % 4 == 0, aligned bases), box dims <= 256 and tile offsets
+// that fit the 16-bit field of the packed column lists.
+static TileGeom plan_tiles(const float *L, const float *R, int C, int W, bool allow_tma)
+{
+    TileGeom g{};
+    const size_t Wp = (size_t)((W + 3) & ~3);
+    bool tma_ok = allow_tma && (W % 4 == 0) && aligned16(L) && aligned16(R) && C <= 256;
+    if (tma_ok) {
+        g.nchunks = (W + 255) / 256;
+        g.bw = ((W + g.nchunks - 1) / g.nchunks + 3) & ~3;
+        g.chunk_stride = (int)(round_up((size_t)C * g.bw * 4, 128) / 4);
+        if ((size_t)g.nchunks * g.chunk_stride > 65535) tma_ok = false;
+    }
+    if (tma_ok) {
+        g.use_tma = 1;
+        g.smem = 2 * (size_t)g.nchunks * g.chunk_stride * 4 + list_smem_bytes(W) + 128;
+    } else {
+        g.use_tma = 0; g.bw = 0; g.nchunks = 0; g.chunk_stride = 0;
+        g.smem = 2 * (size_t)C * Wp * 4 + list_smem_bytes(W) + 128;
+    }
+    return g;
+}
+
+template <int MODE, bool USE_TMA>
+static int launch_forward(const TileGeom &g, const float *L, const float *R, const float *ml, const float *mr,
                           const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
                           int B, int C, int H, int W, int D, cudaStream_t st)
 {
-    const size_t smem = row_smem_bytes(C, W);
-    if (smem > kMaxSmem) {
-        set_error("row slab needs %zu B of shared memory (> %d): C*W=%d too large", smem, (int)kMaxSmem, C * W);
-        return DECNET_ERR_UNSUPPORTED;
+    CUtensorMap tmL, tmR;
+    memset(&tmL, 0, sizeof(tmL)); memset(&tmR, 0, sizeof(tmR));
+    if (USE_TMA) {
+        const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
+        const uint64_t strides[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+        const uint32_t box[3] = {(uint32_t)g.bw, 1u, (uint32_t)C};
+        int rc = encode_tensor_map(&tmL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, L, dims, strides, box,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        rc = encode_tensor_map(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, R, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
     }
-    auto kern = sparse_row_cpasync_kernel<MODE>;
-    DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = sparse_row_kernel<MODE, USE_TMA>;
+    DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int vec_ok = (W % 4 == 0) && aligned16(L) && aligned16(R) && aligned16(out_a) && aligned16(ssim) &&
                        aligned16(mx) && (MODE != MODE_FUSED || aligned16(out_b));
-    kern<<<B * H, kThreads, smem, st>>>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, C, H, W, D, vec_ok);
-    return after_launch("sparse_row_cpasync_kernel");
+    kern<<<B * H, kThreads, g.smem, st>>>(tmL, tmR, L, R, ml, mr, disp, out_a, out_b, ssim, mx, C, H, W, D,
+                                          vec_ok, g.bw, g.nchunks, g.chunk_stride);
+    return after_launch("sparse_row_kernel");
 }
 
 static int forward_dispatch(int mode, const float *L, const float *R, const float *ml, const float *mr,
@@ -317,21 +372,25 @@ static int forward_dispatch(int mode, const float *L, const float *R, const floa
     DECNET_REQUIRE(mode != MODE_FUSED || out_b, "null variance output pointer");
     if (D < 0) D = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (g_forced_path != 1) {
-        bool handled = false;
-        int rc = tma_forward(mode, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st, &handled);
-        if (handled) { g_last_path = 2; return rc; }
-        if (g_forced_path == 2) {
-            set_error("TMA path forced but shape/alignment not eligible (W=%d)", W);
-            return DECNET_ERR_UNSUPPORTED;
-        }
+    TileGeom g = plan_tiles(L, R, C, W, g_forced_path != 1);
+    if (g_forced_path == 2 && !g.use_tma) {
+        set_error("TMA path forced but shape/alignment not eligible (W=%d)", W);
+        return DECNET_ERR_UNSUPPORTED;
     }
-    g_last_path = 1;
+    if (g.smem > kMaxSmem) {
+        set_error("row slab needs %zu B of shared memory (> %d): C*W=%d too large", g.smem, (int)kMaxSmem, C * W);
+        return DECNET_ERR_UNSUPPORTED;
+    }
+    g_last_path = g.use_tma ? 2 : 1;
+#define DECNET_FWD(M)                                                                                         \
+    (g.use_tma ? launch_forward<M, true>(g, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st)     \
+               : launch_forward<M, false>(g, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st))
     switch (mode) {
-        case MODE_MAT: return launch_cpasync<MODE_MAT>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st);
-        case MODE_VAR: return launch_cpasync<MODE_VAR>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st);
-        default:       return launch_cpasync<MODE_FUSED>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st);
+        case MODE_MAT: return DECNET_FWD(MODE_MAT);
+        case MODE_VAR: return DECNET_FWD(MODE_VAR);
+        default:       return DECNET_FWD(MODE_FUSED);
     }
+#undef DECNET_FWD
 }
 
 template <int VARMODE>
@@ -345,7 +404,7 @@ static int backward_dispatch(const float *L, const float *R, const float *ml, co
     DECNET_REQUIRE(outv && ssim && mx && g && dL && dR, "null pointer in backward");
     DECNET_REQUIRE(!VARMODE || (disp && ddisp), "null disparity pointer in backward");
     if (D < 0) D = 0;
-    const size_t smem = row_smem_bytes(C, W);
+    const size_t smem = 2 * (size_t)C * ((W + 3) & ~3) * 4 + list_smem_bytes(W);
     if (smem > kMaxSmem) {
         set_error("row slab needs %zu B of shared memory (> %d)", smem, (int)kMaxSmem);
         return DECNET_ERR_UNSUPPORTED;
@@ -398,7 +457,7 @@ int decnet_candidate_signature(const float *ml, const float *mr, int32_t *count,
     DECNET_REQUIRE(ml && mr && count && hash, "null pointer");
     DECNET_REQUIRE(B > 0 && H > 0 && W > 0 && W <= 65535, "bad size B=%d H=%d W=%d", B, H, W);
     if (D < 0) D = 0;
-    const size_t smem = row_smem_bytes(0, W);
+    const size_t smem = list_smem_bytes(W);
     DECNET_CUDA(cudaFuncSetAttribute(candidate_signature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     candidate_signature_kernel<<<B * H, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         ml, mr, count, reinterpret_cast<unsigned long long *>(hash), W, D);

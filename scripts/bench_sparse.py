@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--rhos", type=float, nargs="+", default=[0.01, 0.03, 0.1, 0.3])
     ap.add_argument("--ref", type=int, default=1)
     ap.add_argument("--paths", type=int, nargs="+", default=[1, 2])
+    ap.add_argument("--levels", nargs="+", default=["s1", "s2", "s3"])
     args = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = peaks.get("hbm_gbs", 6650.0)
@@ -49,6 +50,8 @@ def main():
     levels = [("s1", 72, 60, 108, 24), ("s2", 24, 180, 324, 72), ("s3", 8, 540, 972, 216)]
     rows = []
     for name, C, H, W, D in levels:
+        if name not in args.levels:
+            continue
         L, R = make_feats(args.B, C, H, W, device="cuda")
         for rho in args.rhos:
             ml, mr = make_masks(args.B, H, W, rho, rho, device="cuda")
