@@ -59,14 +59,53 @@ __device__ __forceinline__ int left_prefix(const RowSmem &s, int x) {
 //   tile_bw  > 0 : TMA box layout [chunk][C][bw]  -> (w / bw) * chunk_stride + w % bw
 // Mask test is `!= 0` on fp32 exactly as the reference's `== 0` early-outs
 // (SM_kernel.cu:33,49): -0.0 is unmasked, NaN is masked.
+// Lanes per masked pixel.  Tiny cost model (warp instructions for the row) evaluated for
+// G = 1..32: waves(G) * (chunks(G) * per_chunk + per_pixel + per_shuffle_step * log2 G).
+__device__ __forceinline__ int pick_group_log2(int nL, int nR, int W, int D, int C, int nthreads) {
+    const float avg = (float)nR * (float)min(D, W) / (float)W;
+    const float hi = avg + 2.f * sqrtf(avg) + 1.f;        // ~max candidates over the lanes of a warp
+    const float per_chunk = (float)(KU * (2 * C + 28));
+    int best = 0; float best_cost = 3.0e38f;
+#pragma unroll
+    for (int lg = 0; lg <= 5; ++lg) {
+        const int G = 1 << lg;
+        const float waves = ceilf((float)nL * (float)G / (float)nthreads);
+        const float chunks = ceilf(hi / (float)(KU * G));
+        const float cost = waves * (chunks * per_chunk + 160.f + 45.f * (float)lg);
+        if (cost < best_cost) { best_cost = cost; best = lg; }
+    }
+    return best;
+}
+
+// (see compact_row_masks doc above)
 __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ lmask_row,
                                          const float *__restrict__ rmask_row,
                                          int W, int tid, int nthreads,
-                                         int tile_bw = 0, int chunk_stride = 0)
+                                         int tile_bw = 0, int chunk_stride = 0, uint32_t bw_magic = 0,
+                                         int D = 0, int C = 0)
 {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int nch = (W + 31) >> 5;
-    for (int k = warp; k < nch; k += nwarps) {
+    // all mask loads of this thread are issued before the first ballot (one memory round trip)
+    constexpr int PRE = 4;
+    float lm[PRE], rm[PRE];
+#pragma unroll
+    for (int it = 0; it < PRE; ++it) {
+        const int w = ((warp + it * nwarps) << 5) + lane;
+        const bool in = w < W;
+        lm[it] = in ? __ldg(lmask_row + w) : 0.f;
+        rm[it] = in ? __ldg(rmask_row + w) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < PRE; ++it) {
+        const int k = warp + it * nwarps;
+        if (k < nch) {
+            const uint32_t lb = __ballot_sync(0xffffffffu, lm[it] != 0.f);
+            const uint32_t rb = __ballot_sync(0xffffffffu, rm[it] != 0.f);
+            if (lane == 0) { s.lbits[k] = lb; s.rbits[k] = rb; }
+        }
+    }
+    for (int k = warp + PRE * nwarps; k < nch; k += nwarps) {
         const int w = (k << 5) + lane;
         const bool lv = (w < W) && (__ldg(lmask_row + w) != 0.f);
         const bool rv = (w < W) && (__ldg(rmask_row + w) != 0.f);
@@ -93,7 +132,10 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ l
             carryL += __shfl_sync(0xffffffffu, il, 31);
             carryR += __shfl_sync(0xffffffffu, ir, 31);
         }
-        if (lane == 0) { s.loff[nch] = carryL; s.roff[nch] = carryR; s.counts[0] = carryL; s.counts[1] = carryR; }
+        if (lane == 0) {
+            s.loff[nch] = carryL; s.roff[nch] = carryR; s.counts[0] = carryL; s.counts[1] = carryR;
+            s.counts[2] = pick_group_log2(carryL, carryR, W, D, C, nthreads);
+        }
     }
     __syncthreads();
     for (int k = warp; k < nch; k += nwarps) {
@@ -101,30 +143,15 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ l
         const uint32_t lb = s.lbits[k], rb = s.rbits[k];
         const uint32_t below = (1u << lane) - 1u;
         uint32_t off = (uint32_t)w;
-        if (tile_bw > 0) { const int ch = w / tile_bw; off = (uint32_t)(ch * chunk_stride + (w - ch * tile_bw)); }
+        if (tile_bw > 0) {
+            const int ch = (int)__umulhi((uint32_t)w, bw_magic);     // w / tile_bw (exact for w < 2^16)
+            off = (uint32_t)(ch * chunk_stride + (w - ch * tile_bw));
+        }
         const uint32_t packed = (off << 16) | (uint32_t)w;
         if ((lb >> lane) & 1u) s.llist[s.loff[k] + __popc(lb & below)] = packed;
         if ((rb >> lane) & 1u) s.rlist[s.roff[k] + __popc(rb & below)] = packed;
     }
     __syncthreads();
-}
-
-// Lanes per masked pixel.  Tiny cost model (warp instructions for the row) evaluated for
-// G = 1..32: waves(G) * (chunks(G) * per_chunk + per_pixel + per_shuffle_step * log2 G).
-__device__ __forceinline__ int pick_group_log2(int nL, int nR, int W, int D, int C, int nthreads) {
-    const float avg = (float)nR * (float)min(D, W) / (float)W;
-    const float hi = avg + 2.f * sqrtf(avg) + 1.f;        // ~max candidates over the lanes of a warp
-    const float per_chunk = (float)(KU * (2 * C + 28));
-    int best = 0; float best_cost = 3.0e38f;
-#pragma unroll
-    for (int lg = 0; lg <= 5; ++lg) {
-        const int G = 1 << lg;
-        const float waves = ceilf((float)nL * (float)G / (float)nthreads);
-        const float chunks = ceilf(hi / (float)(KU * G));
-        const float cost = waves * (chunks * per_chunk + 160.f + 45.f * (float)lg);
-        if (cost < best_cost) { best_cost = cost; best = lg; }
-    }
-    return best;
 }
 
 template <int G> __device__ __forceinline__ float gmax(float v) {
@@ -142,17 +169,21 @@ template <int G> __device__ __forceinline__ double gsum(double v) {
 // (the rows were zero-filled earlier by the same CTA, ordered by a __syncthreads()).
 //
 // Single pass per candidate ("online softmax"): running maximum m (starts at the 1e-6
-// floor of SM_kernel.cu:45), sums rescaled by exp(m_old - m_new) when m grows.  The three
-// moments S0 = sum e, S1 = sum e*d, S2 = sum e*d^2 are kept in fp64 so that
+// floor of SM_kernel.cu:45), sums rescaled by exp(m_old - m_new) when m grows (once per
+// chunk of KU candidates).  The three moments S0 = sum e, S1 = sum e*d, S2 = sum e*d^2 are
+// kept in fp64 so that
 //     var = (1e-6 + S2 - 2*mu*S1 + mu^2*S0) / (1e-6 + S0)
 // (identical to sum e*(d-mu)^2 around the FINAL mean) has no fp32 cancellation.
-//   Ls/Rs : staged slabs, element (c, col) at  c*cs + offset(col)
+//   Ls     : staged left slab, element (c, col) at c*cs + offset(col)
+//   RC     : true  -> Rc holds the VALID right columns transposed to [j][Cp] (j = index in
+//                     the compacted list), read with 128-bit loads;
+//            false -> Rs is the staged right slab addressed like Ls.
 //   MODE_MAT   g_a = out
 //   MODE_VAR   g_a = var around disp_row[w]
 //   MODE_FUSED g_a = out, g_b = var around out
-template <int MODE, int G>
+template <int MODE, int G, bool RC>
 __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__restrict__ Ls,
-                                              const float *__restrict__ Rs, int cs, int C, int D,
+                                              const float *__restrict__ Rs, int cs, int C, int Cp, int D,
                                               const float *__restrict__ disp_row,
                                               float *__restrict__ g_a, float *__restrict__ g_b,
                                               float *__restrict__ g_ssim, float *__restrict__ g_max,
@@ -162,6 +193,7 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
     const int t = tid & (G - 1);
     const int gid = tid >> LG, nG = nthreads >> LG;
     const int nL = s.counts[0];
+    const int C4 = C >> 2;
 
     for (int i0 = 0; i0 < nL; i0 += nG) {
         const int i = i0 + gid;
@@ -183,27 +215,52 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
                 const int j = jb + k * G;
-                const uint32_t e = (j < hi) ? s.rlist[j] : 0u;
-                ro[k] = (int)(e >> 16);
+                const bool ok = j < hi;
+                const uint32_t e = ok ? s.rlist[j] : 0u;
+                ro[k] = RC ? (ok ? j * Cp : 0) : (int)(e >> 16);
                 dk[k] = w - (int)(e & 0xffffu);
                 cost[k] = 0.f;
             }
             // the reference's sequential FMA chain over channels, KU independent chains
-#pragma unroll 4
-            for (int c = 0; c < C; ++c) {
-                const float l = lp[c * cs];
-                const float *rp = Rs + c * cs;
+            if (RC) {
+                for (int c4 = 0; c4 < C4; ++c4) {
+                    const float l0 = lp[(4 * c4 + 0) * cs], l1 = lp[(4 * c4 + 1) * cs];
+                    const float l2 = lp[(4 * c4 + 2) * cs], l3 = lp[(4 * c4 + 3) * cs];
 #pragma unroll
-                for (int k = 0; k < KU; ++k) cost[k] = fmaf(l, rp[ro[k]], cost[k]);
+                    for (int k = 0; k < KU; ++k) {
+                        const float4 r = *reinterpret_cast<const float4 *>(Rs + ro[k] + 4 * c4);
+                        cost[k] = fmaf(l0, r.x, cost[k]);
+                        cost[k] = fmaf(l1, r.y, cost[k]);
+                        cost[k] = fmaf(l2, r.z, cost[k]);
+                        cost[k] = fmaf(l3, r.w, cost[k]);
+                    }
+                }
+                for (int c = 4 * C4; c < C; ++c) {
+                    const float l = lp[c * cs];
+#pragma unroll
+                    for (int k = 0; k < KU; ++k) cost[k] = fmaf(l, Rs[ro[k] + c], cost[k]);
+                }
+            } else {
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) {
+                    const float l = lp[c * cs];
+                    const float *rp = Rs + c * cs;
+#pragma unroll
+                    for (int k = 0; k < KU; ++k) cost[k] = fmaf(l, rp[ro[k]], cost[k]);
+                }
+            }
+            // one rescale per chunk, then one exp per candidate
+            float mk = m;
+#pragma unroll
+            for (int k = 0; k < KU; ++k) if (jb + k * G < hi) mk = fmaxf(mk, cost[k]);
+            if (mk > m) {
+                const double sc = (double)expf(m - mk);
+                S0 *= sc; S1 *= sc; if (MODE != MODE_MAT) S2 *= sc;
+                m = mk;
             }
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
                 if (jb + k * G < hi) {
-                    if (cost[k] > m) {
-                        const double sc = (double)expf(m - cost[k]);
-                        S0 *= sc; S1 *= sc; if (MODE != MODE_MAT) S2 *= sc;
-                        m = cost[k];
-                    }
                     const double e = (double)expf(cost[k] - m);
                     const double dd = (double)dk[k];
                     S0 += e;
@@ -241,30 +298,58 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
     }
 }
 
-template <int MODE>
-__device__ inline void process_row(const RowSmem &s, const float *Ls, const float *Rs, int cs, int C,
-                                   int W, int D, const float *disp_row, float *g_a, float *g_b,
+template <int MODE, bool RC>
+__device__ inline void process_row(const RowSmem &s, const float *Ls, const float *Rs, int cs, int C, int Cp,
+                                   int D, const float *disp_row, float *g_a, float *g_b,
                                    float *g_ssim, float *g_max, int tid, int nthreads)
 {
-    const int lg = pick_group_log2(s.counts[0], s.counts[1], W, D, C, nthreads);
-    switch (lg) {
-        case 0: process_row_g<MODE, 1>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
-        case 1: process_row_g<MODE, 2>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
-        case 2: process_row_g<MODE, 4>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
-        case 3: process_row_g<MODE, 8>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
-        case 4: process_row_g<MODE, 16>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
-        default: process_row_g<MODE, 32>(s, Ls, Rs, cs, C, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads); break;
+#define DECNET_PR(GG) process_row_g<MODE, GG, RC>(s, Ls, Rs, cs, C, Cp, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads)
+    switch (s.counts[2]) {
+        case 0: DECNET_PR(1); break;
+        case 1: DECNET_PR(2); break;
+        case 2: DECNET_PR(4); break;
+        case 3: DECNET_PR(8); break;
+        case 4: DECNET_PR(16); break;
+        default: DECNET_PR(32); break;
+    }
+#undef DECNET_PR
+}
+
+// Transpose the VALID right columns of the staged slab into Rc[j][Cp] (j = list index).
+__device__ inline void gather_right_columns(const RowSmem &s, const float *__restrict__ Rs, int cs, int C, int Cp,
+                                            float *__restrict__ Rc, int tid, int nthreads)
+{
+    const int nR = s.counts[1];
+    const int q4 = Cp >> 2;
+    const uint32_t magic = 0xffffffffu / (uint32_t)q4 + 1u;      // idx / q4, exact for idx < 2^16 * q4
+    const int total = nR * q4;
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const int j = (q4 == 1) ? idx : (int)__umulhi((uint32_t)idx, magic);
+        const int q = idx - j * q4;
+        const int off = (int)(s.rlist[j] >> 16);
+        const int c = 4 * q;
+        float4 v;
+        v.x = Rs[(c + 0) * cs + off];
+        v.y = (c + 1 < C) ? Rs[(c + 1) * cs + off] : 0.f;
+        v.z = (c + 2 < C) ? Rs[(c + 2) * cs + off] : 0.f;
+        v.w = (c + 3 < C) ? Rs[(c + 3) * cs + off] : 0.f;
+        *reinterpret_cast<float4 *>(Rc + j * Cp + c) = v;
     }
 }
 
-// coalesced zero fill of one output row
-__device__ __forceinline__ void zero_row(float *__restrict__ dst, int W, int vec_ok, int tid, int nthreads) {
+// coalesced zero fill of the output rows of one image row (n rows of W floats)
+__device__ __forceinline__ void zero_rows(float *__restrict__ r0, float *__restrict__ r1, float *__restrict__ r2,
+                                          float *__restrict__ r3, int W, int vec_ok, int tid, int nthreads) {
     if (vec_ok) {
-        float4 *d4 = reinterpret_cast<float4 *>(dst);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = tid; i < (W >> 2); i += nthreads) d4[i] = z;
+        for (int i = tid; i < (W >> 2); i += nthreads) {
+            reinterpret_cast<float4 *>(r0)[i] = z;
+            reinterpret_cast<float4 *>(r1)[i] = z;
+            reinterpret_cast<float4 *>(r2)[i] = z;
+            if (r3) reinterpret_cast<float4 *>(r3)[i] = z;
+        }
     } else {
-        for (int i = tid; i < W; i += nthreads) dst[i] = 0.f;
+        for (int i = tid; i < W; i += nthreads) { r0[i] = 0.f; r1[i] = 0.f; r2[i] = 0.f; if (r3) r3[i] = 0.f; }
     }
 }
 

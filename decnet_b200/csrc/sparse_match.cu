@@ -49,21 +49,23 @@ sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
                   float *__restrict__ out_a,   // MAT: out   VAR: var   FUSED: out
                   float *__restrict__ out_b,   // FUSED: var, else unused
                   float *__restrict__ sum_sim, float *__restrict__ max_cost,
-                  int C, int H, int W, int D, int vec_ok, int bw, int nchunks, int chunk_stride)
+                  int C, int H, int W, int D, int vec_ok, int bw, int nchunks, int chunk_stride,
+                  uint32_t bw_magic, int rc_cap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     const int tid = threadIdx.x;
-    const int row = blockIdx.x;
-    const int b = row / H, h = row - b * H;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int row = b * H + h;
     const int Wp = (W + 3) & ~3;
+    const int Cp = (C + 3) & ~3;
     unsigned char *base = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const int tile_floats = USE_TMA ? nchunks * chunk_stride : C * Wp;
     float *Ls = reinterpret_cast<float *>(base);
     float *Rs = Ls + tile_floats;
     RowSmem s;
-    carve_lists(s, reinterpret_cast<unsigned char *>(Rs + tile_floats), W);
+    float *Rc = reinterpret_cast<float *>(carve_lists(s, reinterpret_cast<unsigned char *>(Rs + tile_floats), W));
 
     // 1. put the whole [C,W] slabs of both views in flight
     if (USE_TMA) {
@@ -101,21 +103,31 @@ sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
         cp_async_commit();
     }
 
-    // 2. while they fly: zero the output rows in global memory, compact both masks
+    // 2. while they fly: compact both masks (mask loads first), zero the output rows
     const size_t m0 = (size_t)row * W;
-    zero_row(out_a + m0, W, vec_ok, tid, kThreads);
-    if (MODE == MODE_FUSED) zero_row(out_b + m0, W, vec_ok, tid, kThreads);
-    zero_row(sum_sim + m0, W, vec_ok, tid, kThreads);
-    zero_row(max_cost + m0, W, vec_ok, tid, kThreads);
-    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads, USE_TMA ? bw : 0, chunk_stride);
-    if (s.counts[0] == 0) return;          // no masked pixel in this row: zeros are the answer
-    if (USE_TMA) mbar_wait(&mbar, 0);
+    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads, USE_TMA ? bw : 0, chunk_stride, bw_magic, D, C);
+    zero_rows(out_a + m0, sum_sim + m0, max_cost + m0, MODE == MODE_FUSED ? out_b + m0 : nullptr,
+              W, vec_ok, tid, kThreads);
+    // The slabs must have landed before this CTA may retire (its shared memory is recycled),
+    // even when the row has no masked pixel and the zeros are already the answer.
+    if (USE_TMA) { if (tid == 0) mbar_wait(&mbar, 0); }
     else cp_async_wait_all();
     __syncthreads();   // slabs visible to all; also orders the zero fill before the result stores
+    const int nL = s.counts[0], nR = s.counts[1];
+    if (nL == 0) return;
 
     // 3. costs / softmax regression / variance for every masked pixel, stored straight to global
-    process_row<MODE>(s, Ls, Rs, USE_TMA ? bw : Wp, C, W, D, MODE == MODE_VAR ? disp_in + m0 : nullptr,
-                      out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+    const int cs = USE_TMA ? bw : Wp;
+    const float *disp_row = MODE == MODE_VAR ? disp_in + m0 : nullptr;
+    if (nR * Cp <= rc_cap) {
+        gather_right_columns(s, Rs, cs, C, Cp, Rc, tid, kThreads);
+        __syncthreads();
+        process_row<MODE, true>(s, Ls, Rc, cs, C, Cp, D, disp_row,
+                                out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+    } else {
+        process_row<MODE, false>(s, Ls, Rs, cs, C, Cp, D, disp_row,
+                                 out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+    }
 }
 
 // -------------------------------------------------------------------------------------
@@ -302,35 +314,50 @@ static int validate_common(const void *L, const void *R, const void *ml, const v
 {
     DECNET_REQUIRE(L && R && ml && mr, "null input pointer");
     DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size B=%d C=%d H=%d W=%d", B, C, H, W);
-    DECNET_REQUIRE((long long)B * H < (1ll << 31), "B*H too large");
+    DECNET_REQUIRE((long long)B * H < (1ll << 31) && B <= 65535, "B*H too large");
     if (W > 65535) { set_error("W=%d exceeds 65535 columns", W); return DECNET_ERR_UNSUPPORTED; }
     return 0;
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-struct TileGeom { int use_tma, bw, nchunks, chunk_stride; size_t smem; };
+struct TileGeom { int use_tma, bw, nchunks, chunk_stride, rc_cap; uint32_t bw_magic; size_t smem; };
 
 // TMA needs 16-B aligned rows (W % 4 == 0, aligned bases), box dims <= 256 and tile offsets
-// that fit the 16-bit field of the packed column lists.
+// that fit the 16-bit field of the packed column lists.  The leftover shared memory of the
+// chosen occupancy tier (3, 2 or 1 CTAs per SM) becomes the compacted right-column buffer.
 static TileGeom plan_tiles(const float *L, const float *R, int C, int W, bool allow_tma)
 {
     TileGeom g{};
     const size_t Wp = (size_t)((W + 3) & ~3);
+    const size_t Cp = (size_t)((C + 3) & ~3);
     bool tma_ok = allow_tma && (W % 4 == 0) && aligned16(L) && aligned16(R) && C <= 256;
     if (tma_ok) {
         g.nchunks = (W + 255) / 256;
         g.bw = ((W + g.nchunks - 1) / g.nchunks + 3) & ~3;
         g.chunk_stride = (int)(round_up((size_t)C * g.bw * 4, 128) / 4);
+        g.bw_magic = 0xffffffffu / (uint32_t)g.bw + 1u;
         if ((size_t)g.nchunks * g.chunk_stride > 65535) tma_ok = false;
     }
+    size_t fixed;
     if (tma_ok) {
         g.use_tma = 1;
-        g.smem = 2 * (size_t)g.nchunks * g.chunk_stride * 4 + list_smem_bytes(W) + 128;
+        fixed = 2 * (size_t)g.nchunks * g.chunk_stride * 4 + list_smem_bytes(W) + 128;
     } else {
-        g.use_tma = 0; g.bw = 0; g.nchunks = 0; g.chunk_stride = 0;
-        g.smem = 2 * (size_t)C * Wp * 4 + list_smem_bytes(W) + 128;
+        g.use_tma = 0; g.bw = 0; g.nchunks = 0; g.chunk_stride = 0; g.bw_magic = 0;
+        fixed = 2 * (size_t)C * Wp * 4 + list_smem_bytes(W) + 128;
     }
+    const size_t want = Wp * Cp * 4;                      // every right column valid
+    size_t budget = kMaxSmem;
+    for (int n = 3; n >= 1; --n) {
+        const size_t b = (size_t)(228 * 1024) / n - 1024 - 64;   // per-CTA share minus the reserved KB
+        if (fixed + 2048 <= b || n == 1) { budget = b < kMaxSmem ? b : kMaxSmem; break; }
+    }
+    size_t rc = budget > fixed ? budget - fixed : 0;
+    if (rc > want) rc = want;
+    rc &= ~(size_t)15;
+    g.rc_cap = (int)(rc / 4);
+    g.smem = fixed + rc;
     return g;
 }
 
@@ -356,8 +383,8 @@ static int launch_forward(const TileGeom &g, const float *L, const float *R, con
     DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int vec_ok = (W % 4 == 0) && aligned16(L) && aligned16(R) && aligned16(out_a) && aligned16(ssim) &&
                        aligned16(mx) && (MODE != MODE_FUSED || aligned16(out_b));
-    kern<<<B * H, kThreads, g.smem, st>>>(tmL, tmR, L, R, ml, mr, disp, out_a, out_b, ssim, mx, C, H, W, D,
-                                          vec_ok, g.bw, g.nchunks, g.chunk_stride);
+    kern<<<dim3(H, B), kThreads, g.smem, st>>>(tmL, tmR, L, R, ml, mr, disp, out_a, out_b, ssim, mx, C, H, W, D,
+                                               vec_ok, g.bw, g.nchunks, g.chunk_stride, g.bw_magic, g.rc_cap);
     return after_launch("sparse_row_kernel");
 }
 
