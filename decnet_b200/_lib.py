@@ -27,6 +27,16 @@ SIGNATURES = {
     "decnet_spamat_bwd": (_i, [_f32p] * 10 + [_i] * 5 + [C.c_void_p]),
     "decnet_spavar_bwd": (_i, [_f32p] * 12 + [_i] * 5 + [C.c_void_p]),
     "decnet_candidate_signature": (_i, [_f32p] * 4 + [_i] * 4 + [C.c_void_p]),
+    "decnet_costvol_fwd": (_i, [_f32p] * 3 + [_i] * 5 + [C.c_void_p]),
+    "decnet_costvol_bf16_ndhwc": (_i, [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
+    "decnet_softargmin": (_i, [_f32p] * 2 + [_i] * 4 + [C.c_void_p]),
+    "decnet_mask_threshold": (_i, [_f32p] * 2 + [C.c_float] + [_f32p] * 4 + [_i] * 3 + [C.c_void_p]),
+    "decnet_dynup_pack": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
+    "decnet_dynup_glue": (_i, [_f32p] * 3 + [_i] * 3 + [C.c_void_p]),
+    "decnet_attn_pack": (_i, [_f32p] * 6 + [_i] * 4 + [C.c_void_p]),
+    "decnet_blend": (_i, [_f32p] * 5 + [_i] * 3 + [C.c_void_p]),
+    "decnet_warp_bilinear": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
+    "decnet_refine_pack": (_i, [_f32p] * 4 + [_i] * 4 + [C.c_void_p]),
     "decnet_last_sparse_path": (_i, []),
     "decnet_set_sparse_path": (None, [_i]),
 }

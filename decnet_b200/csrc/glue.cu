@@ -1,0 +1,418 @@
+// decnet_b200/csrc/glue.cu -- the HBM-bound glue of the decomposed-matching pipeline (sm_100a):
+// cost-volume build, soft-argmin, mask threshold, dynamic-upsampling pack + glue, soft-attention
+// pack, sigmoid+blend, disparity warp (+ refinement input pack).  One pass over each operand,
+// coalesced along W, no temporaries.  Reference sites: SURVEY.md section 8 rows a2, a4, a6, a8,
+// a13, a14 (file:line quoted at each kernel).
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace decnet {
+namespace glue {
+
+constexpr int kBlock = 256;
+
+// The reference normalises pixel coordinates with (size-1)/2 (align_corners=True style,
+// submodule.py:497-499) and then samples with grid_sample's DEFAULT align_corners=False,
+// whose un-normalisation is ((g+1)*size-1)/2.  Same fp32 operation order here.
+__device__ __forceinline__ float sample_coord(float pos_minus_shift, float size) {
+    const float g = pos_minus_shift / ((size - 1.0f) / 2.0f) - 1.0f;
+    return ((g + 1.0f) * size - 1.0f) / 2.0f;
+}
+
+struct Taps {          // 4-tap bilinear with zero padding
+    int x0, y0;
+    float w00, w01, w10, w11;   // (y0,x0) (y0,x1) (y1,x0) (y1,x1); 0 where the tap is outside
+};
+
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W) {
+    Taps t;
+    const float fx = floorf(ix), fy = floorf(iy);
+    t.x0 = (int)fx; t.y0 = (int)fy;
+    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+    const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+    t.w00 = (xin0 && yin0) ? wx0 * wy0 : 0.f;
+    t.w01 = (xin1 && yin0) ? wx1 * wy0 : 0.f;
+    t.w10 = (xin0 && yin1) ? wx0 * wy1 : 0.f;
+    t.w11 = (xin1 && yin1) ? wx1 * wy1 : 0.f;
+    return t;
+}
+
+__device__ __forceinline__ float sample_plane(const float *__restrict__ p, const Taps &t, int H, int W) {
+    // clamped addresses are always valid; weights of outside taps are exactly 0
+    const int x0 = min(max(t.x0, 0), W - 1), x1 = min(max(t.x0 + 1, 0), W - 1);
+    const int y0 = min(max(t.y0, 0), H - 1), y1 = min(max(t.y0 + 1, 0), H - 1);
+    float v = 0.f;
+    v += __ldg(p + (size_t)y0 * W + x0) * t.w00;
+    v += __ldg(p + (size_t)y0 * W + x1) * t.w01;
+    v += __ldg(p + (size_t)y1 * W + x0) * t.w10;
+    v += __ldg(p + (size_t)y1 * W + x1) * t.w11;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2: cost volume (GetCostVolume.forward -> get_warped_feats_by_homgrp -> cost_computation_cor,
+// submodule.py:532-562, 479-510, 518-522) for the stage-0 candidates d = 0..D-1 (:390):
+//   vol[b,c,d,h,w] = (w >= d ? L[b,c,h,w] : 0) * bilinear0(R[b,c], y'(h), x'(w-d))
+// LAYOUT 0: fp32 NCDHW [B,C,D,H,W] (the reference's layout, parity / drop-in)
+// LAYOUT 1: bf16 NDHWC [B,D,H,W,Cpad] (channels-last, zero-padded to Cpad: the tcgen05 conv input)
+// One thread per (b,d,h,w); taps computed once and reused over the channel loop.
+// ---------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(kBlock)
+costvol_kernel(const float *__restrict__ L, const float *__restrict__ R, void *__restrict__ out,
+               int B, int C, int H, int W, int D, int Cpad)
+{
+    const long long n = (long long)B * D * H * W;
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= n) return;
+    const int w = (int)(idx % W);
+    const int h = (int)((idx / W) % H);
+    const int d = (int)((idx / ((long long)W * H)) % D);
+    const int b = (int)(idx / ((long long)W * H * D));
+    const float ix = sample_coord((float)w - (float)d, (float)W);
+    const float iy = sample_coord((float)h, (float)H);
+    const Taps t = make_taps(ix, iy, H, W);
+    const bool left_on = w >= d;
+    const size_t plane = (size_t)H * W;
+    const float *Lb = L + (size_t)b * C * plane + (size_t)h * W + w;
+    const float *Rb = R + (size_t)b * C * plane;
+    if (LAYOUT == 0) {
+        float *o = static_cast<float *>(out) + (((size_t)b * C * D + d) * H + h) * W + w;
+        for (int c = 0; c < C; ++c) {
+            const float r = sample_plane(Rb + (size_t)c * plane, t, H, W);
+            const float l = left_on ? __ldg(Lb + (size_t)c * plane) : 0.f;
+            o[(size_t)c * D * plane] = l * r;
+        }
+    } else {
+        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out) + (size_t)idx * Cpad;
+        for (int c0 = 0; c0 < Cpad; c0 += 8) {
+            __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = c0 + k;
+                float val = 0.f;
+                if (c < C) {
+                    const float r = sample_plane(Rb + (size_t)c * plane, t, H, W);
+                    const float l = left_on ? __ldg(Lb + (size_t)c * plane) : 0.f;
+                    val = l * r;
+                }
+                v[k] = __float2bfloat16(val);
+            }
+            *reinterpret_cast<uint4 *>(o + c0) = *reinterpret_cast<const uint4 *>(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4: soft-argmin (disparity_regression, submodule.py:766-777): pred = sum_d softmax_d(cost) * d
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+softargmin_kernel(const float *__restrict__ cost, float *__restrict__ pred, int B, int D, int HW)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= (long long)B * HW) return;
+    const int b = (int)(idx / HW), p = (int)(idx % HW);
+    const float *c = cost + (size_t)b * D * HW + p;
+    float mx = -INFINITY;
+    for (int d = 0; d < D; ++d) mx = fmaxf(mx, __ldg(c + (size_t)d * HW));
+    float s0 = 0.f, s1 = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float e = expf(__ldg(c + (size_t)d * HW) - mx);
+        s0 += e; s1 += e * (float)d;
+    }
+    pred[idx] = s1 / s0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6: mask selection (SparseDenseNetRefinementMask.py:164-170):
+//   m = p > thold ? 1 : (p <= thold ? 0 : p)      (NaN stays NaN)
+// for the left and right probability maps in one launch; one CTA per row also emits the number
+// of selected pixels of the row for both views (ballot + popc), which the host can use to size
+// work and report densities without another pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+mask_threshold_kernel(const float *__restrict__ pl, const float *__restrict__ pr, float thold,
+                      float *__restrict__ ml, float *__restrict__ mr,
+                      int *__restrict__ row_count_l, int *__restrict__ row_count_r, int W)
+{
+    __shared__ int cnt[2];
+    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t m0 = (size_t)blockIdx.x * W;
+    int nl = 0, nr = 0;
+    for (int w0 = 0; w0 < W; w0 += kBlock) {
+        const int w = w0 + threadIdx.x;
+        bool sl = false, sr = false;
+        if (w < W) {
+            const float a = pl[m0 + w], b = pr[m0 + w];
+            const float va = a > thold ? 1.f : (a <= thold ? 0.f : a);
+            const float vb = b > thold ? 1.f : (b <= thold ? 0.f : b);
+            ml[m0 + w] = va; mr[m0 + w] = vb;
+            sl = va != 0.f; sr = vb != 0.f;
+        }
+        nl += __popc(__ballot_sync(0xffffffffu, sl));
+        nr += __popc(__ballot_sync(0xffffffffu, sr));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt[0], nl); atomicAdd(&cnt[1], nr); }
+    __syncthreads();
+    if (threadIdx.x == 0 && row_count_l) row_count_l[blockIdx.x] = cnt[0];
+    if (threadIdx.x == 1 && row_count_r) row_count_r[blockIdx.x] = cnt[1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8 (input side): DynamicUpsampling's conv input (submodule.py:580):
+//   cat(disp.unsqueeze(1), unfold(Lf, k=3, s=3)) -> [B, 1+9C, h, w]
+//   ch 0 = disp,  ch 1 + c*9 + ky*3 + kx = Lf[b, c, 3y+ky, 3x+kx]
+// One CTA per (b, c, y): the three source rows are read coalesced into shared memory and the nine
+// destination rows written coalesced.  blockIdx.y == C handles the disparity plane.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+dynup_pack_kernel(const float *__restrict__ disp, const float *__restrict__ Lf, float *__restrict__ out,
+                  int C, int h, int w)
+{
+    extern __shared__ float rows[];            // [3][3w]
+    const int y = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+    const int W3 = 3 * w;
+    const size_t oplane = (size_t)h * w;
+    float *ob = out + (size_t)b * (9 * C + 1) * oplane + (size_t)y * w;
+    if (c == C) {
+        for (int x = threadIdx.x; x < w; x += kBlock) ob[x] = disp[((size_t)b * h + y) * w + x];
+        return;
+    }
+    const float *src = Lf + (((size_t)b * C + c) * (3 * h) + 3 * y) * W3;
+    for (int i = threadIdx.x; i < 3 * W3; i += kBlock) rows[i] = src[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * w; i += kBlock) {
+        const int k = i / w, x = i - k * w;
+        const int ky = k / 3, kx = k - ky * 3;
+        ob[(size_t)(1 + c * 9 + k) * oplane + x] = rows[ky * W3 + 3 * x + kx];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8 (output side): softmax over the 9 taps of each of the 9 sub-pixels, 3x3 gather of the
+// replication-padded coarse disparity, weighted sum, pixel-shuffle, x3 (submodule.py:582-589):
+//   out[3y+i, 3x+j] = 3 * sum_k softmax_k(logits[(i*3+j)*9 + k]) * disp[clamp(y+ky-1), clamp(x+kx-1)]
+// One thread per coarse pixel (81 coalesced channel reads, 9 x 3-wide writes).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+dynup_glue_kernel(const float *__restrict__ logits, const float *__restrict__ disp, float *__restrict__ out,
+                  int B, int h, int w)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long n = (long long)B * h * w;
+    if (idx >= n) return;
+    const int x = (int)(idx % w), y = (int)((idx / w) % h), b = (int)(idx / ((long long)w * h));
+    const size_t plane = (size_t)h * w;
+    const float *db = disp + (size_t)b * plane;
+    float nb[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int yy = min(max(y + ky - 1, 0), h - 1), xx = min(max(x + kx - 1, 0), w - 1);
+            nb[ky * 3 + kx] = __ldg(db + (size_t)yy * w + xx);
+        }
+    const float *lg = logits + (size_t)b * 81 * plane + (size_t)y * w + x;
+    float *ob = out + (size_t)b * 9 * plane;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float res[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int sub = i * 3 + j;
+            float v[9], mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { v[k] = __ldg(lg + (size_t)(sub * 9 + k) * plane); mx = fmaxf(mx, v[k]); }
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { const float e = expf(v[k] - mx); s0 += e; s1 += e * nb[k]; }
+            res[j] = (s1 / s0) * 3.0f;
+        }
+        float *o = ob + (size_t)(3 * y + i) * (3 * w) + 3 * x;
+        o[0] = res[0]; o[1] = res[1]; o[2] = res[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a13 (input side): cat(Lf, dense, sparse, lmask, -var) -> [B, C+4, H, W]
+// (SparseDenseNetRefinementMask.py:197).  Flat copy, float4 where aligned.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+attn_pack_kernel(const float *__restrict__ Lf, const float *__restrict__ dense, const float *__restrict__ sparse,
+                 const float *__restrict__ lmask, const float *__restrict__ var, float *__restrict__ out,
+                 int C, long long HW, long long total)
+{
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
+        const long long per = (long long)(C + 4) * HW;
+        const int b = (int)(i / per);
+        const long long r = i - (long long)b * per;
+        const int c = (int)(r / HW);
+        const long long p = r - (long long)c * HW;
+        float v;
+        if (c < C) v = Lf[((long long)b * C + c) * HW + p];
+        else if (c == C) v = dense[(long long)b * HW + p];
+        else if (c == C + 1) v = sparse[(long long)b * HW + p];
+        else if (c == C + 2) v = lmask[(long long)b * HW + p];
+        else v = -var[(long long)b * HW + p];
+        out[i] = v;
+    }
+}
+
+// a13 (output side): m = sigmoid(logit); fused = dense*(1-m) + m*sparse
+// (submodule.py:602-604, SparseDenseNetRefinementMask.py:202)
+__global__ void __launch_bounds__(kBlock)
+blend_kernel(const float *__restrict__ logit, const float *__restrict__ dense, const float *__restrict__ sparse,
+             float *__restrict__ soft_mask, float *__restrict__ fused, long long n)
+{
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const float m = 1.0f / (1.0f + expf(-logit[i]));
+        const float d = dense[i], s = sparse[i];
+        if (soft_mask) soft_mask[i] = m;
+        fused[i] = d * (1.0f - m) + m * s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a14: warp the right features by the (fractional) disparity (Refinement.get_warped_feats_by_homgrp,
+// submodule.py:719-745) and, when `packed` is given, build the refinement conv input
+// cat(Lf, warped, disp) -> [B, 2C+1, H, W] (:758-759) in the same pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const float *__restrict__ disp,
+            float *__restrict__ warped, float *__restrict__ packed, int B, int C, int H, int W)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long n = (long long)B * H * W;
+    if (idx >= n) return;
+    const int w = (int)(idx % W), h = (int)((idx / W) % H), b = (int)(idx / ((long long)W * H));
+    const float dv = disp[idx];
+    const float ix = sample_coord((float)w - dv, (float)W);
+    const float iy = sample_coord((float)h, (float)H);
+    const Taps t = make_taps(ix, iy, H, W);
+    const size_t plane = (size_t)H * W;
+    const size_t pix = (size_t)h * W + w;
+    const float *Rb = Rf + (size_t)b * C * plane;
+    if (packed) {
+        float *pb = packed + (size_t)b * (2 * C + 1) * plane + pix;
+        const float *Lb = Lf + (size_t)b * C * plane + pix;
+        for (int c = 0; c < C; ++c) {
+            pb[(size_t)c * plane] = __ldg(Lb + (size_t)c * plane);
+            pb[(size_t)(C + c) * plane] = sample_plane(Rb + (size_t)c * plane, t, H, W);
+        }
+        pb[(size_t)(2 * C) * plane] = dv;
+    } else {
+        float *wb = warped + (size_t)b * C * plane + pix;
+        for (int c = 0; c < C; ++c) wb[(size_t)c * plane] = sample_plane(Rb + (size_t)c * plane, t, H, W);
+    }
+}
+
+static inline int grid_for(long long n, int cap = 148 * 16) {
+    long long g = (n + kBlock - 1) / kBlock;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace glue
+}  // namespace decnet
+
+using namespace decnet;
+using namespace decnet::glue;
+
+extern "C" {
+
+int decnet_costvol_fwd(const float *L, const float *R, float *vol, int B, int C, int H, int W, int D, void *stream) {
+    DECNET_REQUIRE(L && R && vol, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "non-positive size");
+    const long long n = (long long)B * D * H * W;
+    costvol_kernel<0><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(L, R, vol, B, C, H, W, D, C);
+    return after_launch("costvol_kernel<f32>");
+}
+
+int decnet_costvol_bf16_ndhwc(const float *L, const float *R, void *vol, int B, int C, int Cpad, int H, int W, int D,
+                              void *stream) {
+    DECNET_REQUIRE(L && R && vol, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "non-positive size");
+    DECNET_REQUIRE(Cpad >= C && Cpad % 8 == 0, "Cpad=%d must be >= C=%d and a multiple of 8", Cpad, C);
+    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15u) == 0, "volume must be 16-byte aligned");
+    const long long n = (long long)B * D * H * W;
+    costvol_kernel<1><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(L, R, vol, B, C, H, W, D, Cpad);
+    return after_launch("costvol_kernel<bf16>");
+}
+
+int decnet_softargmin(const float *cost, float *pred, int B, int D, int H, int W, void *stream) {
+    DECNET_REQUIRE(cost && pred, "null pointer");
+    DECNET_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "non-positive size");
+    const long long n = (long long)B * H * W;
+    softargmin_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(cost, pred, B, D, H * W);
+    return after_launch("softargmin_kernel");
+}
+
+int decnet_mask_threshold(const float *prob_l, const float *prob_r, float thold, float *mask_l, float *mask_r,
+                          int32_t *row_count_l, int32_t *row_count_r, int B, int H, int W, void *stream) {
+    DECNET_REQUIRE(prob_l && prob_r && mask_l && mask_r, "null pointer");
+    DECNET_REQUIRE(B > 0 && H > 0 && W > 0, "non-positive size");
+    mask_threshold_kernel<<<B * H, kBlock, 0, (cudaStream_t)stream>>>(prob_l, prob_r, thold, mask_l, mask_r,
+                                                                     row_count_l, row_count_r, W);
+    return after_launch("mask_threshold_kernel");
+}
+
+int decnet_dynup_pack(const float *disp, const float *left_fea, float *out, int B, int C, int h, int w, void *stream) {
+    DECNET_REQUIRE(disp && left_fea && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0, "non-positive size");
+    DECNET_REQUIRE(C + 1 <= 65535 && B <= 65535, "C or B too large for the launch grid");
+    const size_t smem = (size_t)9 * w * sizeof(float);
+    DECNET_REQUIRE(smem <= 200 * 1024, "row too wide");
+    if (smem > 48 * 1024)
+        DECNET_CUDA(cudaFuncSetAttribute(dynup_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dynup_pack_kernel<<<dim3(h, C + 1, B), kBlock, smem, (cudaStream_t)stream>>>(disp, left_fea, out, C, h, w);
+    return after_launch("dynup_pack_kernel");
+}
+
+int decnet_dynup_glue(const float *logits, const float *disp, float *out, int B, int h, int w, void *stream) {
+    DECNET_REQUIRE(logits && disp && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && h > 0 && w > 0, "non-positive size");
+    const long long n = (long long)B * h * w;
+    dynup_glue_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(logits, disp, out, B, h, w);
+    return after_launch("dynup_glue_kernel");
+}
+
+int decnet_attn_pack(const float *left_fea, const float *dense, const float *sparse, const float *left_mask,
+                     const float *var, float *out, int B, int C, int H, int W, void *stream) {
+    DECNET_REQUIRE(left_fea && dense && sparse && left_mask && var && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
+    const long long total = (long long)B * (C + 4) * H * W;
+    attn_pack_kernel<<<grid_for(total, 148 * 32), kBlock, 0, (cudaStream_t)stream>>>(left_fea, dense, sparse, left_mask, var, out,
+                                                                                   C, (long long)H * W, total);
+    return after_launch("attn_pack_kernel");
+}
+
+int decnet_blend(const float *logit, const float *dense, const float *sparse, float *soft_mask, float *fused,
+                 int B, int H, int W, void *stream) {
+    DECNET_REQUIRE(logit && dense && sparse && fused, "null pointer");
+    DECNET_REQUIRE(B > 0 && H > 0 && W > 0, "non-positive size");
+    const long long n = (long long)B * H * W;
+    blend_kernel<<<grid_for(n, 148 * 32), kBlock, 0, (cudaStream_t)stream>>>(logit, dense, sparse, soft_mask, fused, n);
+    return after_launch("blend_kernel");
+}
+
+int decnet_warp_bilinear(const float *right_fea, const float *disp, float *warped, int B, int C, int H, int W, void *stream) {
+    DECNET_REQUIRE(right_fea && disp && warped, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
+    const long long n = (long long)B * H * W;
+    warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(nullptr, right_fea, disp, warped, nullptr,
+                                                                                          B, C, H, W);
+    return after_launch("warp_kernel");
+}
+
+int decnet_refine_pack(const float *left_fea, const float *right_fea, const float *disp, float *out,
+                       int B, int C, int H, int W, void *stream) {
+    DECNET_REQUIRE(left_fea && right_fea && disp && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
+    const long long n = (long long)B * H * W;
+    warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(left_fea, right_fea, disp, nullptr, out,
+                                                                                          B, C, H, W);
+    return after_launch("warp_kernel<pack>");
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference's hot-path modules, backed by libdecnet_b200.so.
+
+Same class names, constructor arguments, forward signatures and state_dict keys as
+modules/submodule.py (GetCostVolume :428, CostRegNetNoDown :608, disparity_regression :766,
+GenerateSparseMask :347, DynamicUpsampling :566, SoftAttention :593, Refinement :666) so that a
+reference checkpoint loads unchanged and the reference's stage loop can call them.  What runs:
+
+  * hand-written sm_100a kernels (through the C ABI) for everything SURVEY.md section 8 marks
+    "ours": cost volume, 3-D aggregation (tcgen05 implicit GEMM), soft-argmin, mask threshold,
+    dynamic-upsampling pack + glue, SpaMat / SpaVar, soft-attention pack, sigmoid + blend,
+    disparity warp + refinement pack;
+  * cuDNN (through torch) for the tiny 2-D conv stacks the north star leaves to the library
+    (a5 / a8 / a13 / a14 convs), with eval-mode BatchNorm folded into the conv weights.
+
+Inference only (eval-mode BN).  CUDA tensors only: there is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .modules import SpaMat, SpaVar
+
+BN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# units with the reference's parameter names (conv.weight / conv.bias / bn.*)
+# --------------------------------------------------------------------------------------
+class Conv2dUnit(nn.Module):
+    """Conv2d [+ BN(eval)] [+ ReLU]; keys as modules/submodule.py:15-49."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, dilation=1, relu=True, bn=True,
+                 padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, dilation=dilation,
+                              padding=padding, bias=not bn)
+        self.bn = nn.BatchNorm2d(out_channels) if bn else None
+        self.relu = relu
+        self._folded = None
+
+    def folded(self):
+        if self._folded is None:
+            w = self.conv.weight.detach()
+            b = self.conv.bias.detach() if self.conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+            if self.bn is not None:
+                scale = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + BN_EPS)
+                w = w * scale.view(-1, 1, 1, 1)
+                b = (b - self.bn.running_mean) * scale + self.bn.bias.detach()
+            self._folded = (w.contiguous(), b.contiguous())
+        return self._folded
+
+    def forward(self, x):
+        w, b = self.folded()
+        x = F.conv2d(x, w, b, stride=self.conv.stride, padding=self.conv.padding, dilation=self.conv.dilation)
+        return F.relu_(x) if self.relu else x
+
+
+class Deconv2dUnit(nn.Module):
+    """ConvTranspose2d(bias) + ReLU; keys as modules/submodule.py:52-87 with bn=False."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride):
+        super().__init__()
+        self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=stride, bias=True)
+
+    def forward(self, x):
+        return F.relu_(self.conv(x))
+
+
+class Conv3dUnit(nn.Module):
+    """Conv3d 3^3 pad 1 (no bias) + BN3d(eval) [+ ReLU]; keys as modules/submodule.py:90-123."""
+
+    def __init__(self, in_channels, out_channels, relu=True):
+        super().__init__()
+        self.conv = nn.Conv3d(in_channels, out_channels, 3, padding=1, bias=False)
+        self.bn = nn.BatchNorm3d(out_channels)
+        self.relu = relu
+
+    def scale_bias(self):
+        scale = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + BN_EPS)
+        return scale, self.bn.bias.detach() - self.bn.running_mean * scale
+
+
+def _reset_folded(module):
+    for m in module.modules():
+        if hasattr(m, "_folded"):
+            m._folded = None
+        if hasattr(m, "_packed"):
+            m._packed = None
+
+
+# --------------------------------------------------------------------------------------
+# a1/a2: cost volume
+# --------------------------------------------------------------------------------------
+class GetCostVolume(nn.Module):
+    """Drop-in for modules/submodule.py:428-562, restricted to what the shipped model uses:
+    warp_ope="homgrp", cost_func="cor", stage-0 candidates 0..D-1 (get_disp_samples :376-390).
+    forward(left, right, disp_samples=[B,D,H,W] | max_disp=D) -> [B,C,D,H,W] fp32."""
+
+    def __init__(self, warp_ope="homgrp", cost_func="cor"):
+        super().__init__()
+        if warp_ope != "homgrp" or cost_func != "cor":
+            raise NotImplementedError("decnet_b200 implements the shipped configuration only: homgrp + cor")
+        self.warp_ope, self.cost_func = warp_ope, cost_func
+
+    def forward(self, left_feature_map, right_feature_map, **kargs):
+        if kargs.get("disp_samples") is not None:
+            D = int(kargs["disp_samples"].shape[1])
+        else:
+            D = int(kargs["max_disp"])
+        return ops.cost_volume(left_feature_map.contiguous(), right_feature_map.contiguous(), D)
+
+
+def get_disp_samples(max_dis, feature_map, stage_id=0, **_unused):
+    """Stage-0 branch of modules/submodule.py:376-390 (the only one the model executes)."""
+    B, _, H, W = feature_map.shape
+    return torch.arange(int(max_dis), dtype=feature_map.dtype, device=feature_map.device) \
+        .view(1, -1, 1, 1).expand(B, -1, H, W)
+
+
+def disparity_regression(cost_vol, disp_samples=None):
+    """Drop-in for modules/submodule.py:766-777 with integer candidates 0..D-1."""
+    return ops.softargmin(cost_vol.contiguous())
+
+
+# --------------------------------------------------------------------------------------
+# a3: 3-D aggregation
+# --------------------------------------------------------------------------------------
+class CostRegNetNoDown(nn.Module):
+    """Drop-in for modules/submodule.py:608-662 (cost_func 'cor').  forward([B,C,D,H,W]) -> [B,D,H,W].
+
+    `impl`:
+      "tcgen05"  hand-written bf16 implicit-GEMM kernels (decnet_conv3d_*), fp32 accumulate
+      "cudnn"    torch/cuDNN Conv3d with folded BN (fp32 or bf16 per `dtype`): bring-up/compare only
+    """
+
+    def __init__(self, in_channels, base_channels=None, cost_func="cor", down_scale=3, impl="tcgen05",
+                 dtype=torch.float32):
+        super().__init__()
+        if cost_func != "cor":
+            raise NotImplementedError("cost_func 'cor' only")
+        c = in_channels
+        self.conv0 = nn.Sequential(Conv3dUnit(c, c), Conv3dUnit(c, c))
+        self.conv1 = nn.Sequential(Conv3dUnit(c, c), Conv3dUnit(c, c), Conv3dUnit(c, c))
+        self.conv2 = nn.Sequential(Conv3dUnit(c, c), Conv3dUnit(c, c), Conv3dUnit(c, 1, relu=False))
+        self.impl = impl
+        self.dtype = dtype
+        self._folded = None
+        self._packed = None
+
+    def units(self):
+        return [*self.conv0, *self.conv1, *self.conv2]
+
+    # ---- cuDNN bring-up path --------------------------------------------------------
+    def _fold(self):
+        if self._folded is None:
+            out = []
+            for u in self.units():
+                s, b = u.scale_bias()
+                w = (u.conv.weight.detach() * s.view(-1, 1, 1, 1, 1)).to(self.dtype)
+                out.append((w.contiguous(memory_format=torch.channels_last_3d), b.to(self.dtype), u.relu))
+            self._folded = out
+        return self._folded
+
+    def _forward_cudnn(self, x):
+        f = self._fold()
+        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last_3d)
+
+        def run(x, i):
+            w, b, relu = f[i]
+            y = F.conv3d(x, w, b, padding=1)
+            return F.relu_(y) if relu else y
+        x = run(x, 0); o0 = run(x, 1)
+        x = run(o0, 2); x = run(x, 3); x = run(x, 4) + o0
+        x = run(x, 5); x = run(x, 6); x = run(x, 7)
+        return x.squeeze(1).float().contiguous()
+
+    def forward(self, x):
+        if self.impl == "cudnn":
+            return self._forward_cudnn(x)
+        from . import conv3d
+        return conv3d.cost_regularizer_forward(self, x)
+
+
+# --------------------------------------------------------------------------------------
+# a5: learned lost-detail detector (convs stay cuDNN)
+# --------------------------------------------------------------------------------------
+class GenerateSparseMask(nn.Module):
+    """Drop-in for modules/submodule.py:347-372."""
+
+    def __init__(self, in_channels, down_scale=3):
+        super().__init__()
+        self.deconv = nn.Sequential(Deconv2dUnit(in_channels * down_scale, 8, 3, 3),
+                                    Conv2dUnit(8, 3, 3, padding=1, relu=False))
+        self.conv_sub = nn.Sequential(Conv2dUnit(in_channels, 8, 3, padding=1, relu=True, bn=False),
+                                      Conv2dUnit(8, 3, 3, padding=1, relu=False))
+        self.conv = nn.Sequential(Conv2dUnit(3, 3, 3, padding=1, relu=False),
+                                  Conv2dUnit(3, 1, 1, padding=0, relu=False))
+
+    def forward(self, cur_fea, pre_fea):
+        pre = self.deconv(pre_fea)
+        cur = self.conv_sub(cur_fea)
+        res = (cur - pre) ** 2
+        return self.conv(res).squeeze(1), cur, pre
+
+
+# --------------------------------------------------------------------------------------
+# a8: dynamic up-sampling
+# --------------------------------------------------------------------------------------
+class DynamicUpsampling(nn.Module):
+    """Drop-in for modules/submodule.py:566-589: pack kernel -> 3 cuDNN convs -> glue kernel."""
+
+    def __init__(self, in_channels, down_scale=3):
+        super().__init__()
+        assert down_scale == 3, "the reference hard-codes x3 (SURVEY.md D1)"
+        n = down_scale ** 2 * 9
+        self.weight_learning = nn.Sequential(Conv2dUnit(in_channels * 9 + 1, n, 3, padding=1),
+                                             Conv2dUnit(n, n, 3, padding=1),
+                                             Conv2dUnit(n, n, 3, padding=1, relu=False))
+
+    def forward(self, disp_map, left_fea):
+        disp_map = disp_map.contiguous()
+        x = ops.dynup_pack(disp_map, left_fea.contiguous())
+        logits = self.weight_learning(x)
+        return ops.dynup_glue(logits.contiguous(), disp_map)
+
+
+# --------------------------------------------------------------------------------------
+# a13: soft attention (+ blend)
+# --------------------------------------------------------------------------------------
+class SoftAttention(nn.Module):
+    """Drop-in for modules/submodule.py:593-604.  forward(x=[B,C+4,H,W]) -> sigmoid mask like the
+    reference; `logits()` + ops.blend() is the fused route the pipeline uses."""
+
+    def __init__(self, in_channels, base_channels):
+        super().__init__()
+        self.conv = nn.Sequential(Conv2dUnit(in_channels, base_channels, 3, padding=1),
+                                  Conv2dUnit(base_channels, base_channels, 3, padding=1),
+                                  Conv2dUnit(base_channels, 1, 3, padding=1, relu=False))
+
+    def logits(self, x):
+        return self.conv(x)
+
+    def forward(self, x):
+        return torch.sigmoid(self.conv(x))
+
+
+# --------------------------------------------------------------------------------------
+# a14: refinement
+# --------------------------------------------------------------------------------------
+_REFINE_DIL = {0: (1,) * 6, 1: (1,) * 6, 2: (2, 1, 4, 1, 6, 1), 3: (3, 1, 6, 1, 9, 1)}
+
+
+class Refinement(nn.Module):
+    """Drop-in for modules/submodule.py:666-762: warp+pack kernel -> 7 cuDNN convs -> add."""
+
+    def __init__(self, in_channels, base_channels=None, stage_id=-1, down_scale=3):
+        super().__init__()
+        c = in_channels
+        dil = _REFINE_DIL[stage_id]
+        chain = [(2 * c + 1, c), (c, c), (c, c), (c, c // 2), (c // 2, c // 2), (c // 2, c // 2)]
+        layers = [Conv2dUnit(ci, co, 3, padding=d, dilation=d) for (ci, co), d in zip(chain, dil)]
+        layers.append(Conv2dUnit(c // 2, 1, 3, padding=1, relu=False, bn=False))
+        self.conv = nn.Sequential(*layers)
+
+    def forward(self, left_fea, right_fea, disp_map):
+        disp_map = disp_map.contiguous()
+        x = ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map)
+        residual = self.conv(x).squeeze(1)
+        return disp_map + residual, residual
+
+
+# --------------------------------------------------------------------------------------
+# a16: the stage loop
+# --------------------------------------------------------------------------------------
+class DecompMatching(nn.Module):
+    """The decomposed-matching hot path: body of SparseDenseNetRefinementMask.forward after feature
+    extraction (modules/SparseDenseNetRefinementMask.py:118-212), same hyper-parameters and the
+    same sub-module names, so `load_state_dict(reference_state, strict=False)` picks up every
+    hot-path weight (feature_extractor.* is ignored: out of scope).
+
+    forward(left_feats, right_feats, left_mask_list=None, right_mask_list=None, is_check=False)
+      left_feats/right_feats: {"stage0".."stage3"} NCHW fp32 CUDA tensors (C = 216,72,24,8)
+      returns [pred] like the reference's inference path, or (pred, taps) with is_check.
+    """
+
+    def __init__(self, max_disp=216, base_channels=8, num_stage=4, down_scale=3, skip_stage_id=4,
+                 use_detail=True, thold=0.9, conv3d_impl="tcgen05", channels=None):
+        super().__init__()
+        assert down_scale == 3 and num_stage == 4, "shipped configuration (demo.sh:1)"
+        assert max_disp % (down_scale ** (num_stage - 1)) == 0, "max_disp must be a multiple of 27"
+        self.max_disp, self.num_stage, self.down_scale = max_disp, num_stage, down_scale
+        self.skip_stage_id, self.use_detail, self.thold = skip_stage_id, use_detail, thold
+        ch = list(channels) if channels is not None else [27 * base_channels, 9 * base_channels,
+                                                          3 * base_channels, base_channels]
+        self.channels = ch
+        self.get_cost_volume = GetCostVolume("homgrp", "cor")
+        self.sparse_matching = nn.ModuleList([SpaMat() for _ in range(num_stage - 1)])
+        self.sparse_var = nn.ModuleList([SpaVar() for _ in range(num_stage - 1)])
+        self.cost_regularizer = CostRegNetNoDown(ch[0], ch[0] * 2, "cor", down_scale, impl=conv3d_impl)
+        self.detail_detection = nn.ModuleList([GenerateSparseMask(ch[i + 1], down_scale) for i in range(num_stage - 1)])
+        self.dynamic_upsampling = nn.ModuleList([DynamicUpsampling(ch[i + 1], down_scale) for i in range(num_stage - 1)])
+        self.soft_attention = nn.ModuleList([SoftAttention(ch[i + 1] + 4, base_channels) for i in range(num_stage - 1)])
+        self.refinement = nn.ModuleList([Refinement(ch[i + 1], base_channels // (2 ** i), stage_id=i + 1,
+                                                    down_scale=down_scale) for i in range(num_stage - 1)])
+        self.eval()
+
+    def load_state_dict(self, state_dict, strict=False, **kw):
+        sd = {k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()}   # demo.py:124-135
+        sd = {k: v for k, v in sd.items() if not k.startswith("feature_extractor")}
+        res = super().load_state_dict(sd, strict=strict, **kw)
+        _reset_folded(self)
+        return res
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        _reset_folded(self)
+        return out
+
+    @torch.no_grad()
+    def forward(self, left_feats, right_feats, left_mask_list=None, right_mask_list=None, is_check=False):
+        taps = {k: [] for k in ("pred", "dense", "sparse", "var", "soft_mask", "fusion", "residual",
+                                "left_mask", "right_mask", "left_detail", "right_detail")} if is_check else None
+        pred = None
+        pre_l = pre_r = None
+        for s in range(self.num_stage):
+            Lf = left_feats[f"stage{s}"].contiguous()
+            Rf = right_feats[f"stage{s}"].contiguous()
+            D = self.max_disp // (self.down_scale ** (self.num_stage - s - 1))
+            if s == 0:
+                pred, cost = self.dense_stage(Lf, Rf, D)
+                if is_check:
+                    taps["cost"] = cost
+                pre_l, pre_r = Lf, Rf
+            elif s >= self.skip_stage_id:
+                # SparseDenseNetRefinementMask.py:143-144 (Middlebury's finest level); single ATen kernel
+                pred = F.interpolate(pred.unsqueeze(1) * self.down_scale, list(Lf.shape[-2:]), mode="bicubic").squeeze(1)
+            else:
+                l = s - 1
+                if self.use_detail:
+                    ld, _, _ = self.detail_detection[l](Lf, pre_l)
+                    rd, _, _ = self.detail_detection[l](Rf, pre_r)
+                    pre_l, pre_r = Lf, Rf
+                    ld, rd = torch.sigmoid(ld).contiguous(), torch.sigmoid(rd).contiguous()
+                    lm, rm = ops.mask_threshold(ld, rd, self.thold)
+                    if is_check:
+                        taps["left_detail"].append(ld); taps["right_detail"].append(rd)
+                else:
+                    lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
+                dense = self.dynamic_upsampling[l](pred, Lf)
+                sparse, var, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm, rm, D)     # SpaMat + SpaVar, one pass
+                x = ops.attn_pack(Lf, dense, sparse, lm, var)
+                logit = self.soft_attention[l].logits(x).squeeze(1).contiguous()
+                soft, fused = ops.blend(logit, dense, sparse, want_mask=is_check)
+                pred, residual = self.refinement[l](Lf, Rf, fused)
+                if is_check:
+                    for k, v in (("dense", dense), ("sparse", sparse), ("var", var), ("soft_mask", soft),
+                                 ("fusion", fused), ("residual", residual), ("left_mask", lm), ("right_mask", rm)):
+                        taps[k].append(v)
+            if is_check:
+                taps["pred"].append(pred)
+        return (pred, taps) if is_check else [pred]
+
+    def dense_stage(self, Lf, Rf, D):
+        """a1-a4: cost volume -> 3-D aggregation -> soft-argmin.  Returns (pred [B,H,W], cost [B,D,H,W])."""
+        if self.cost_regularizer.impl == "tcgen05":
+            from . import conv3d
+            cost = conv3d.dense_cost(self.cost_regularizer, Lf, Rf, D)
+        else:
+            vol = ops.cost_volume(Lf, Rf, D)
+            cost = self.cost_regularizer(vol)
+        return ops.softargmin(cost), cost

@@ -141,3 +141,119 @@ def candidate_signature(ref_mask, tar_mask, max_disp):
             B, H, W, int(max_disp), _stream(ref_mask))
     _lib.check(st, "decnet_candidate_signature")
     return count, hsh
+
+
+# --------------------------------------------------------------------------------------
+# dense stage + glue
+# --------------------------------------------------------------------------------------
+def _call(name, t, *args):
+    with torch.cuda.device_of(t):
+        st = getattr(_lib.lib(), name)(*args, _stream(t))
+    _lib.check(st, name)
+
+
+def cost_volume(left_fea, right_fea, D):
+    """fp32 NCDHW cost volume [B,C,D,H,W] (reference layout)."""
+    _chk("left_fea", left_fea)
+    B, Cc, H, W = left_fea.shape
+    _chk("right_fea", right_fea, left_fea, (B, Cc, H, W))
+    vol = torch.empty((B, Cc, int(D), H, W), dtype=torch.float32, device=left_fea.device)
+    _call("decnet_costvol_fwd", left_fea, left_fea.data_ptr(), right_fea.data_ptr(), vol.data_ptr(), B, Cc, H, W, int(D))
+    return vol
+
+
+def cost_volume_bf16_ndhwc(left_fea, right_fea, D, Cpad):
+    """bf16 channels-last cost volume [B,D,H,W,Cpad] (input of the tcgen05 conv)."""
+    _chk("left_fea", left_fea)
+    B, Cc, H, W = left_fea.shape
+    _chk("right_fea", right_fea, left_fea, (B, Cc, H, W))
+    vol = torch.empty((B, int(D), H, W, int(Cpad)), dtype=torch.bfloat16, device=left_fea.device)
+    _call("decnet_costvol_bf16_ndhwc", left_fea, left_fea.data_ptr(), right_fea.data_ptr(), vol.data_ptr(),
+          B, Cc, int(Cpad), H, W, int(D))
+    return vol
+
+
+def softargmin(cost):
+    _chk("cost", cost)
+    B, D, H, W = cost.shape
+    pred = torch.empty((B, H, W), dtype=torch.float32, device=cost.device)
+    _call("decnet_softargmin", cost, cost.data_ptr(), pred.data_ptr(), B, D, H, W)
+    return pred
+
+
+def mask_threshold(prob_l, prob_r, thold, with_counts=False):
+    _chk("prob_l", prob_l)
+    _chk("prob_r", prob_r, prob_l, prob_l.shape)
+    B, H, W = prob_l.shape
+    ml, mr = torch.empty_like(prob_l), torch.empty_like(prob_r)
+    cl = cr = None
+    if with_counts:
+        cl = torch.empty(B * H, dtype=torch.int32, device=prob_l.device)
+        cr = torch.empty(B * H, dtype=torch.int32, device=prob_l.device)
+    _call("decnet_mask_threshold", prob_l, prob_l.data_ptr(), prob_r.data_ptr(), float(thold), ml.data_ptr(),
+          mr.data_ptr(), cl.data_ptr() if with_counts else None, cr.data_ptr() if with_counts else None, B, H, W)
+    return (ml, mr, cl, cr) if with_counts else (ml, mr)
+
+
+def dynup_pack(disp, left_fea):
+    _chk("disp", disp)
+    B, h, w = disp.shape
+    _chk("left_fea", left_fea, disp)
+    Cc = left_fea.shape[1]
+    if tuple(left_fea.shape) != (B, Cc, 3 * h, 3 * w):
+        raise ValueError(f"left_fea {tuple(left_fea.shape)} is not 3x the disparity map {tuple(disp.shape)}")
+    out = torch.empty((B, 9 * Cc + 1, h, w), dtype=torch.float32, device=disp.device)
+    _call("decnet_dynup_pack", disp, disp.data_ptr(), left_fea.data_ptr(), out.data_ptr(), B, Cc, h, w)
+    return out
+
+
+def dynup_glue(logits, disp):
+    _chk("disp", disp)
+    B, h, w = disp.shape
+    _chk("logits", logits, disp, (B, 81, h, w))
+    out = torch.empty((B, 3 * h, 3 * w), dtype=torch.float32, device=disp.device)
+    _call("decnet_dynup_glue", disp, logits.data_ptr(), disp.data_ptr(), out.data_ptr(), B, h, w)
+    return out
+
+
+def attn_pack(left_fea, dense, sparse, left_mask, var):
+    _chk("left_fea", left_fea)
+    B, Cc, H, W = left_fea.shape
+    for n, t in (("dense", dense), ("sparse", sparse), ("left_mask", left_mask), ("var", var)):
+        _chk(n, t, left_fea, (B, H, W))
+    out = torch.empty((B, Cc + 4, H, W), dtype=torch.float32, device=left_fea.device)
+    _call("decnet_attn_pack", left_fea, left_fea.data_ptr(), dense.data_ptr(), sparse.data_ptr(),
+          left_mask.data_ptr(), var.data_ptr(), out.data_ptr(), B, Cc, H, W)
+    return out
+
+
+def blend(logit, dense, sparse, want_mask=True):
+    _chk("logit", logit)
+    B, H, W = logit.shape
+    _chk("dense", dense, logit, (B, H, W))
+    _chk("sparse", sparse, logit, (B, H, W))
+    fused = torch.empty_like(dense)
+    soft = torch.empty_like(dense) if want_mask else None
+    _call("decnet_blend", logit, logit.data_ptr(), dense.data_ptr(), sparse.data_ptr(),
+          soft.data_ptr() if want_mask else None, fused.data_ptr(), B, H, W)
+    return soft, fused
+
+
+def warp_bilinear(right_fea, disp):
+    _chk("right_fea", right_fea)
+    B, Cc, H, W = right_fea.shape
+    _chk("disp", disp, right_fea, (B, H, W))
+    out = torch.empty_like(right_fea)
+    _call("decnet_warp_bilinear", right_fea, right_fea.data_ptr(), disp.data_ptr(), out.data_ptr(), B, Cc, H, W)
+    return out
+
+
+def refine_pack(left_fea, right_fea, disp):
+    _chk("left_fea", left_fea)
+    B, Cc, H, W = left_fea.shape
+    _chk("right_fea", right_fea, left_fea, (B, Cc, H, W))
+    _chk("disp", disp, left_fea, (B, H, W))
+    out = torch.empty((B, 2 * Cc + 1, H, W), dtype=torch.float32, device=left_fea.device)
+    _call("decnet_refine_pack", left_fea, left_fea.data_ptr(), right_fea.data_ptr(), disp.data_ptr(), out.data_ptr(),
+          B, Cc, H, W)
+    return out

@@ -114,6 +114,76 @@ int decnet_last_sparse_path(void);
 /* Force a path for the forward ops on this thread: 0 = auto, 1 = cp.async, 2 = TMA. */
 void decnet_set_sparse_path(int path);
 
+/* ------------------------------------------------------------------------- *
+ * Coarse dense stage.
+ * ------------------------------------------------------------------------- */
+
+/* Cost volume for the stage-0 candidates d = 0..D-1:
+ *   vol[b,c,d,h,w] = (w >= d ? L[b,c,h,w] : 0) * bilinear0(R[b,c], y'(h), x'(w-d))
+ * with the reference's coordinate quirk (normalise with (size-1)/2, sample with
+ * align_corners=False, zero padding).  Output fp32 NCDHW [B,C,D,H,W].
+ * Replaces GetCostVolume.forward / get_warped_feats_by_homgrp / cost_computation_cor
+ * (modules/submodule.py:532-562, 479-510, 518-522) + get_disp_samples (:376-390). */
+int decnet_costvol_fwd(const float *left_fea, const float *right_fea, float *vol,
+                       int B, int C, int H, int W, int D, void *stream);
+
+/* Same volume written as bf16 channels-last [B,D,H,W,Cpad] (Cpad >= C, multiple of 8,
+ * channels C..Cpad-1 zero): the input layout of decnet_conv3d_* (tcgen05 implicit GEMM). */
+int decnet_costvol_bf16_ndhwc(const float *left_fea, const float *right_fea, void *vol_bf16,
+                              int B, int C, int Cpad, int H, int W, int D, void *stream);
+
+/* pred[b,h,w] = sum_d softmax_d(cost[b,:,h,w]) * d.  Replaces disparity_regression
+ * (modules/submodule.py:766-777) for integer candidates 0..D-1. */
+int decnet_softargmin(const float *cost, float *pred, int B, int D, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Lost-detail mask selection (row a6).
+ *   m = p > thold ? 1 : (p <= thold ? 0 : p)  for the left and right maps [B,H,W];
+ * row_count_* (optional, [B*H] int32) receive the number of selected pixels per row.
+ * Replaces the clone + 4 boolean index_puts of
+ * modules/SparseDenseNetRefinementMask.py:164-170. */
+int decnet_mask_threshold(const float *prob_l, const float *prob_r, float thold,
+                          float *mask_l, float *mask_r,
+                          int32_t *row_count_l, int32_t *row_count_r,
+                          int B, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fusion / up-sampling glue (rows a8, a13, a14).
+ * ------------------------------------------------------------------------- */
+
+/* DynamicUpsampling conv input: out[B,1+9C,h,w], ch0 = disp, ch 1+c*9+ky*3+kx =
+ * left_fea[b,c,3y+ky,3x+kx]; left_fea is [B,C,3h,3w].  Replaces unfold + cat
+ * (modules/submodule.py:580). */
+int decnet_dynup_pack(const float *disp, const float *left_fea, float *out,
+                      int B, int C, int h, int w, void *stream);
+
+/* DynamicUpsampling output: logits [B,81,h,w] (channel = sub*9+k), disp [B,h,w] ->
+ * out [B,3h,3w] = 3 * sum_k softmax_k(logits[sub]) * disp_replicate_pad[y+ky-1, x+kx-1],
+ * pixel-shuffled.  Replaces softmax/unfold/mul/sum/pixel_shuffle (submodule.py:581-589). */
+int decnet_dynup_glue(const float *logits, const float *disp, float *out,
+                      int B, int h, int w, void *stream);
+
+/* SoftAttention conv input cat(left_fea, dense, sparse, left_mask, -var) -> [B,C+4,H,W]
+ * (modules/SparseDenseNetRefinementMask.py:197). */
+int decnet_attn_pack(const float *left_fea, const float *dense, const float *sparse,
+                     const float *left_mask, const float *var, float *out,
+                     int B, int C, int H, int W, void *stream);
+
+/* m = sigmoid(logit); fused = dense*(1-m) + m*sparse; soft_mask may be NULL.
+ * Replaces F.sigmoid (submodule.py:604) + the blend (SparseDenseNetRefinementMask.py:202). */
+int decnet_blend(const float *logit, const float *dense, const float *sparse,
+                 float *soft_mask, float *fused, int B, int H, int W, void *stream);
+
+/* warped[b,c,h,w] = bilinear0(right_fea[b,c], y'(h), x'(w - disp[b,h,w])).
+ * Replaces Refinement.get_warped_feats_by_homgrp (modules/submodule.py:719-745). */
+int decnet_warp_bilinear(const float *right_fea, const float *disp, float *warped,
+                         int B, int C, int H, int W, void *stream);
+
+/* Refinement conv input cat(left_fea, warped, disp) -> [B,2C+1,H,W] in one pass
+ * (modules/submodule.py:757-759). */
+int decnet_refine_pack(const float *left_fea, const float *right_fea, const float *disp, float *out,
+                       int B, int C, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

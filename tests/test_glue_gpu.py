@@ -1,0 +1,153 @@
+"""GPU parity of the dense-stage and glue kernels (through the C ABI) against
+(a) the golden vectors of the unmodified reference, teacher-forced op by op, and
+(b) the torch oracle on seeded random inputs at other shapes (incl. odd sizes)."""
+import pytest
+import torch
+
+from golden_util import CASES, chain_close, gold_list, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg, P, conv3d_impl="cudnn"):
+    from decnet_b200.model import DecompMatching
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = DecompMatching(max_disp=cfg["max_disp"], skip_stage_id=cfg["skip_stage_id"], use_detail=cfg["use_detail"],
+                       thold=cfg["thold"], conv3d_impl=conv3d_impl)
+    m.load_state_dict(P)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_ops_teacher_forced_vs_reference_golden(name):
+    from decnet_b200 import ops
+    z, P, left, right, lmasks, rmasks, cfg = load_case(name, device="cuda")
+    model = _model(cfg, P)
+    D0 = cfg["max_disp"] // 27
+    vol = ops.cost_volume(left["stage0"], right["stage0"], D0)
+    gvol = torch.from_numpy(z["vol"]).cuda()
+    assert torch.allclose(vol, gvol, atol=1e-4, rtol=1e-4), (vol - gvol).abs().max()
+    gcost = torch.from_numpy(z["cost"]).cuda()
+    cost = model.cost_regularizer(gvol)                      # cuDNN fp32 bring-up path (TF32 off)
+    assert torch.allclose(cost, gcost, atol=1e-3, rtol=1e-4), (cost - gcost).abs().max()
+    pred = gold_list(z, "pred", "cuda")
+    assert torch.allclose(ops.softargmin(gcost), pred[0], atol=1e-4)
+    dense, sparse, var = gold_list(z, "dense", "cuda"), gold_list(z, "sparse", "cuda"), gold_list(z, "var", "cuda")
+    soft, fusion, resid = gold_list(z, "soft_mask", "cuda"), gold_list(z, "fusion", "cuda"), gold_list(z, "residual", "cuda")
+    lm, rm = gold_list(z, "lmask", "cuda"), gold_list(z, "rmask", "cuda")
+    for l in range(len(dense)):
+        s = l + 1
+        Lf, Rf = left[f"stage{s}"], right[f"stage{s}"]
+        D = cfg["max_disp"] // 3 ** (3 - s)
+        tol = 1e-3 + 1e-5 * float(dense[l].abs().max())
+        d = model.dynamic_upsampling[l](pred[s - 1], Lf)
+        assert float((d - dense[l]).abs().max()) <= tol, ("dynup", l)
+        sp, vr, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm[l], rm[l], D)
+        assert torch.allclose(sp, sparse[l], atol=1e-3, rtol=1e-5), ("sparse", l)
+        assert torch.allclose(vr, var[l], atol=1e-3, rtol=1e-4), ("var", l)
+        x = ops.attn_pack(Lf, dense[l], sparse[l], lm[l], var[l])
+        logit = model.soft_attention[l].logits(x).squeeze(1).contiguous()
+        sm, fu = ops.blend(logit, dense[l], sparse[l])
+        assert torch.allclose(sm, soft[l], atol=1e-3), ("soft", l, (sm - soft[l]).abs().max())  # cuDNN-vs-CPU conv noise on |x|~1e3 inputs
+        # blend arithmetic against the same soft mask (the gold fusion used the gold mask, and the
+        # mask carries cuDNN-vs-CPU conv noise multiplied by |dense - sparse| ~ 1e2 px here)
+        want_fu = dense[l] * (1 - sm) + sm * sparse[l]
+        assert float((fu - want_fu).abs().max()) <= tol, ("fusion", l)
+        fu_gold_mask = dense[l] * (1 - soft[l]) + soft[l] * sparse[l]
+        assert float((fu_gold_mask - fusion[l]).abs().max()) <= tol, ("fusion-formula", l)
+        p_, r_ = model.refinement[l](Lf, Rf, fusion[l])
+        assert float((r_ - resid[l]).abs().max()) <= tol, ("residual", l, (r_ - resid[l]).abs().max())
+        assert float((p_ - pred[s]).abs().max()) <= tol, ("pred", l)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pipeline_chained_vs_reference_golden(name):
+    z, P, left, right, lmasks, rmasks, cfg = load_case(name, device="cuda")
+    model = _model(cfg, P)
+    pred, taps = model(left, right, lmasks, rmasks, is_check=True)
+    for got, want in zip(taps["left_mask"], gold_list(z, "lmask", "cuda")):
+        assert torch.equal(got, want)                        # mask selection bit-exact
+    for got, want in zip(taps["right_mask"], gold_list(z, "rmask", "cuda")):
+        assert torch.equal(got, want)
+    for key in ("pred", "dense", "sparse", "fusion", "residual", "soft_mask", "var"):
+        want = gold_list(z, key, "cuda")
+        assert len(want) == len(taps[key]), key
+        for i, (g_, w_) in enumerate(zip(taps[key], want)):
+            # chained through ~40 random-init conv layers on another conv library (cuDNN vs the CPU
+            # ATen of the golden run): the strict 1e-3 gates are the teacher-forced tests above
+            assert chain_close(g_, w_, rel=3e-3, abs_=3e-3), f"{key}[{i}] max diff {(g_ - w_).abs().max()} of {w_.abs().max()}"
+            assert float((g_ - w_).abs().mean()) <= 1e-3 + 2e-4 * float(w_.abs().max()), (key, i)
+    out = model(left, right, lmasks, rmasks)
+    assert isinstance(out, list) and torch.equal(out[0], pred)
+
+
+@pytest.mark.parametrize("B,C,H,W,D", [(1, 216, 20, 36, 8), (2, 216, 14, 47, 8), (1, 24, 5, 7, 11), (1, 8, 2, 2, 3)])
+def test_cost_volume_vs_oracle(B, C, H, W, D):
+    from decnet_b200 import ops
+    from oracle import dense as od
+    from helpers import make_feats
+    L, R = make_feats(B, C, H, W, device="cuda")
+    want = od.cost_volume(L, R, D)
+    got = ops.cost_volume(L, R, D)
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5), (got - want).abs().max()
+    Cpad = (C + 15) // 16 * 16
+    got16 = ops.cost_volume_bf16_ndhwc(L, R, D, Cpad)
+    assert got16.shape == (B, D, H, W, Cpad)
+    ref16 = want.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    assert torch.equal(got16[..., :C], ref16) or torch.allclose(got16[..., :C].float(), ref16.float(), atol=1e-2, rtol=1e-2)
+    assert got16[..., C:].abs().max().item() == 0 if Cpad > C else True
+
+
+def test_mask_threshold_bit_exact():
+    from decnet_b200 import ops
+    from oracle import glue as og
+    g = torch.Generator(device="cuda").manual_seed(4)
+    p = torch.rand(2, 13, 37, device="cuda", generator=g)
+    q = torch.rand(2, 13, 37, device="cuda", generator=g)
+    thold = 0.9
+    p[0, 0, 0] = 0.9; p[0, 0, 1] = float("nan"); p[0, 0, 2] = torch.nextafter(torch.tensor(0.9), torch.tensor(1.0)).item()
+    ml, mr, cl, cr = ops.mask_threshold(p, q, thold, with_counts=True)
+    wl, wr = og.threshold_mask(p, thold), og.threshold_mask(q, thold)
+    assert torch.equal(torch.nan_to_num(ml, nan=-7.0), torch.nan_to_num(wl, nan=-7.0))
+    assert torch.equal(mr, wr)
+    assert torch.isnan(ml[0, 0, 1]) and ml[0, 0, 0] == 0 and ml[0, 0, 2] == 1
+    assert torch.equal(cl.view(2, 13), (ml != 0).sum(-1).int()) and torch.equal(cr.view(2, 13), (mr != 0).sum(-1).int())
+
+
+@pytest.mark.parametrize("B,C,h,w", [(2, 8, 6, 9), (1, 24, 4, 5), (1, 72, 3, 4)])
+def test_dynup_pack_and_glue_vs_oracle(B, C, h, w):
+    from decnet_b200 import ops
+    from oracle import glue as og
+    g = torch.Generator(device="cuda").manual_seed(5)
+    disp = torch.rand(B, h, w, device="cuda", generator=g) * 20
+    Lf = torch.randn(B, C, 3 * h, 3 * w, device="cuda", generator=g)
+    assert torch.equal(ops.dynup_pack(disp, Lf), og.dynup_pack(disp, Lf))          # pure data movement
+    logits = torch.randn(B, 81, h, w, device="cuda", generator=g) * 3
+    assert torch.allclose(ops.dynup_glue(logits, disp), og.dynup_glue(logits, disp), atol=1e-4, rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 8, 27, 54), (1, 24, 9, 13), (1, 72, 4, 4)])
+def test_warp_pack_blend_vs_oracle(B, C, H, W):
+    from decnet_b200 import ops
+    from oracle import glue as og
+    g = torch.Generator(device="cuda").manual_seed(6)
+    Lf = torch.randn(B, C, H, W, device="cuda", generator=g)
+    Rf = torch.randn(B, C, H, W, device="cuda", generator=g)
+    disp = (torch.rand(B, H, W, device="cuda", generator=g) - 0.1) * W      # fractional, some out of range
+    want = og.warp_by_disparity(Rf, disp)
+    got = ops.warp_bilinear(Rf, disp)
+    assert torch.allclose(got, want, atol=1e-4, rtol=1e-4), (got - want).abs().max()
+    packed = ops.refine_pack(Lf, Rf, disp)
+    assert torch.equal(packed[:, :C], Lf) and torch.equal(packed[:, 2 * C], disp)
+    assert torch.equal(packed[:, C:2 * C], got)
+    dense = torch.randn(B, H, W, device="cuda", generator=g) * 10
+    sparse = torch.randn(B, H, W, device="cuda", generator=g) * 10
+    lm = (torch.rand(B, H, W, device="cuda", generator=g) < 0.2).float()
+    var = torch.rand(B, H, W, device="cuda", generator=g) * 100
+    x = ops.attn_pack(Lf, dense, sparse, lm, var)
+    assert torch.equal(x, torch.cat((Lf, dense[:, None], sparse[:, None], lm[:, None], -var[:, None]), 1))
+    logit = torch.randn(B, H, W, device="cuda", generator=g) * 4
+    sm, fu = ops.blend(logit, dense, sparse)
+    m = torch.sigmoid(logit)
+    assert torch.allclose(sm, m, atol=1e-6) and torch.allclose(fu, og.blend(dense, sparse, m), atol=1e-4)
