@@ -136,6 +136,18 @@ int decnet_costvol_bf16_ndhwc(const float *left_fea, const float *right_fea, voi
  * (modules/submodule.py:766-777) for integer candidates 0..D-1. */
 int decnet_softargmin(const float *cost, float *pred, int B, int D, int H, int W, void *stream);
 
+/* One Conv3dUnit of the aggregation stack (Conv3d 3x3x3 pad 1 no bias -> BN(eval) -> ReLU
+ * [-> + residual], modules/submodule.py:90-123, 650-662) as a bf16 implicit GEMM on tcgen05
+ * tensor cores, fp32 accumulation in TMEM.
+ *   x        bf16 channels-last [B,D,H,W,cp]           (cp = padded C_in, multiple of 16)
+ *   w_packed bf16 [27][np][cp], tap = (kd*3+kh)*3+kw, BN scale folded in, zero padded
+ *   bias     fp32 [np] (BN shift), residual bf16 [B,D,H,W,np] or NULL (added AFTER the ReLU)
+ *   out_mode 0: out bf16 [B,D,H,W,np];  1: out fp32 [B,D,H,W] = channel 0 (the 216->1 layer)
+ * All pointers 16-byte aligned. */
+int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *bias,
+                       const void *residual, void *out, int out_mode,
+                       int B, int D, int H, int W, int cp, int np, int relu, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * Lost-detail mask selection (row a6).
  *   m = p > thold ? 1 : (p <= thold ? 0 : p)  for the left and right maps [B,H,W];

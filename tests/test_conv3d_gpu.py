@@ -1,0 +1,78 @@
+"""GPU parity of the tcgen05 implicit-GEMM Conv3d (through the C ABI).
+Tolerance (north star): the bf16 aggregation may move the disparity by <= 0.05 px EPE; single layers are
+checked against an fp32 torch convolution of the SAME bf16-rounded operands (so only accumulation order
+and the bf16 output rounding differ)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from golden_util import CASES, gold_list, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_layer(x_ndhwc, w_packed, bias, relu, residual=None):
+    """fp32 reference on the bf16-rounded operands: x [B,D,H,W,CP], w [27][NP][CP]."""
+    torch.backends.cudnn.allow_tf32 = False
+    x = x_ndhwc.float().permute(0, 4, 1, 2, 3).contiguous()
+    NP, CP = w_packed.shape[1:]
+    w = w_packed.float().view(3, 3, 3, NP, CP).permute(3, 4, 0, 1, 2).contiguous()
+    y = F.conv3d(x, w, bias, padding=1)
+    if relu:
+        y = F.relu(y)
+    y = y.permute(0, 2, 3, 4, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+@pytest.mark.parametrize("B,D,H,W,C,Cout", [(1, 8, 20, 36, 216, 216), (2, 8, 14, 47, 216, 216), (1, 3, 5, 7, 32, 48),
+                                              (1, 8, 4, 6, 216, 1), (1, 29, 9, 11, 64, 64), (1, 1, 1, 1, 16, 16)])
+@pytest.mark.parametrize("relu,use_res", [(True, False), (True, True), (False, False)])
+def test_single_layer_vs_fp32_conv(B, D, H, W, C, Cout, relu, use_res):
+    from decnet_b200 import conv3d as c3
+    g = torch.Generator(device="cuda").manual_seed(11)
+    cp, np_ = c3._pad16(C), c3._pad16(Cout)
+    x = torch.zeros(B, D, H, W, cp, device="cuda", dtype=torch.bfloat16)
+    x[..., :C] = (torch.randn(B, D, H, W, C, device="cuda", generator=g)).to(torch.bfloat16)
+    w = torch.zeros(27, np_, cp, device="cuda", dtype=torch.bfloat16)
+    w[:, :Cout, :C] = (torch.randn(27, Cout, C, device="cuda", generator=g) * (2.0 / (27 * C)) ** 0.5).to(torch.bfloat16)
+    bias = torch.zeros(np_, device="cuda"); bias[:Cout] = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    res = None
+    if use_res:
+        if Cout == 1:
+            pytest.skip("no residual on the single-channel layer")
+        res = torch.zeros(B, D, H, W, np_, device="cuda", dtype=torch.bfloat16)
+        res[..., :Cout] = torch.randn(B, D, H, W, Cout, device="cuda", generator=g).to(torch.bfloat16)
+    want = _ref_layer(x, w, bias, relu, res)
+    if Cout == 1:
+        got = c3.conv3d_layer(x, w, bias, np_, relu, out_f32=True)
+        assert torch.allclose(got, want[..., 0], atol=2e-3, rtol=1e-3), (got - want[..., 0]).abs().max()
+    else:
+        got = c3.conv3d_layer(x, w, bias, np_, relu, residual=res).float()
+        err = (got - want).abs().max().item()
+        scale = want.abs().max().item()
+        assert err <= 2 ** -7 * scale + 1e-3, (err, scale)          # bf16 output rounding (2^-8 rel) + slack
+        if np_ > Cout:
+            assert got[..., Cout:].abs().max().item() == 0          # padded channels stay exactly zero
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stack_vs_reference_golden(name):
+    """Full a2+a3+a4 with the bf16 tcgen05 stack against the reference's fp32 golden coarse disparity."""
+    from decnet_b200.model import DecompMatching
+    z, P, left, right, lmasks, rmasks, cfg = load_case(name, device="cuda")
+    m = DecompMatching(max_disp=cfg["max_disp"], skip_stage_id=cfg["skip_stage_id"], use_detail=cfg["use_detail"],
+                       thold=cfg["thold"], conv3d_impl="tcgen05")
+    m.load_state_dict(P)
+    m = m.cuda()
+    pred0, cost = m.dense_stage(left["stage0"], right["stage0"], cfg["max_disp"] // 27)
+    gpred = gold_list(z, "pred", "cuda")[0]
+    gcost = torch.from_numpy(z["cost"]).cuda()
+    epe = (pred0 - gpred).abs().mean().item()
+    assert epe <= 0.05, f"coarse EPE delta {epe}"
+    rel = (cost - gcost).abs().max().item() / gcost.abs().max().item()
+    assert rel <= 0.05, f"cost relative error {rel}"
+    # drop-in forward([B,C,D,H,W]) route gives the same numbers as the fused route
+    cost2 = m.cost_regularizer(torch.from_numpy(z["vol"]).cuda())
+    assert (cost2 - cost).abs().max().item() <= 0.02 * gcost.abs().max().item()
