@@ -220,7 +220,12 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    prof_range = os.environ.get("DECNET_PROFILE_RANGE") == "1"   # ncu --profile-from-start off
+    if prof_range:
+        torch.cuda.profiler.start()
     ms = timed(step, args.steps)
+    if prof_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
