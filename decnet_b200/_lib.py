@@ -38,6 +38,7 @@ SIGNATURES = {
     "decnet_blend": (_i, [_f32p] * 5 + [_i] * 3 + [C.c_void_p]),
     "decnet_warp_bilinear": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
     "decnet_refine_pack": (_i, [_f32p] * 4 + [_i] * 4 + [C.c_void_p]),
+    "decnet_haar_level": (_i, [_f32p] * 6 + [_i] * 3 + [C.c_void_p]),
     "decnet_last_sparse_path": (_i, []),
     "decnet_set_sparse_path": (None, [_i]),
 }

@@ -308,6 +308,79 @@ warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a7: Haar wavelet lost-detail masks (utils/Wavelet.py:8-123; the reference's filter pickle is
+// absent, orthonormal Haar is used -- parity unpinned, see oracle/glue.py).  Per x2 level:
+//   haar_analysis_kernel : LL and v = max(|LH|,|HL|,|HH|) per 2x2 block, per-image min/max of v
+//   haar_count_kernel    : per image, how many normalised values are <= t_k for the 10 thresholds
+//   haar_mask_kernel     : t = first t_k with >= 85 % of the pixels below it (else 1), mask = vn >= t
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+haar_analysis_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__restrict__ v,
+                     unsigned int *__restrict__ minmax, int H, int W, int h, int w)
+{
+    const int b = blockIdx.y;
+    const long long n = (long long)h * w;
+    float lmin = INFINITY, lmax = 0.f;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const int xx = (int)(i % w), yy = (int)(i / w);
+        const float *p = x + ((size_t)b * H + 2 * yy) * W + 2 * xx;
+        const float a = p[0], bb = p[1], c = p[W], d = p[W + 1];
+        ll[(size_t)b * n + i] = (a + bb + c + d) * 0.5f;
+        const float lh = (a - bb + c - d) * 0.5f, hl = (a + bb - c - d) * 0.5f, hh = (a - bb - c + d) * 0.5f;
+        const float m = fmaxf(fmaxf(fabsf(lh), fabsf(hl)), fabsf(hh));
+        v[(size_t)b * n + i] = m;
+        lmin = fminf(lmin, m); lmax = fmaxf(lmax, m);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {       // v >= 0: the uint bit pattern orders like the float
+        atomicMin(minmax + 2 * b, __float_as_uint(lmin));
+        atomicMax(minmax + 2 * b + 1, __float_as_uint(lmax));
+    }
+}
+
+struct HaarThresholds { float t[10]; };
+
+__global__ void __launch_bounds__(kBlock)
+haar_count_kernel(const float *__restrict__ v, const unsigned int *__restrict__ minmax, HaarThresholds th,
+                  unsigned int *__restrict__ counts, long long n)
+{
+    const int b = blockIdx.y;
+    const float mn = __uint_as_float(minmax[2 * b]), mx = __uint_as_float(minmax[2 * b + 1]);
+    unsigned int c[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) c[k] = 0;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const float vn = (v[(size_t)b * n + i] - mn) / (mx - mn);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) c[k] += (vn <= th.t[k]) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        unsigned int s = c[k];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(counts + 10 * b + k, s);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+haar_mask_kernel(const float *__restrict__ v, const unsigned int *__restrict__ minmax,
+                 const unsigned int *__restrict__ counts, HaarThresholds th, float *__restrict__ mask, long long n)
+{
+    const int b = blockIdx.y;
+    const float mn = __uint_as_float(minmax[2 * b]), mx = __uint_as_float(minmax[2 * b + 1]);
+    float t = 1.0f;
+    for (int k = 0; k < 10; ++k)
+        if ((float)counts[10 * b + k] / (float)n >= 0.85f) { t = th.t[k]; break; }
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const float vn = (v[(size_t)b * n + i] - mn) / (mx - mn);
+        mask[(size_t)b * n + i] = (vn >= t) ? 1.f : 0.f;
+    }
+}
+
 static inline int grid_for(long long n, int cap = 148 * 16) {
     long long g = (n + kBlock - 1) / kBlock;
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
@@ -413,6 +486,31 @@ int decnet_refine_pack(const float *left_fea, const float *right_fea, const floa
     warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(left_fea, right_fea, disp, nullptr, out,
                                                                                           B, C, H, W);
     return after_launch("warp_kernel<pack>");
+}
+
+int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, void *workspace,
+                      const float *thresholds10, int B, int H, int W, void *stream) {
+    DECNET_REQUIRE(x && ll && detail && mask && workspace && thresholds10, "null pointer");
+    DECNET_REQUIRE(B > 0 && B <= 65535 && H >= 2 && W >= 2, "bad size B=%d H=%d W=%d", B, H, W);
+    const int h = H / 2, w = W / 2;
+    const long long n = (long long)h * w;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int *minmax = static_cast<unsigned int *>(workspace);           // [B][2]
+    unsigned int *counts = minmax + 2 * (size_t)B;                            // [B][10]
+    HaarThresholds th;
+    for (int k = 0; k < 10; ++k) th.t[k] = thresholds10[k];
+    // min slots start at +inf bits, max slots and the counters at 0
+    DECNET_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * 12 * sizeof(unsigned int), st));
+    DECNET_CUDA(cudaMemset2DAsync(minmax, 2 * sizeof(unsigned int), 0x7f, sizeof(unsigned int), B, st));
+    const int gx = grid_for(n, 148 * 4);
+    haar_analysis_kernel<<<dim3(gx, B), kBlock, 0, st>>>(x, ll, detail, minmax, H, W, h, w);
+    int rc = after_launch("haar_analysis_kernel");
+    if (rc) return rc;
+    haar_count_kernel<<<dim3(gx, B), kBlock, 0, st>>>(detail, minmax, th, counts, n);
+    rc = after_launch("haar_count_kernel");
+    if (rc) return rc;
+    haar_mask_kernel<<<dim3(gx, B), kBlock, 0, st>>>(detail, minmax, counts, th, mask, n);
+    return after_launch("haar_mask_kernel");
 }
 
 }  // extern "C"

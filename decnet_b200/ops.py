@@ -257,3 +257,26 @@ def refine_pack(left_fea, right_fea, disp):
     _call("decnet_refine_pack", left_fea, left_fea.data_ptr(), right_fea.data_ptr(), disp.data_ptr(), out.data_ptr(),
           B, Cc, H, W)
     return out
+
+
+def haar_detail_masks(x, levels):
+    """Haar lost-detail masks (row a7): x [B,1,H,W] -> ([mask_level1, ...] each [B,1,H/2^k,W/2^k], LL)."""
+    import ctypes
+    import numpy as np
+    _chk("x", x)
+    if x.dim() != 4 or x.shape[1] != 1:
+        raise ValueError("x must be [B,1,H,W]")
+    th = (ctypes.c_float * 10)(*[float(np.float32(t)) for t in (np.arange(0, 1, 0.1) + 0.1)])
+    masks, cur = [], x
+    for _ in range(int(levels)):
+        B, _, H, W = cur.shape
+        h, w = H // 2, W // 2
+        ll = torch.empty((B, 1, h, w), dtype=torch.float32, device=x.device)
+        det = torch.empty_like(ll)
+        mask = torch.empty_like(ll)
+        ws = torch.empty(B * 12, dtype=torch.int32, device=x.device)
+        _call("decnet_haar_level", cur, cur.data_ptr(), ll.data_ptr(), det.data_ptr(), mask.data_ptr(), ws.data_ptr(),
+              ctypes.cast(th, ctypes.c_void_p), B, H, W)
+        masks.append(mask)
+        cur = ll
+    return masks, cur

@@ -196,6 +196,17 @@ int decnet_warp_bilinear(const float *right_fea, const float *disp, float *warpe
 int decnet_refine_pack(const float *left_fea, const float *right_fea, const float *disp, float *out,
                        int B, int C, int H, int W, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Haar wavelet lost-detail masks (row a7; utils/Wavelet.py:8-123).  One x2 level:
+ *   x [B,1,H,W] -> ll [B,1,H/2,W/2] (next level's input), detail = max(|LH|,|HL|,|HH|),
+ *   mask = ((detail-min)/(max-min) >= t), t = first of thresholds10 with >= 85 % of the
+ *   pixels below it (else 1.0).  thresholds10 is a HOST array (float32 of
+ *   numpy.arange(0,1,.1)+.1).  workspace: device, >= 48*B bytes.
+ * The reference's filter bank (wavelet_weights_c2.pkl) is not in the repository:
+ * orthonormal Haar is used and parity for this row is UNPINNED. */
+int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, void *workspace,
+                      const float *thresholds10, int B, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,7 @@ def bicubic_skip(pred, size):
 def haar_analysis(x):
     """x [B,1,H,W] (H, W even) -> LL, LH, HL, HH each [B,1,H/2,W/2]; orthonormal Haar
     (2x2 stride-2 analysis, the `rec2` filter bank of utils/Wavelet.py:29-51)."""
+    x = x[:, :, : x.shape[2] // 2 * 2, : x.shape[3] // 2 * 2]      # stride-2 conv without padding drops an odd tail
     a = x[:, :, 0::2, 0::2]; b = x[:, :, 0::2, 1::2]
     c = x[:, :, 1::2, 0::2]; d = x[:, :, 1::2, 1::2]
     ll = (a + b + c + d) * 0.5

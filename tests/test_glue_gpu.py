@@ -151,3 +151,48 @@ def test_warp_pack_blend_vs_oracle(B, C, H, W):
     sm, fu = ops.blend(logit, dense, sparse)
     m = torch.sigmoid(logit)
     assert torch.allclose(sm, m, atol=1e-6) and torch.allclose(fu, og.blend(dense, sparse, m), atol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,W,levels", [(2, 64, 96, 3), (1, 54, 97, 2)])
+def test_haar_detail_masks_vs_oracle(B, H, W, levels):
+    """a7 (parity unpinned against the reference, see oracle/glue.py): CUDA vs the torch restatement,
+    plus perfect reconstruction of the orthonormal analysis."""
+    from decnet_b200 import ops
+    from oracle import glue as og
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.rand(B, 1, H, W, device="cuda", generator=g)
+    x = torch.nn.functional.avg_pool2d(x, 5, 1, 2) + 0.3 * (torch.rand(B, 1, H, W, device="cuda", generator=g) > 0.97)
+    masks, ll = ops.haar_detail_masks(x.contiguous(), levels)
+    wm, wll = og.haar_detail_masks(x, levels)
+    assert torch.allclose(ll, wll, atol=1e-5)
+    for a, b_ in zip(masks, wm):
+        assert a.shape == b_.shape
+        assert (a != b_).float().mean().item() <= 1e-4          # ties at the threshold are fp-order sensitive
+    a_, b2, c_, d_ = og.haar_analysis(x[:, :, : H // 2 * 2, : W // 2 * 2])
+    rec = torch.zeros_like(x[:, :, : H // 2 * 2, : W // 2 * 2])
+    rec[:, :, 0::2, 0::2] = (a_ + b2 + c_ + d_) * 0.5
+    rec[:, :, 0::2, 1::2] = (a_ - b2 + c_ - d_) * 0.5
+    rec[:, :, 1::2, 0::2] = (a_ + b2 - c_ - d_) * 0.5
+    rec[:, :, 1::2, 1::2] = (a_ - b2 - c_ + d_) * 0.5
+    assert torch.allclose(rec, x[:, :, : H // 2 * 2, : W // 2 * 2], atol=1e-5)
+
+
+def test_extension_shim_reference_calling_convention():
+    """The reference's functions/SpaMat.py:25-28 allocates zero-filled outputs and calls the pybind
+    module in place; decnet_b200.ext must honour that surface and return 1."""
+    from decnet_b200 import ext, ops
+    from helpers import make_feats, make_masks
+    L, R = make_feats(2, 24, 9, 60, device="cuda")
+    ml, mr = make_masks(2, 9, 60, 0.3, 0.3, device="cuda")
+    out, ssim, mx = (torch.zeros_like(ml) for _ in range(3))
+    assert ext.SpaMat.sparse_matching_cuda_forward(L, R, ml, mr, out, ssim, mx, 20) == 1
+    w_out, w_ssim, w_mx = ops.spamat_forward(L, R, ml, mr, 20)
+    assert torch.equal(out, w_out) and torch.equal(ssim, w_ssim) and torch.equal(mx, w_mx)
+    var, s2, m2 = (torch.zeros_like(ml) for _ in range(3))
+    assert ext.SpaVar.sparse_var_cuda_forward(L, R, ml, mr, out, var, s2, m2, 20) == 1
+    g = torch.ones_like(out)
+    dL, dR = torch.zeros_like(L), torch.zeros_like(R)
+    assert ext.SpaMat.sparse_matching_cuda_backward(L, R, ml, mr, out, ssim, mx, g, dL, dR, 20) == 1
+    assert dL.abs().sum() > 0 and dR.abs().sum() > 0
+    dL2, dR2, dd = torch.zeros_like(L), torch.zeros_like(R), torch.zeros_like(out)
+    assert ext.SpaVar.sparse_var_cuda_backward(L, R, ml, mr, out, var, s2, m2, g, dL2, dR2, dd, 20) == 1
