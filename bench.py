@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="stereo pairs per GPU per step")
     ap.add_argument("--rho", type=float, default=0.10, help="calibrated lost-detail mask density")
     ap.add_argument("--conv3d", default=os.environ.get("DECNET_CONV3D", "tcgen05"), choices=["tcgen05", "cudnn"])
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "bands"],
+                    help="pairs: shard by stereo pair (weak scaling); bands: ONE pair split into row bands "
+                         "with halo exchange over NCCL (strong scaling, BASELINE.json configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs in the bounded CPU sample")
     return ap.parse_args()
@@ -166,12 +169,19 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
     lib = _lib.lib()
 
-    model, left, right, info = build_workload(args.workload, args.batch, seed=17 + rank, device=dev, rho=args.rho,
-                                              conv3d_impl=args.conv3d)
+    bands_mode = args.mode == "bands"
+    model, left, right, info = build_workload(args.workload, args.batch, seed=17 + (0 if bands_mode else rank),
+                                              device=dev, rho=args.rho, conv3d_impl=args.conv3d)
     B = args.batch
+    if bands_mode:
+        from decnet_b200 import bands as _bands
+        transport = _bands.DistTransport() if world > 1 else _bands.LocalTransport(1)
 
-    def step():
-        return model(left, right)[0]
+        def step():
+            return _bands.forward_bands(model, left, right, transport)[rank if world > 1 else 0]
+    else:
+        def step():
+            return model(left, right)[0]
 
     # pinned host copies for the end-to-end leg
     host_l = {k: v.cpu().pin_memory() for k, v in left.items()}
@@ -186,7 +196,8 @@ def run_ours(args):
         for k in host_l:
             dev_l[k].copy_(host_l[k], non_blocking=True)
             dev_r[k].copy_(host_r[k], non_blocking=True)
-        out = model(dev_l, dev_r)[0]
+        out = (_bands.forward_bands(model, dev_l, dev_r, transport)[rank if world > 1 else 0] if bands_mode
+               else model(dev_l, dev_r)[0])
         host_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -227,13 +238,14 @@ def run_ours(args):
     if prof_range:
         torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms * 1e-3)
+    n_units = B if bands_mode else world * B          # bands: all ranks work on the SAME B pairs
+    value = n_units * args.steps / (ms * 1e-3)
 
     for _ in range(2):
         step_e2e()
     e2e_steps = max(3, args.steps // 2)
     ms_e2e = timed(step_e2e, e2e_steps)
-    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+    e2e_value = n_units * e2e_steps / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant sparse kernel (fused SpaMat+SpaVar at the finest level), measured
     # live with CUDA events on the launching stream; inputs (370 MB at B=8) exceed the 126 MB L2.
@@ -288,14 +300,17 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (sparse/glue), bf16 in / f32 acc (3-D aggregation)",
+                "scaling": "strong" if bands_mode else "weak", "vs_baseline": None,
+                "dtype": "f32 (sparse/glue), bf16 in / f32 acc (3-D aggregation)",
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload} {info['H']}x{info['W']} padded, batch {B}/GPU, max_disp {info['max_disp']}, "
                                        "full decomposition pyramid (BASELINE.json configs[1])",
                            "levels": "1/27 C216 D8 | 1/9 C72 D24 | 1/3 C24 D72 | 1/1 C8 D216",
                            "left_mask_density": info["left_mask_density"], "conv3d_impl": args.conv3d,
                            "l2": "inputs (400 MB of feature pyramids per step) exceed the 126 MB L2; no flush",
-                           "parallelism": f"by stereo pair, {world} rank(s), no collective"},
+                           "parallelism": (f"row bands of one batch over {world} rank(s): per-layer halo send/recv in the "
+                                           "3-D aggregation, all-gather of the per-level disparity") if bands_mode
+                           else f"by stereo pair, {world} rank(s), no collective"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps,
                         "note": "pinned host feature pyramids -> device, hot path, disparity -> pinned host, every step"},

@@ -61,28 +61,33 @@ __device__ __forceinline__ float sample_plane(const float *__restrict__ p, const
 template <int LAYOUT>
 __global__ void __launch_bounds__(kBlock)
 costvol_kernel(const float *__restrict__ L, const float *__restrict__ R, void *__restrict__ out,
-               int B, int C, int H, int W, int D, int Cpad)
+               int B, int C, int H, int W, int D, int Cpad, int row0, int nrows)
 {
-    const long long n = (long long)B * D * H * W;
+    // output rows are the window [row0, row0 + nrows) of the H-row volume (row-band mode); rows
+    // outside the image are written as zeros (they are the conv's zero padding)
+    const long long n = (long long)B * D * nrows * W;
     const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (idx >= n) return;
     const int w = (int)(idx % W);
-    const int h = (int)((idx / W) % H);
-    const int d = (int)((idx / ((long long)W * H)) % D);
-    const int b = (int)(idx / ((long long)W * H * D));
+    const int hl = (int)((idx / W) % nrows);
+    const int d = (int)((idx / ((long long)W * nrows)) % D);
+    const int b = (int)(idx / ((long long)W * nrows * D));
+    const int h = row0 + hl;
+    const bool in_img = h >= 0 && h < H;
+    const int hc = min(max(h, 0), H - 1);
     const float ix = sample_coord((float)w - (float)d, (float)W);
-    const float iy = sample_coord((float)h, (float)H);
+    const float iy = sample_coord((float)hc, (float)H);
     const Taps t = make_taps(ix, iy, H, W);
-    const bool left_on = w >= d;
+    const bool left_on = (w >= d) && in_img;
     const size_t plane = (size_t)H * W;
-    const float *Lb = L + (size_t)b * C * plane + (size_t)h * W + w;
+    const float *Lb = L + (size_t)b * C * plane + (size_t)hc * W + w;
     const float *Rb = R + (size_t)b * C * plane;
     if (LAYOUT == 0) {
-        float *o = static_cast<float *>(out) + (((size_t)b * C * D + d) * H + h) * W + w;
+        float *o = static_cast<float *>(out) + (((size_t)b * C * D + d) * nrows + hl) * W + w;
         for (int c = 0; c < C; ++c) {
             const float r = sample_plane(Rb + (size_t)c * plane, t, H, W);
             const float l = left_on ? __ldg(Lb + (size_t)c * plane) : 0.f;
-            o[(size_t)c * D * plane] = l * r;
+            o[(size_t)c * D * nrows * W] = l * r;
         }
     } else {
         __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out) + (size_t)idx * Cpad;
@@ -281,15 +286,18 @@ blend_kernel(const float *__restrict__ logit, const float *__restrict__ dense, c
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const float *__restrict__ disp,
-            float *__restrict__ warped, float *__restrict__ packed, int B, int C, int H, int W)
+            float *__restrict__ warped, float *__restrict__ packed, int B, int C, int H, int W,
+            int H_total, int row0)
 {
+    // H rows are the window [row0, row0 + H) of an H_total-row image (row-band mode): the vertical
+    // coordinate follows the reference's formula on GLOBAL rows; taps outside the window read 0
     const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
     const long long n = (long long)B * H * W;
     if (idx >= n) return;
     const int w = (int)(idx % W), h = (int)((idx / W) % H), b = (int)(idx / ((long long)W * H));
     const float dv = disp[idx];
     const float ix = sample_coord((float)w - dv, (float)W);
-    const float iy = sample_coord((float)h, (float)H);
+    const float iy = sample_coord((float)(row0 + h), (float)H_total) - (float)row0;
     const Taps t = make_taps(ix, iy, H, W);
     const size_t plane = (size_t)H * W;
     const size_t pix = (size_t)h * W + w;
@@ -398,19 +406,25 @@ int decnet_costvol_fwd(const float *L, const float *R, float *vol, int B, int C,
     DECNET_REQUIRE(L && R && vol, "null pointer");
     DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "non-positive size");
     const long long n = (long long)B * D * H * W;
-    costvol_kernel<0><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(L, R, vol, B, C, H, W, D, C);
+    costvol_kernel<0><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(L, R, vol, B, C, H, W, D, C, 0, H);
     return after_launch("costvol_kernel<f32>");
+}
+
+int decnet_costvol_bf16_ndhwc_rows(const float *L, const float *R, void *vol, int B, int C, int Cpad, int H, int W, int D,
+                                   int row0, int nrows, void *stream) {
+    DECNET_REQUIRE(L && R && vol, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0 && nrows > 0, "non-positive size");
+    DECNET_REQUIRE(Cpad >= C && Cpad % 8 == 0, "Cpad=%d must be >= C=%d and a multiple of 8", Cpad, C);
+    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15u) == 0, "volume must be 16-byte aligned");
+    const long long n = (long long)B * D * nrows * W;
+    costvol_kernel<1><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(L, R, vol, B, C, H, W, D, Cpad,
+                                                                                               row0, nrows);
+    return after_launch("costvol_kernel<bf16>");
 }
 
 int decnet_costvol_bf16_ndhwc(const float *L, const float *R, void *vol, int B, int C, int Cpad, int H, int W, int D,
                               void *stream) {
-    DECNET_REQUIRE(L && R && vol, "null pointer");
-    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "non-positive size");
-    DECNET_REQUIRE(Cpad >= C && Cpad % 8 == 0, "Cpad=%d must be >= C=%d and a multiple of 8", Cpad, C);
-    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15u) == 0, "volume must be 16-byte aligned");
-    const long long n = (long long)B * D * H * W;
-    costvol_kernel<1><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(L, R, vol, B, C, H, W, D, Cpad);
-    return after_launch("costvol_kernel<bf16>");
+    return decnet_costvol_bf16_ndhwc_rows(L, R, vol, B, C, Cpad, H, W, D, 0, H, stream);
 }
 
 int decnet_softargmin(const float *cost, float *pred, int B, int D, int H, int W, void *stream) {
@@ -474,18 +488,24 @@ int decnet_warp_bilinear(const float *right_fea, const float *disp, float *warpe
     DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
     const long long n = (long long)B * H * W;
     warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(nullptr, right_fea, disp, warped, nullptr,
-                                                                                          B, C, H, W);
+                                                                                          B, C, H, W, H, 0);
     return after_launch("warp_kernel");
+}
+
+int decnet_refine_pack_rows(const float *left_fea, const float *right_fea, const float *disp, float *out,
+                            int B, int C, int H, int W, int H_total, int row0, void *stream) {
+    DECNET_REQUIRE(left_fea && right_fea && disp && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
+    DECNET_REQUIRE(row0 >= 0 && row0 + H <= H_total, "row window [%d,%d) outside the %d-row image", row0, row0 + H, H_total);
+    const long long n = (long long)B * H * W;
+    warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(left_fea, right_fea, disp, nullptr, out,
+                                                                                          B, C, H, W, H_total, row0);
+    return after_launch("warp_kernel<pack>");
 }
 
 int decnet_refine_pack(const float *left_fea, const float *right_fea, const float *disp, float *out,
                        int B, int C, int H, int W, void *stream) {
-    DECNET_REQUIRE(left_fea && right_fea && disp && out, "null pointer");
-    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
-    const long long n = (long long)B * H * W;
-    warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(left_fea, right_fea, disp, nullptr, out,
-                                                                                          B, C, H, W);
-    return after_launch("warp_kernel<pack>");
+    return decnet_refine_pack_rows(left_fea, right_fea, disp, out, B, C, H, W, H, 0, stream);
 }
 
 int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, void *workspace,

@@ -132,6 +132,13 @@ int decnet_costvol_fwd(const float *left_fea, const float *right_fea, float *vol
 int decnet_costvol_bf16_ndhwc(const float *left_fea, const float *right_fea, void *vol_bf16,
                               int B, int C, int Cpad, int H, int W, int D, void *stream);
 
+/* Row-band variant (single huge pair split across GPUs): writes only the
+ * rows [row0, row0+nrows) of the H-row volume -> [B,D,nrows,W,Cpad]; rows outside the image
+ * (row0 < 0 or beyond H) are zeros, i.e. the aggregation's zero padding / halo slots. */
+int decnet_costvol_bf16_ndhwc_rows(const float *left_fea, const float *right_fea, void *vol_bf16,
+                                   int B, int C, int Cpad, int H, int W, int D,
+                                   int row0, int nrows, void *stream);
+
 /* pred[b,h,w] = sum_d softmax_d(cost[b,:,h,w]) * d.  Replaces disparity_regression
  * (modules/submodule.py:766-777) for integer candidates 0..D-1. */
 int decnet_softargmin(const float *cost, float *pred, int B, int D, int H, int W, void *stream);
@@ -206,6 +213,12 @@ int decnet_refine_pack(const float *left_fea, const float *right_fea, const floa
  * orthonormal Haar is used and parity for this row is UNPINNED. */
 int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, void *workspace,
                       const float *thresholds10, int B, int H, int W, void *stream);
+
+/* Row-band variant of decnet_refine_pack: the tensors hold the H rows [row0, row0+H) of an
+ * H_total-row image; the vertical sampling coordinate uses GLOBAL rows (the reference's
+ * y' = h*H/(H-1) - 1/2 depends on them), taps outside the window read 0. */
+int decnet_refine_pack_rows(const float *left_fea, const float *right_fea, const float *disp, float *out,
+                            int B, int C, int H, int W, int H_total, int row0, void *stream);
 
 #ifdef __cplusplus
 }

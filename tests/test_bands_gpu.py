@@ -1,0 +1,52 @@
+"""GPU: row-band execution (all ranks simulated in one process, LocalTransport) against the
+single-device pipeline on the same pair.  The multi-process NCCL transport is exercised by
+`bench.py --mode bands` under torchrun."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(H, W, max_disp, skip, use_detail, seed=31, B=1):
+    from decnet_b200.model import DecompMatching
+    from decnet_b200.params import make_features, make_hotpath_state
+    torch.backends.cudnn.allow_tf32 = False
+    m = DecompMatching(max_disp=max_disp, skip_stage_id=skip, use_detail=use_detail, thold=0.6)
+    m.load_state_dict(make_hotpath_state(seed))
+    m = m.cuda()
+    left, right = make_features(B, H, W, seed=seed, device="cuda")
+    g = torch.Generator().manual_seed(seed + 1)
+    lm = [(torch.rand(B, H // f, W // f, generator=g) < 0.2).float().cuda() for f in (9, 3, 1)]
+    rm = [(torch.rand(B, H // f, W // f, generator=g) < 0.2).float().cuda() for f in (9, 3, 1)]
+    return m, left, right, lm, rm
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("H,W,max_disp,skip,use_detail", [(162, 108, 216, 4, False), (162, 135, 243, 3, True),
+                                                           (243, 108, 216, 4, True)])
+def test_bands_match_single_device(world, H, W, max_disp, skip, use_detail):
+    from decnet_b200 import bands
+    m, left, right, lm, rm = _build(H, W, max_disp, skip, use_detail)
+    want, taps = m(left, right, lm, rm, is_check=True)
+    tr = bands.LocalTransport(world)
+    full = bands.forward_bands(m, left, right, tr, lm, rm)
+    for r in range(world):
+        got = full[r]
+        assert got.shape == want.shape
+        scale = float(want.abs().max())
+        err = float((got - want).abs().max())
+        assert err <= 1e-3 + 2e-3 * scale, (r, err, scale)
+        assert float((got - want).abs().mean()) <= 1e-3 + 1e-4 * scale
+
+
+def test_dense_stage_bands_bit_exact():
+    """The banded 3-D aggregation (halo rows exchanged after every layer) reproduces the full-volume
+    result exactly: same kernel, same K order, halo values == the neighbour's owned rows."""
+    from decnet_b200 import bands
+    m, left, right, lm, rm = _build(243, 108, 216, 4, False)
+    want, _ = m.dense_stage(left["stage0"], right["stage0"], 8)
+    for world in (2, 3, 4):
+        tr = bands.LocalTransport(world)
+        pred = bands._dense_stage_bands(m, left["stage0"], right["stage0"], 8, tr)
+        got = torch.cat([pred[r] for r in range(world)], dim=1)
+        assert torch.equal(got, want), (world, (got - want).abs().max())
