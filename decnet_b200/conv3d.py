@@ -97,10 +97,23 @@ def measure_roofline(model, Lf, Rf, D, peaks, iters=10):
     for _ in range(3):
         run_stack(reg, vol)
     torch.cuda.synchronize()
+    # the 8 launches are captured in a CUDA graph so that the device time is measured, not the host's
+    # launch path (8 ctypes calls + tensor-map lookups per stack)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run_stack(reg, vol)
+        with torch.cuda.graph(graph, stream=side):
+            run_stack(reg, vol)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        run_stack(reg, vol)
+        graph.replay()
     e1.record(); torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / iters
     B, _, H, W = Lf.shape

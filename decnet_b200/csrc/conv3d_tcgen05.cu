@@ -26,11 +26,12 @@
 #include "tma_utils.cuh"
 #include <cuda_bf16.h>
 #include <cstring>
+#include <mutex>
 
 namespace decnet {
 namespace conv3d {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 channels per stage row = 128 bytes
@@ -55,6 +56,67 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Warp-converged variants: every lane executes the statement with warp-uniform operands and
+// elect.sync picks the single issuing lane INSIDE the asm block.  This keeps the descriptors in
+// uniform registers; issuing from a divergent `if (lane == 0)` region makes nvcc wrap every
+// UTCHMMA in an ELECT/BRA.U.ANY loop with R2UR moves (~140 cycles per MMA instead of ~40).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// One stage = `KSTEPS` K-steps of 16 (32 bytes each inside the 128-byte swizzle row = +2 in the
+// descriptor's 16-byte address field) followed by the commit that releases the stage: a single
+// asm block with ONE elect.sync, so the issuing warp's dependent instruction chain per stage stays
+// well below the 4 x 112 cycles the tensor pipe needs for it.
+#define DECNET_MMA_NEXT(OFF)                                                       \
+        "add.u64 a, %1, " #OFF ";\n\t"                                              \
+        "add.u64 b, %2, " #OFF ";\n\t"                                              \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+#define DECNET_STAGE_HEAD                                                          \
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b;\n\t"                            \
+        "elect.sync _|e, 0xffffffff;\n\t"                                           \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                 \
+        "setp.eq.b32 t, 0, 0;\n\t"                                                  \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+#define DECNET_STAGE_TAIL                                                          \
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+template <int KSTEPS>
+__device__ __forceinline__ void umma_stage_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate_first, uint32_t bar_addr) {
+    static_assert(KSTEPS >= 1 && KSTEPS <= 4, "1..4 K-steps per stage");
+    if constexpr (KSTEPS == 4) {
+        asm volatile(DECNET_STAGE_HEAD DECNET_MMA_NEXT(2) DECNET_MMA_NEXT(4) DECNET_MMA_NEXT(6) DECNET_STAGE_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    } else if constexpr (KSTEPS == 3) {
+        asm volatile(DECNET_STAGE_HEAD DECNET_MMA_NEXT(2) DECNET_MMA_NEXT(4) DECNET_STAGE_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    } else if constexpr (KSTEPS == 2) {
+        asm volatile(DECNET_STAGE_HEAD DECNET_MMA_NEXT(2) DECNET_STAGE_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    } else {
+        asm volatile(DECNET_STAGE_HEAD DECNET_STAGE_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit_addr_elect(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -84,16 +146,19 @@ struct Params {
     int cp, np;                        // padded in / out channels
     int nchunks, last_ksteps;          // ceil(cp/64), K-steps of 16 in the last chunk
     int bw, bh, bd, tw, th, td;        // tile box and tiles per axis
-    int relu, mode, tmem_cols;
+    int relu, mode, tmem_cols;         // tmem_cols = 2 accumulator slots
+    int num_tiles, stages;
+    long long *dbg;                    // optional per-CTA timing (decnet_conv3d_debug_timing), else null
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ __align__(8) uint64_t empty_bar[kStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,19 +166,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.np * kChunkK * 2;
     const int stage_bytes = kABytes + b_bytes;
-
-    // tile -> origin in the volume
-    int t = blockIdx.x;
-    const int twi = t % p.tw; t /= p.tw;
-    const int thi = t % p.th; t /= p.th;
-    const int tdi = t % p.td; t /= p.td;
-    const int b = t;
-    const int w0 = twi * p.bw, h0 = thi * p.bh, d0 = tdi * p.bd;
+    const int kStages = p.stages;
+    const int acc_stride = p.tmem_cols >> 1;              // two accumulator slots (double buffering)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -125,89 +184,147 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    const int total_iters = 27 * p.nchunks;
+    const int iters_per_tile = 27 * p.nchunks;
 
+    // Persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and the
+    // two TMEM accumulator slots keep rolling across tiles, so the epilogue of tile j overlaps the
+    // main loop of tile j+1.
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int it = 0;
-            for (int tap = 0; tap < 27; ++tap) {
-                const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-                for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    unsigned char *sa = base + (size_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                    tma_load_5d(sa, &tmA, ck * kChunkK, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, &full_bar[s]);
-                    tma_load_3d(sa + kABytes, &tmB, ck * kChunkK, 0, tap, &full_bar[s]);
-                }
+            int s = 0; uint32_t ph = 0;                   // ring slot / phase, advanced without divisions
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int w0 = (t % p.tw) * p.bw; t /= p.tw;
+                const int h0 = (t % p.th) * p.bh; t /= p.th;
+                const int d0 = (t % p.td) * p.bd; t /= p.td;
+                const int b = t;
+                int tap = 0;
+                for (int kd = 0; kd < 3; ++kd)
+                    for (int kh = 0; kh < 3; ++kh)
+                        for (int kw = 0; kw < 3; ++kw, ++tap)
+                            for (int ck = 0; ck < p.nchunks; ++ck) {
+                                mbar_wait(&empty_bar[s], ph ^ 1u);
+                                unsigned char *sa = base + (size_t)s * stage_bytes;
+                                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                                tma_load_5d(sa, &tmA, ck * kChunkK, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, &full_bar[s]);
+                                tma_load_3d(sa + kABytes, &tmB, ck * kChunkK, 0, tap, &full_bar[s]);
+                                if (++s == kStages) { s = 0; ph ^= 1u; }
+                            }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+        {
             const uint32_t idesc = make_idesc_bf16_f32(kTileM, p.np);
-            int it = 0;
-            for (int tap = 0; tap < 27; ++tap) {
-                for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
-                    const uint64_t da = make_smem_desc_sw128(sa);
-                    const uint64_t db = make_smem_desc_sw128(sa + kABytes);
-                    const int ksteps = (ck == p.nchunks - 1) ? p.last_ksteps : (kChunkK / 16);
-                    for (int k = 0; k < ksteps; ++k) {
-                        // +32 bytes along K inside the 128-byte swizzle row = +2 in the 16-byte address field
-                        umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                  (it > 0 || k > 0) ? 1u : 0u);
+            int it = 0, j = 0;
+            int s = 0; uint32_t ph = 0;                   // ring slot / phase, advanced without divisions
+            const uint32_t smem_base = smem_u32(base);
+            const uint32_t empty_base = smem_u32(&empty_bar[0]);
+            bool ready = false;
+            long long t_begin = clock64(), t_wait = 0;
+            unsigned long long ns_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+                const int slot = j & 1;
+                mbar_wait(&tmem_empty_bar[slot], ((uint32_t)(j >> 1) & 1u) ^ 1u);   // epilogue drained this slot
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
+                uint32_t first = 1u;
+                const int last_ck = p.nchunks - 1;
+                for (int tap = 0; tap < 27; ++tap) {
+                    for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
+                        // `ready` was probed one stage ahead (the probe's latency hides behind the MMA issue)
+                        if (!ready) {
+                            if (p.dbg) { const long long w0_ = clock64(); mbar_wait(&full_bar[s], ph); t_wait += clock64() - w0_; }
+                            else mbar_wait(&full_bar[s], ph);
+                        }
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
+                        const uint64_t da = make_smem_desc_sw128(sa);
+                        const uint64_t db = make_smem_desc_sw128(sa + kABytes);
+                        const uint32_t ebar = empty_base + (uint32_t)(s * 8);
+                        int sn = s + 1; uint32_t phn = ph;
+                        if (sn == kStages) { sn = 0; phn ^= 1u; }
+                        ready = mbar_try_wait(&full_bar[sn], phn);       // probe the NEXT stage now
+                        // K-steps of the stage + the commit that frees it: one asm block, one elect.sync
+                        if (ck != last_ck) umma_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar);
+                        else switch (p.last_ksteps) {
+                            case 4: umma_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                            case 3: umma_stage_elect<3>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                            case 2: umma_stage_elect<2>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                            default: umma_stage_elect<1>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                        }
+                        first = 0u;
+                        s = sn; ph = phn;
                     }
-                    umma_commit(&empty_bar[s]);           // frees the stage once these MMAs have read it
                 }
+                umma_commit_elect(&tmem_full_bar[slot]);  // accumulator of this tile complete
             }
-            umma_commit(&tmem_full_bar);                  // accumulator complete
+            if (p.dbg && lane == 0) {
+                unsigned long long ns_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+                p.dbg[4 * blockIdx.x + 0] = clock64() - t_begin;     // cycles the issuer was alive
+                p.dbg[4 * blockIdx.x + 1] = t_wait;                  // cycles blocked on full barriers
+                p.dbg[4 * blockIdx.x + 2] = (long long)(ns_end - ns_begin);
+                p.dbg[4 * blockIdx.x + 3] = it;
+            }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                      // accumulator row = voxel within the tile
         const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dd = r / (p.bw * p.bh);
-        const int w = w0 + dw, h = h0 + dh, d = d0 + dd;
-        const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
-        const size_t m = (((size_t)b * p.D + d) * p.H + h) * p.W + w;
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (p.mode == 1) {
-            float v[16];
-            tmem_ld16(trow, v);
-            if (valid) { float x = v[0] + p.bias[0]; if (p.relu) x = fmaxf(x, 0.f); p.out_f32[m] = x; }
-        } else {
-            for (int c0 = 0; c0 < p.np; c0 += 16) {
+        int j = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+            int t = tile;
+            const int w = (t % p.tw) * p.bw + dw; t /= p.tw;
+            const int h = (t % p.th) * p.bh + dh; t /= p.th;
+            const int d = (t % p.td) * p.bd + dd; t /= p.td;
+            const int b = t;
+            const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
+            const size_t m = (((size_t)b * p.D + d) * p.H + h) * p.W + w;
+            const int slot = j & 1;
+            mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * acc_stride);
+            if (p.mode == 1) {
                 float v[16];
-                tmem_ld16(trow + (uint32_t)c0, v);        // warp-collective: every lane takes part
-                if (valid) {
-                    __align__(16) __nv_bfloat16 o[16];
-                    __align__(16) __nv_bfloat16 rs[16];
-                    if (p.residual) {
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + m * p.np + c0);
-                        *reinterpret_cast<uint4 *>(rs) = __ldg(rp);
-                        *reinterpret_cast<uint4 *>(rs + 8) = __ldg(rp + 1);
-                    }
+                tmem_ld16(trow, v);
+                if (valid) { float x = v[0] + p.bias[0]; if (p.relu) x = fmaxf(x, 0.f); p.out_f32[m] = x; }
+            } else {
+                for (int c0 = 0; c0 < p.np; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + (uint32_t)c0, v);    // warp-collective: every lane takes part
+                    if (valid) {
+                        __align__(16) __nv_bfloat16 o[16];
+                        __align__(16) __nv_bfloat16 rs[16];
+                        if (p.residual) {
+                            const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + m * p.np + c0);
+                            *reinterpret_cast<uint4 *>(rs) = __ldg(rp);
+                            *reinterpret_cast<uint4 *>(rs + 8) = __ldg(rp + 1);
+                        }
+                        const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float x = v[i] + __ldg(p.bias + c0 + i);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        if (p.residual) x += __bfloat162float(rs[i]);
-                        o[i] = __float2bfloat16(x);
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 bv = __ldg(bp + i4);
+                            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float x = v[4 * i4 + i] + bb[i];
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                if (p.residual) x += __bfloat162float(rs[4 * i4 + i]);
+                                o[4 * i4 + i] = __float2bfloat16(x);
+                            }
+                        }
+                        uint4 *op = reinterpret_cast<uint4 *>(p.out_bf16 + m * p.np + c0);
+                        op[0] = *reinterpret_cast<const uint4 *>(o);
+                        op[1] = *reinterpret_cast<const uint4 *>(o + 8);
                     }
-                    uint4 *op = reinterpret_cast<uint4 *>(p.out_bf16 + m * p.np + c0);
-                    op[0] = *reinterpret_cast<const uint4 *>(o);
-                    op[1] = *reinterpret_cast<const uint4 *>(o + 8);
                 }
             }
+            // this warp has read its lanes of the slot: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
         }
     }
     tc_fence_before();
@@ -216,7 +333,6 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
-    (void)total_iters;
 }
 
 // pick the (bw, bh, bd) power-of-two box with bw*bh*bd = 128 that wastes the fewest voxels
@@ -241,6 +357,9 @@ using namespace decnet::conv3d;
 
 extern "C" {
 
+static thread_local long long *g_conv3d_dbg = nullptr;
+void decnet_conv3d_debug_timing(void *dbg_buffer) { g_conv3d_dbg = static_cast<long long *>(dbg_buffer); }
+
 int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *bias, const void *residual,
                        void *out, int out_mode, int B, int D, int H, int W, int cp, int np, int relu, void *stream)
 {
@@ -263,7 +382,7 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
     pick_tile(W, H, D, p.bw, p.bh, p.bd);
     p.tw = (W + p.bw - 1) / p.bw; p.th = (H + p.bh - 1) / p.bh; p.td = (D + p.bd - 1) / p.bd;
     p.relu = relu; p.mode = out_mode;
-    p.tmem_cols = np <= 32 ? 32 : np <= 64 ? 64 : np <= 128 ? 128 : 256;
+    p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;   // 2 slots
 
     CUtensorMap tmA, tmB;
     {
@@ -283,11 +402,29 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)kStages * (kABytes + (size_t)np * kChunkK * 2) + 1024;
-    DECNET_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t stage_bytes = kABytes + (size_t)np * kChunkK * 2;
+    p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    DECNET_REQUIRE(p.stages >= 2, "stage too large");
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    {   // raise the dynamic smem limit once per device and size (the call costs host time on every launch)
+        static std::mutex mu;
+        static size_t set_for[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || set_for[dev] < smem) {
+            DECNET_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) set_for[dev] = smem;
+        }
+    }
     const long long tiles = (long long)B * p.tw * p.th * p.td;
     DECNET_REQUIRE(tiles < (1ll << 31), "too many tiles");
-    conv3d_tcgen05_kernel<<<(unsigned)tiles, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+    p.num_tiles = (int)tiles;
+    p.dbg = g_conv3d_dbg;
+    const int sms = sm_count_cached();
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);       // persistent: one CTA per SM
+    conv3d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
     return after_launch("conv3d_tcgen05_kernel");
 }
 

@@ -26,6 +26,7 @@
 #include "sparse_core.cuh"
 #include "tma_utils.cuh"
 #include <cstring>
+#include <mutex>
 
 namespace decnet {
 namespace sparse {
@@ -380,7 +381,17 @@ static int launch_forward(const TileGeom &g, const float *L, const float *R, con
         if (rc) return rc;
     }
     auto kern = sparse_row_kernel<MODE, USE_TMA>;
-    DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    {   // once per (instantiation, device, size): the attribute call costs host time on every launch
+        static std::mutex mu;
+        static size_t set_for[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || set_for[dev] < g.smem) {
+            DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+            if (dev >= 0 && dev < 64) set_for[dev] = g.smem;
+        }
+    }
     const int vec_ok = (W % 4 == 0) && aligned16(L) && aligned16(R) && aligned16(out_a) && aligned16(ssim) &&
                        aligned16(mx) && (MODE != MODE_FUSED || aligned16(out_b));
     kern<<<dim3(H, B), kThreads, g.smem, st>>>(tmL, tmR, L, R, ml, mr, disp, out_a, out_b, ssim, mx, C, H, W, D,

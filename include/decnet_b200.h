@@ -155,6 +155,11 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
                        const void *residual, void *out, int out_mode,
                        int B, int D, int H, int W, int cp, int np, int relu, void *stream);
 
+/* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
+ * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
+ * pass NULL to disable (default). */
+void decnet_conv3d_debug_timing(void *dbg_buffer);
+
 /* ------------------------------------------------------------------------- *
  * Lost-detail mask selection (row a6).
  *   m = p > thold ? 1 : (p <= thold ? 0 : p)  for the left and right maps [B,H,W];
