@@ -27,6 +27,8 @@ from . import ops
 from .modules import SpaMat, SpaVar
 
 BN_EPS = 1e-5
+# direct sm_100a kernels for the tiny-channel 2-D convs (section 8f rank 1); False = cuDNN everywhere
+USE_NATIVE_CONV2D = True
 
 
 # --------------------------------------------------------------------------------------
@@ -55,10 +57,30 @@ class Conv2dUnit(nn.Module):
             self._folded = (w.contiguous(), b.contiguous())
         return self._folded
 
-    def forward(self, x):
+    def native(self):
+        """Packed weights for the direct-conv kernel when this layer is one of its shapes (else None)."""
+        c = self.conv
+        k, d = c.kernel_size[0], c.dilation[0]
+        ok = (c.kernel_size[0] == c.kernel_size[1] and c.stride == (1, 1) and c.dilation[0] == c.dilation[1]
+              and c.padding == (d * (k // 2), d * (k // 2)) and c.groups == 1
+              and ops.conv2d_small_supported(c.in_channels, c.out_channels, k))
+        if not ok:
+            return None
+        if getattr(self, "_native", None) is None or self._native[0] is not self._folded:
+            w, b = self.folded()
+            self._native = (self._folded, ops.pack_conv2d_weights(w), b.float().contiguous())
+        return self._native
+
+    def forward(self, x, addend=None):
+        nat = self.native() if (x.is_cuda and x.dtype == torch.float32 and USE_NATIVE_CONV2D) else None
+        if nat is not None:
+            c = self.conv
+            return ops.conv2d_small(x.contiguous(), nat[1], nat[2], c.out_channels, c.kernel_size[0], c.dilation[0],
+                                    self.relu, addend)
         w, b = self.folded()
         x = F.conv2d(x, w, b, stride=self.conv.stride, padding=self.conv.padding, dilation=self.conv.dilation)
-        return F.relu_(x) if self.relu else x
+        x = F.relu_(x) if self.relu else x
+        return x if addend is None else x + addend.unsqueeze(1)
 
 
 class Deconv2dUnit(nn.Module):
@@ -69,6 +91,10 @@ class Deconv2dUnit(nn.Module):
         self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=stride, bias=True)
 
     def forward(self, x):
+        c = self.conv
+        if (USE_NATIVE_CONV2D and x.is_cuda and x.dtype == torch.float32 and c.kernel_size == (3, 3)
+                and c.stride == (3, 3) and c.out_channels == 8 and c.padding == (0, 0)):
+            return ops.deconv3x3s3(x.contiguous(), c.weight.detach().contiguous(), c.bias.detach().contiguous(), True)
         return F.relu_(self.conv(x))
 
 
@@ -92,6 +118,8 @@ def _reset_folded(module):
             m._folded = None
         if hasattr(m, "_packed"):
             m._packed = None
+        if hasattr(m, "_native"):
+            m._native = None
 
 
 # --------------------------------------------------------------------------------------
@@ -271,7 +299,9 @@ class Refinement(nn.Module):
     def forward(self, left_fea, right_fea, disp_map):
         disp_map = disp_map.contiguous()
         x = ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map)
-        residual = self.conv(x).squeeze(1)
+        for unit in list(self.conv)[:-1]:
+            x = unit(x)
+        residual = self.conv[-1](x).squeeze(1)
         return disp_map + residual, residual
 
 

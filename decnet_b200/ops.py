@@ -280,3 +280,41 @@ def haar_detail_masks(x, levels):
         masks.append(mask)
         cur = ll
     return masks, cur
+
+
+# --------------------------------------------------------------------------------------
+# tiny-channel 2-D convolutions (section 8f rank 1)
+# --------------------------------------------------------------------------------------
+def conv2d_small_supported(cin, cout, ksize):
+    return bool(_lib.lib().decnet_conv2d_small_supported(int(cin), int(cout), int(ksize)))
+
+
+def pack_conv2d_weights(w):
+    """[Cout,Cin,k,k] -> [Cin][k*k][CoutP] fp32 (CoutP = Cout rounded up to 4)."""
+    cout, cin, k, _ = w.shape
+    coutp = (cout + 3) // 4 * 4
+    out = torch.zeros((cin, k * k, coutp), dtype=torch.float32, device=w.device)
+    out[:, :, :cout] = w.float().permute(1, 2, 3, 0).reshape(cin, k * k, cout)
+    return out.contiguous()
+
+
+def conv2d_small(x, w_packed, bias, cout, ksize, dilation=1, relu=False, addend=None):
+    _chk("x", x)
+    B, cin, H, W = x.shape
+    out = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
+    if addend is not None:
+        _chk("addend", addend, x, (B, H, W))
+    _call("decnet_conv2d_small", x, x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(),
+          addend.data_ptr() if addend is not None else None, out.data_ptr(), B, cin, H, W, int(cout), int(ksize),
+          int(dilation), 1 if relu else 0)
+    return out
+
+
+def deconv3x3s3(x, w, bias, relu=True):
+    _chk("x", x)
+    B, cin, h, wd = x.shape
+    cout = w.shape[1]
+    out = torch.empty((B, cout, 3 * h, 3 * wd), dtype=torch.float32, device=x.device)
+    _call("decnet_deconv3x3s3", x, x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, cin, h, wd, cout,
+          1 if relu else 0)
+    return out

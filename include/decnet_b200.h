@@ -225,6 +225,23 @@ int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, voi
 int decnet_refine_pack_rows(const float *left_fea, const float *right_fea, const float *disp, float *out,
                             int B, int C, int H, int W, int H_total, int row0, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Tiny-channel 2-D convolutions of the per-level stacks (SURVEY.md section 8f rank 1;
+ * modules/submodule.py:351-364 GenerateSparseMask, :596-600 SoftAttention, :677-716 Refinement).
+ *   out[b,co,y,x] = act(bias[co] + sum_{ci,ky,kx} x[b,ci,y+(ky-1)*dil,x+(kx-1)*dil] * w[co,ci,ky,kx]) [+ addend[b,y,x]]
+ * NCHW fp32, stride 1, zero padding dil*(k/2), k in {1,3}; BatchNorm(eval) is folded into w / bias
+ * by the caller.  w_packed is [Cin][k*k][CoutP] (CoutP = Cout rounded up to 4, zero padded).
+ * Supported shapes: decnet_conv2d_small_supported(); `addend` (single-channel outputs only, may be
+ * NULL) is added after the activation (Refinement: disp + residual, submodule.py:761). */
+int decnet_conv2d_small_supported(int Cin, int Cout, int ksize);
+int decnet_conv2d_small(const float *x, const float *w_packed, const float *bias, const float *addend, float *out,
+                        int B, int Cin, int H, int W, int Cout, int ksize, int dilation, int relu, void *stream);
+
+/* ConvTranspose2d(kernel 3, stride 3) + bias + ReLU (GenerateSparseMask.deconv.0, submodule.py:350-351):
+ * x [B,Cin,h,w], w [Cin,Cout,3,3] (PyTorch layout), out [B,Cout,3h,3w]; Cout must be 8. */
+int decnet_deconv3x3s3(const float *x, const float *w, const float *bias, float *out,
+                       int B, int Cin, int h, int w_in, int Cout, int relu, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
