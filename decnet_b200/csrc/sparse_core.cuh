@@ -181,7 +181,7 @@ template <int G> __device__ __forceinline__ double gsum(double v) {
 //   MODE_MAT   g_a = out
 //   MODE_VAR   g_a = var around disp_row[w]
 //   MODE_FUSED g_a = out, g_b = var around out
-template <int MODE, int G, bool RC>
+template <int MODE, int G, int VAR>
 __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__restrict__ Ls,
                                               const float *__restrict__ Rs, int cs, int C, int Cp, int D,
                                               const float *__restrict__ disp_row,
@@ -192,6 +192,8 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
     constexpr int LG = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
     const int t = tid & (G - 1);
     const int gid = tid >> LG, nG = nthreads >> LG;
+    constexpr bool RC = VAR >= 1;          // right columns compacted to Rc[j][Cp]
+    constexpr bool LC = VAR >= 2;          // masked left pixels compacted to Lc[i][Cp] (passed in Ls)
     const int nL = s.counts[0];
     const int C4 = C >> 2;
 
@@ -207,7 +209,8 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
         }
         float m = kEps6;
         double S0 = 0.0, S1 = 0.0, S2 = 0.0;
-        const float *lp = Ls + lw;
+        const float *lp = LC ? Ls + (act ? i : 0) * Cp : Ls + lw;
+        const int lcs = LC ? 1 : cs;          // channel stride of the left operand
 
         for (int jb = lo + t; jb < hi; jb += KU * G) {
             int ro[KU], dk[KU];
@@ -224,8 +227,14 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
             // the reference's sequential FMA chain over channels, KU independent chains
             if (RC) {
                 for (int c4 = 0; c4 < C4; ++c4) {
-                    const float l0 = lp[(4 * c4 + 0) * cs], l1 = lp[(4 * c4 + 1) * cs];
-                    const float l2 = lp[(4 * c4 + 2) * cs], l3 = lp[(4 * c4 + 3) * cs];
+                    float l0, l1, l2, l3;
+                    if (LC) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(lp + 4 * c4);
+                        l0 = lv.x; l1 = lv.y; l2 = lv.z; l3 = lv.w;
+                    } else {
+                        l0 = lp[(4 * c4 + 0) * cs]; l1 = lp[(4 * c4 + 1) * cs];
+                        l2 = lp[(4 * c4 + 2) * cs]; l3 = lp[(4 * c4 + 3) * cs];
+                    }
 #pragma unroll
                     for (int k = 0; k < KU; ++k) {
                         const float4 r = *reinterpret_cast<const float4 *>(Rs + ro[k] + 4 * c4);
@@ -236,7 +245,7 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
                     }
                 }
                 for (int c = 4 * C4; c < C; ++c) {
-                    const float l = lp[c * cs];
+                    const float l = lp[c * lcs];
 #pragma unroll
                     for (int k = 0; k < KU; ++k) cost[k] = fmaf(l, Rs[ro[k] + c], cost[k]);
                 }
@@ -254,14 +263,15 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
 #pragma unroll
             for (int k = 0; k < KU; ++k) if (jb + k * G < hi) mk = fmaxf(mk, cost[k]);
             if (mk > m) {
-                const double sc = (double)expf(m - mk);
+                const double sc = (double)__expf(m - mk);
                 S0 *= sc; S1 *= sc; if (MODE != MODE_MAT) S2 *= sc;
                 m = mk;
             }
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
                 if (jb + k * G < hi) {
-                    const double e = (double)expf(cost[k] - m);
+                    // ex2.approx(x*log2e): rel. error ~2e-7 (+6e-8*|x|), far inside the 1e-3 abs gate on disparities
+                    const double e = (double)__expf(cost[k] - m);
                     const double dd = (double)dk[k];
                     S0 += e;
                     const double ed = e * dd;
@@ -273,7 +283,7 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
         // merge the G lanes of the group
         if (G > 1) {
             const float mg = gmax<G>(m);
-            const double sc = (double)expf(m - mg);
+            const double sc = (double)__expf(m - mg);
             S0 = gsum<G>(S0 * sc);
             S1 = gsum<G>(S1 * sc);
             if (MODE != MODE_MAT) S2 = gsum<G>(S2 * sc);
@@ -298,12 +308,12 @@ __device__ __forceinline__ void process_row_g(const RowSmem &s, const float *__r
     }
 }
 
-template <int MODE, bool RC>
+template <int MODE, int VAR>
 __device__ inline void process_row(const RowSmem &s, const float *Ls, const float *Rs, int cs, int C, int Cp,
                                    int D, const float *disp_row, float *g_a, float *g_b,
                                    float *g_ssim, float *g_max, int tid, int nthreads)
 {
-#define DECNET_PR(GG) process_row_g<MODE, GG, RC>(s, Ls, Rs, cs, C, Cp, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads)
+#define DECNET_PR(GG) process_row_g<MODE, GG, VAR>(s, Ls, Rs, cs, C, Cp, D, disp_row, g_a, g_b, g_ssim, g_max, tid, nthreads)
     switch (s.counts[2]) {
         case 0: DECNET_PR(1); break;
         case 1: DECNET_PR(2); break;
@@ -315,18 +325,17 @@ __device__ inline void process_row(const RowSmem &s, const float *Ls, const floa
 #undef DECNET_PR
 }
 
-// Transpose the VALID right columns of the staged slab into Rc[j][Cp] (j = list index).
-__device__ inline void gather_right_columns(const RowSmem &s, const float *__restrict__ Rs, int cs, int C, int Cp,
-                                            float *__restrict__ Rc, int tid, int nthreads)
+// Transpose the listed (valid right / masked left) columns of a staged slab into Rc[j][Cp] (j = list index).
+__device__ inline void gather_columns(const uint32_t *__restrict__ list, int nR, const float *__restrict__ Rs,
+                                      int cs, int C, int Cp, float *__restrict__ Rc, int tid, int nthreads)
 {
-    const int nR = s.counts[1];
     const int q4 = Cp >> 2;
     const uint32_t magic = 0xffffffffu / (uint32_t)q4 + 1u;      // idx / q4, exact for idx < 2^16 * q4
     const int total = nR * q4;
     for (int idx = tid; idx < total; idx += nthreads) {
         const int j = (q4 == 1) ? idx : (int)__umulhi((uint32_t)idx, magic);
         const int q = idx - j * q4;
-        const int off = (int)(s.rlist[j] >> 16);
+        const int off = (int)(list[j] >> 16);
         const int c = 4 * q;
         float4 v;
         v.x = Rs[(c + 0) * cs + off];

@@ -120,14 +120,22 @@ sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
     // 3. costs / softmax regression / variance for every masked pixel, stored straight to global
     const int cs = USE_TMA ? bw : Wp;
     const float *disp_row = MODE == MODE_VAR ? disp_in + m0 : nullptr;
-    if (nR * Cp <= rc_cap) {
-        gather_right_columns(s, Rs, cs, C, Cp, Rc, tid, kThreads);
+    if ((nR + nL) * Cp <= rc_cap) {
+        // both operands compacted: Rc[j][Cp] for the valid right columns, Lc[i][Cp] for the masked left pixels
+        float *Lc = Rc + nR * Cp;
+        gather_columns(s.rlist, nR, Rs, cs, C, Cp, Rc, tid, kThreads);
+        gather_columns(s.llist, nL, Ls, cs, C, Cp, Lc, tid, kThreads);
         __syncthreads();
-        process_row<MODE, true>(s, Ls, Rc, cs, C, Cp, D, disp_row,
-                                out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+        process_row<MODE, 2>(s, Lc, Rc, cs, C, Cp, D, disp_row,
+                             out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+    } else if (nR * Cp <= rc_cap) {
+        gather_columns(s.rlist, nR, Rs, cs, C, Cp, Rc, tid, kThreads);
+        __syncthreads();
+        process_row<MODE, 1>(s, Ls, Rc, cs, C, Cp, D, disp_row,
+                             out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
     } else {
-        process_row<MODE, false>(s, Ls, Rs, cs, C, Cp, D, disp_row,
-                                 out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+        process_row<MODE, 0>(s, Ls, Rs, cs, C, Cp, D, disp_row,
+                             out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
     }
 }
 
