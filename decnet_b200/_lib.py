@@ -33,6 +33,7 @@ SIGNATURES = {
     "decnet_costvol_bf16_ndhwc_rows": (_i, [_f32p] * 3 + [_i] * 8 + [C.c_void_p]),
     "decnet_refine_pack_rows": (_i, [_f32p] * 4 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv3d_debug_timing": (None, [C.c_void_p]),
+    "decnet_conv3d_set_variant": (None, [_i]),
     "decnet_softargmin": (_i, [_f32p] * 2 + [_i] * 4 + [C.c_void_p]),
     "decnet_mask_threshold": (_i, [_f32p] * 2 + [C.c_float] + [_f32p] * 4 + [_i] * 3 + [C.c_void_p]),
     "decnet_dynup_pack": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),

@@ -335,6 +335,270 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
+// =============================================================================================
+// 2-CTA variant (cta_group::2): a CTA PAIR (cluster of 2 SMs) computes two 128-voxel tiles with ONE
+// M=256 MMA per K-step.  Each CTA stages its own A tile (128 voxels x 64 ch) and HALF of the weight
+// tile (np/2 output channels x 64 ch); the tensor cores of both SMs read the two B halves, so per
+// CTA the shared-memory fill and operand traffic per stage drops from 16+28 KB to 16+14 KB and the
+// single issuing thread launches half as many instructions per FLOP.
+//   * TMA loads are issued by both CTAs with .cta_group::2 and complete_tx on the LEADER's full barrier
+//     (count 2: leader arrive.expect_tx for both CTAs' bytes + the peer's remote arrive);
+//   * the leader's tcgen05.commit is multicast to both CTAs' empty / tmem_full barriers;
+//   * epilogue warps of both CTAs arrive on the leader's tmem_empty barrier (count 8).
+// =============================================================================================
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4,
+                                                uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+          "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *tm, int c0, int c1, int c2,
+                                                uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar) : "memory");
+}
+#define DECNET_MMA2_NEXT(OFF)                                                      \
+        "add.u64 a, %1, " #OFF ";\n\t"                                              \
+        "add.u64 b, %2, " #OFF ";\n\t"                                              \
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, t;\n\t"
+#define DECNET_STAGE2_HEAD                                                         \
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b;\n\t.reg .b16 m;\n\t"            \
+        "elect.sync _|e, 0xffffffff;\n\t"                                           \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                 \
+        "setp.eq.b32 t, 0, 0;\n\t"                                                  \
+        "mov.b16 m, 3;\n\t"                                                         \
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+#define DECNET_STAGE2_TAIL                                                         \
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n\t}"
+template <int KSTEPS>
+__device__ __forceinline__ void umma2_stage_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate_first, uint32_t bar_addr) {
+    if constexpr (KSTEPS == 4) {
+        asm volatile(DECNET_STAGE2_HEAD DECNET_MMA2_NEXT(2) DECNET_MMA2_NEXT(4) DECNET_MMA2_NEXT(6) DECNET_STAGE2_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    } else if constexpr (KSTEPS == 3) {
+        asm volatile(DECNET_STAGE2_HEAD DECNET_MMA2_NEXT(2) DECNET_MMA2_NEXT(4) DECNET_STAGE2_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    } else if constexpr (KSTEPS == 2) {
+        asm volatile(DECNET_STAGE2_HEAD DECNET_MMA2_NEXT(2) DECNET_STAGE2_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    } else {
+        asm volatile(DECNET_STAGE2_HEAD DECNET_STAGE2_TAIL
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
+    }
+}
+__device__ __forceinline__ void umma2_commit_mc_elect(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(bar_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t cta_rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    unsigned char *base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int half_n = p.np >> 1;
+    const int b_bytes = half_n * kChunkK * 2;             // this CTA's half of the weight tile
+    const int stage_bytes = kABytes + b_bytes;
+    const int kStages = p.stages;
+    const int acc_stride = p.tmem_cols >> 1;
+    const int num_units = (p.num_tiles + 1) >> 1;         // a unit = two consecutive tiles (one per CTA)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // barriers of both CTAs initialised before any remote use
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int u = cluster_id; u < num_units; u += num_clusters) {
+                int t = min(2 * u + (int)cta_rank, p.num_tiles - 1);
+                const int w0 = (t % p.tw) * p.bw; t /= p.tw;
+                const int h0 = (t % p.th) * p.bh; t /= p.th;
+                const int d0 = (t % p.td) * p.bd; t /= p.td;
+                const int b = t;
+                int tap = 0;
+                for (int kd = 0; kd < 3; ++kd)
+                    for (int kh = 0; kh < 3; ++kh)
+                        for (int kw = 0; kw < 3; ++kw, ++tap)
+                            for (int ck = 0; ck < p.nchunks; ++ck) {
+                                mbar_wait(&empty_bar[s], ph ^ 1u);
+                                unsigned char *sa = base + (size_t)s * stage_bytes;
+                                const uint32_t lbar = map_to_cta(smem_u32(&full_bar[s]), 0);
+                                if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));
+                                else remote_arrive(lbar);
+                                tma_load_5d_2sm(sa, &tmA, ck * kChunkK, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, lbar);
+                                tma_load_3d_2sm(sa + kABytes, &tmB, ck * kChunkK, (int)cta_rank * half_n, tap, lbar);
+                                if (++s == kStages) { s = 0; ph ^= 1u; }
+                            }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only; whole warp converged) =====================
+        if (leader) {
+            const uint32_t idesc = make_idesc_bf16_f32(2 * kTileM, p.np);
+            int j = 0;
+            int s = 0; uint32_t ph = 0;
+            const uint32_t smem_base = smem_u32(base);
+            const uint32_t empty_base = smem_u32(&empty_bar[0]);
+            bool ready = false;
+            long long t_begin = clock64(), t_wait = 0, t_wait_acc = 0; int it = 0;
+            for (int u = cluster_id; u < num_units; u += num_clusters, ++j) {
+                const int slot = j & 1;
+                { const long long w0_ = clock64(); mbar_wait(&tmem_empty_bar[slot], ((uint32_t)(j >> 1) & 1u) ^ 1u); t_wait_acc += clock64() - w0_; }
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
+                uint32_t first = 1u;
+                const int last_ck = p.nchunks - 1;
+                for (int tap = 0; tap < 27; ++tap) {
+                    for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
+                        if (!ready) { const long long w0_ = clock64(); mbar_wait(&full_bar[s], ph); t_wait += clock64() - w0_; }
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
+                        const uint64_t da = make_smem_desc_sw128(sa);
+                        const uint64_t db = make_smem_desc_sw128(sa + kABytes);
+                        const uint32_t ebar = empty_base + (uint32_t)(s * 8);
+                        int sn = s + 1; uint32_t phn = ph;
+                        if (sn == kStages) { sn = 0; phn ^= 1u; }
+                        ready = mbar_try_wait(&full_bar[sn], phn);
+                        if (ck != last_ck) umma2_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar);
+                        else switch (p.last_ksteps) {
+                            case 4: umma2_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                            case 3: umma2_stage_elect<3>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                            case 2: umma2_stage_elect<2>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                            default: umma2_stage_elect<1>(acc, da, db, idesc, first ^ 1u, ebar); break;
+                        }
+                        first = 0u;
+                        s = sn; ph = phn;
+                    }
+                }
+                umma2_commit_mc_elect(smem_u32(&tmem_full_bar[slot]));     // both CTAs' epilogues
+            }
+            if (p.dbg && lane == 0) {
+                p.dbg[4 * blockIdx.x + 0] = clock64() - t_begin;
+                p.dbg[4 * blockIdx.x + 1] = t_wait;
+                p.dbg[4 * blockIdx.x + 2] = t_wait_acc;
+                p.dbg[4 * blockIdx.x + 3] = it;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 of both CTAs) =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dd = r / (p.bw * p.bh);
+        int j = 0;
+        for (int u = cluster_id; u < num_units; u += num_clusters, ++j) {
+            const int tile = 2 * u + (int)cta_rank;
+            const bool tile_ok = tile < p.num_tiles;
+            int t = min(tile, p.num_tiles - 1);
+            const int w = (t % p.tw) * p.bw + dw; t /= p.tw;
+            const int h = (t % p.th) * p.bh + dh; t /= p.th;
+            const int d = (t % p.td) * p.bd + dd; t /= p.td;
+            const int b = t;
+            const bool valid = tile_ok && (w < p.W) && (h < p.H) && (d < p.D);
+            const size_t m = (((size_t)b * p.D + d) * p.H + h) * p.W + w;
+            const int slot = j & 1;
+            mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * acc_stride);
+            if (p.mode == 1) {
+                float v[16];
+                tmem_ld16(trow, v);
+                if (valid) { float x = v[0] + p.bias[0]; if (p.relu) x = fmaxf(x, 0.f); p.out_f32[m] = x; }
+            } else {
+                for (int c0 = 0; c0 < p.np; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + (uint32_t)c0, v);
+                    if (valid) {
+                        __align__(16) __nv_bfloat16 o[16];
+                        __align__(16) __nv_bfloat16 rs[16];
+                        if (p.residual) {
+                            const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + m * p.np + c0);
+                            *reinterpret_cast<uint4 *>(rs) = __ldg(rp);
+                            *reinterpret_cast<uint4 *>(rs + 8) = __ldg(rp + 1);
+                        }
+                        const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 bv = __ldg(bp + i4);
+                            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float x = v[4 * i4 + i] + bb[i];
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                if (p.residual) x += __bfloat162float(rs[4 * i4 + i]);
+                                o[4 * i4 + i] = __float2bfloat16(x);
+                            }
+                        }
+                        uint4 *op = reinterpret_cast<uint4 *>(p.out_bf16 + m * p.np + c0);
+                        op[0] = *reinterpret_cast<const uint4 *>(o);
+                        op[1] = *reinterpret_cast<const uint4 *>(o + 8);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&tmem_empty_bar[slot]);
+                else remote_arrive(map_to_cta(smem_u32(&tmem_empty_bar[slot]), 0));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // the peer may still be signalling my barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                     ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 // pick the (bw, bh, bd) power-of-two box with bw*bh*bd = 128 that wastes the fewest voxels
 static void pick_tile(int W, int H, int D, int &bw, int &bh, int &bd) {
     double best = 1e30;
@@ -358,6 +622,8 @@ using namespace decnet::conv3d;
 extern "C" {
 
 static thread_local long long *g_conv3d_dbg = nullptr;
+static thread_local int g_conv3d_variant = 0;      // 0 = auto (1-CTA kernel), 1 = force 1-CTA, 2 = CTA-pair kernel
+void decnet_conv3d_set_variant(int v) { g_conv3d_variant = v; }
 void decnet_conv3d_debug_timing(void *dbg_buffer) { g_conv3d_dbg = static_cast<long long *>(dbg_buffer); }
 
 int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *bias, const void *residual,
@@ -384,6 +650,19 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
     p.relu = relu; p.mode = out_mode;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;   // 2 slots
 
+    const long long tiles = (long long)B * p.tw * p.th * p.td;
+    DECNET_REQUIRE(tiles < (1ll << 31), "too many tiles");
+    p.num_tiles = (int)tiles;
+    p.dbg = g_conv3d_dbg;
+    const int sms = sm_count_cached();
+    // The CTA-pair kernel is correct (same tests) but measured 2x slower than the single-CTA one in
+    // round 1 (MMAs slow down 3x while TMA fills run): opt-in only.
+    const bool two_cta = g_conv3d_variant == 2 && tiles >= 2 && sms >= 2;
+    const size_t stage_bytes = kABytes + (size_t)(two_cta ? np / 2 : np) * kChunkK * 2;
+    p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    DECNET_REQUIRE(p.stages >= 2, "stage too large");
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[5] = {(uint64_t)cp, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)B};
@@ -397,16 +676,28 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
     {
         const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, 27ull};
         const uint64_t strides[2] = {(uint64_t)cp * 2, (uint64_t)np * cp * 2};
-        const uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)np, 1u};
+        const uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)(two_cta ? np / 2 : np), 1u};
         int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_packed, dims, strides, box,
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
-    const size_t stage_bytes = kABytes + (size_t)np * kChunkK * 2;
-    p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
-    if (p.stages > kMaxStages) p.stages = kMaxStages;
-    DECNET_REQUIRE(p.stages >= 2, "stage too large");
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    if (two_cta) {
+        static std::mutex mu2;
+        static size_t set_for2[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        {
+            std::lock_guard<std::mutex> lk(mu2);
+            if (dev < 0 || dev >= 64 || set_for2[dev] < smem) {
+                DECNET_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (dev >= 0 && dev < 64) set_for2[dev] = smem;
+            }
+        }
+        const long long units = (tiles + 1) / 2;
+        const long long clusters = units < sms / 2 ? units : sms / 2;
+        conv3d_tcgen05_2cta_kernel<<<(unsigned)(2 * clusters), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+        return after_launch("conv3d_tcgen05_2cta_kernel");
+    }
     {   // raise the dynamic smem limit once per device and size (the call costs host time on every launch)
         static std::mutex mu;
         static size_t set_for[64] = {0};
@@ -418,11 +709,6 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
             if (dev >= 0 && dev < 64) set_for[dev] = smem;
         }
     }
-    const long long tiles = (long long)B * p.tw * p.th * p.td;
-    DECNET_REQUIRE(tiles < (1ll << 31), "too many tiles");
-    p.num_tiles = (int)tiles;
-    p.dbg = g_conv3d_dbg;
-    const int sms = sm_count_cached();
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);       // persistent: one CTA per SM
     conv3d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
     return after_launch("conv3d_tcgen05_kernel");

@@ -159,6 +159,9 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */
 void decnet_conv3d_debug_timing(void *dbg_buffer);
+/* 0 = auto (single-CTA kernel), 1 = force single-CTA, 2 = CTA-pair kernel (tcgen05 cta_group::2,
+ * correct but slower in round 1; kept for tuning).  Per calling thread. */
+void decnet_conv3d_set_variant(int variant);
 
 /* ------------------------------------------------------------------------- *
  * Lost-detail mask selection (row a6).

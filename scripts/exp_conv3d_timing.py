@@ -19,4 +19,4 @@ for np_ in (16, 224):
     d = dbg.view(148, 4).cpu().double()
     three = d[:, 3] == 324
     q = d[three]
-    print(f"np={np_:3d} 3-tile CTAs: {q[:,0].mean()/324:6.1f} cyc/stage, wait(full) {q[:,1].mean()/324:6.1f}, {q[:,2].mean()/324:6.1f} ns/stage, {q[:,0].mean()/q[:,2].mean()*1e3:5.0f} MHz")
+    print(f"np={np_:3d} 3-unit CTAs n={int(three.sum())}: {q[:,0].mean()/324:6.1f} cyc/stage, wait(full) {q[:,1].mean()/324:6.1f}, wait(tmem_empty) total {q[:,2].mean():8.0f} cyc")

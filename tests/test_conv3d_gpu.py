@@ -76,3 +76,24 @@ def test_stack_vs_reference_golden(name):
     # drop-in forward([B,C,D,H,W]) route gives the same numbers as the fused route
     cost2 = m.cost_regularizer(torch.from_numpy(z["vol"]).cuda())
     assert (cost2 - cost).abs().max().item() <= 0.02 * gcost.abs().max().item()
+
+
+@pytest.mark.parametrize("B,D,H,W,C,Cout", [(2, 8, 20, 36, 216, 216), (1, 8, 14, 47, 216, 216), (1, 8, 4, 6, 216, 1), (3, 3, 5, 7, 32, 48)])
+def test_cta_pair_variant_matches_single_cta(B, D, H, W, C, Cout):
+    """The cta_group::2 kernel (opt-in) must give the same numbers as the default single-CTA kernel."""
+    from decnet_b200 import _lib, conv3d as c3
+    g = torch.Generator(device="cuda").manual_seed(12)
+    cp, np_ = c3._pad16(C), c3._pad16(Cout)
+    x = torch.zeros(B, D, H, W, cp, device="cuda", dtype=torch.bfloat16)
+    x[..., :C] = torch.randn(B, D, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.zeros(27, np_, cp, device="cuda", dtype=torch.bfloat16)
+    w[:, :Cout, :C] = (torch.randn(27, Cout, C, device="cuda", generator=g) * (2.0 / (27 * C)) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(np_, device="cuda", generator=g) * 0.1
+    f32 = Cout == 1
+    a = c3.conv3d_layer(x, w, bias, np_, True, out_f32=f32)
+    _lib.lib().decnet_conv3d_set_variant(2)
+    try:
+        b_ = c3.conv3d_layer(x, w, bias, np_, True, out_f32=f32)
+    finally:
+        _lib.lib().decnet_conv3d_set_variant(0)
+    assert torch.equal(a, b_), (a.float() - b_.float()).abs().max()
