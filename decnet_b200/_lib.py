@@ -44,6 +44,7 @@ SIGNATURES = {
     "decnet_refine_pack": (_i, [_f32p] * 4 + [_i] * 4 + [C.c_void_p]),
     "decnet_haar_level": (_i, [_f32p] * 6 + [_i] * 3 + [C.c_void_p]),
     "decnet_conv2d_small_supported": (_i, [_i] * 3),
+    "decnet_conv2d_set_variant": (None, [_i]),
     "decnet_conv2d_small": (_i, [_f32p] * 5 + [_i] * 8 + [C.c_void_p]),
     "decnet_deconv3x3s3": (_i, [_f32p] * 4 + [_i] * 6 + [C.c_void_p]),
     "decnet_last_sparse_path": (_i, []),

@@ -85,6 +85,130 @@ conv2d_small_kernel(const float *__restrict__ x, const float *__restrict__ wpk, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-memory tiled variant for the large (fine-level) maps.  A CTA owns a 64 x 16 output tile; the
+// input tile (+ dilation halo, zero filled outside the image) of a few channels at a time is staged
+// in shared memory with coalesced loads, so the 9 taps are conflict-free LDS with immediate offsets
+// (no per-tap bounds checks or address arithmetic) and the weights are broadcast float4 LDS.
+// Thread (tx, ty) computes the 4 pixels (tx, ty + 4*r) x COUT channels.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTW = 64, kTH = 16, kRows = 4;
+
+template <int COUT, int DIL>
+__global__ void __launch_bounds__(256)
+conv2d_tiled_kernel(const float *__restrict__ x, const float *__restrict__ wpk, const float *__restrict__ bias,
+                    const float *__restrict__ addend, float *__restrict__ out,
+                    int Cin, int H, int W, int cc /*channels per round*/, int relu)
+{
+    constexpr int COUTP = (COUT + 3) & ~3;
+    constexpr int PW = kTW + 2 * DIL;                     // tile pitch (floats)
+    constexpr int PH = kTH + 2 * DIL;
+    extern __shared__ __align__(16) float sm[];
+    float *ws = sm;                                       // [Cin][9][COUTP]
+    float *tile = sm + Cin * 9 * COUTP;                   // [cc][PH][PW]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Cin * 9 * COUTP; i += 256) ws[i] = wpk[i];
+
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int tx = tid & 63, ty = tid >> 6;
+    float acc[kRows][COUT];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[r][co] = __ldg(bias + co);
+
+    const size_t plane = (size_t)H * W;
+    const float *xb = x + (size_t)b * Cin * plane;
+    for (int c0 = 0; c0 < Cin; c0 += cc) {
+        const int nc = min(cc, Cin - c0);
+        __syncthreads();                                  // previous round's tile fully consumed (and ws written)
+        for (int i = tid; i < nc * PH * PW; i += 256) {
+            const int c = i / (PH * PW), rem = i - c * (PH * PW);
+            const int yy = rem / PW, xx = rem - yy * PW;
+            const int gy = y0 + yy - DIL, gx = x0 + xx - DIL;
+            float v = 0.f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(xb + (size_t)(c0 + c) * plane + (size_t)gy * W + gx);
+            tile[i] = v;
+        }
+        __syncthreads();
+        for (int c = 0; c < nc; ++c) {
+            const float *tc = tile + c * PH * PW + ty * PW + tx;
+            const float *wc = ws + (c0 + c) * 9 * COUTP;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    float w[COUTP];
+                    const float4 *wv = reinterpret_cast<const float4 *>(wc + (ky * 3 + kx) * COUTP);
+#pragma unroll
+                    for (int q = 0; q < COUTP / 4; ++q) {
+                        const float4 t = wv[q];
+                        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        const float v = tc[(4 * r + ky * DIL) * PW + kx * DIL];
+#pragma unroll
+                        for (int co = 0; co < COUT; ++co) acc[r][co] = fmaf(v, w[co], acc[r][co]);
+                    }
+                }
+        }
+    }
+    const int gx = x0 + tx;
+    if (gx < W) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int gy = y0 + ty + 4 * r;
+            if (gy < H) {
+                float *ob = out + (size_t)b * COUT * plane + (size_t)gy * W + gx;
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    float v = acc[r][co];
+                    if (relu) v = fmaxf(v, 0.f);
+                    if (COUT == 1 && addend) v += addend[(size_t)b * plane + (size_t)gy * W + gx];
+                    ob[(size_t)co * plane] = v;
+                }
+            }
+        }
+    }
+}
+
+template <int COUT, int DIL>
+static int launch_tiled(const float *x, const float *wpk, const float *bias, const float *addend, float *out,
+                        int B, int Cin, int H, int W, int relu, cudaStream_t st)
+{
+    constexpr int COUTP = (COUT + 3) & ~3;
+    constexpr int PW = kTW + 2 * DIL, PH = kTH + 2 * DIL;
+    const size_t wbytes = (size_t)Cin * 9 * COUTP * sizeof(float);
+    // channels per round: keep the CTA around 48 KB so that several CTAs share an SM
+    int cc = (int)((48 * 1024 - (long long)wbytes) / (long long)(PH * PW * sizeof(float)));
+    if (cc < 1) cc = 1;
+    if (cc > Cin) cc = Cin;
+    const size_t smem = wbytes + (size_t)cc * PH * PW * sizeof(float);
+    auto kern = conv2d_tiled_kernel<COUT, DIL>;
+    if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B);
+    kern<<<grid, 256, smem, st>>>(x, wpk, bias, addend, out, Cin, H, W, cc, relu);
+    return after_launch("conv2d_tiled_kernel");
+}
+
+template <int COUT>
+static int launch_tiled_dil(int dil, const float *x, const float *wpk, const float *bias, const float *addend, float *out,
+                            int B, int Cin, int H, int W, int relu, cudaStream_t st, bool *handled)
+{
+    *handled = true;
+    switch (dil) {
+        case 1: return launch_tiled<COUT, 1>(x, wpk, bias, addend, out, B, Cin, H, W, relu, st);
+        case 2: return launch_tiled<COUT, 2>(x, wpk, bias, addend, out, B, Cin, H, W, relu, st);
+        case 3: return launch_tiled<COUT, 3>(x, wpk, bias, addend, out, B, Cin, H, W, relu, st);
+        case 4: return launch_tiled<COUT, 4>(x, wpk, bias, addend, out, B, Cin, H, W, relu, st);
+        case 6: return launch_tiled<COUT, 6>(x, wpk, bias, addend, out, B, Cin, H, W, relu, st);
+        case 9: return launch_tiled<COUT, 9>(x, wpk, bias, addend, out, B, Cin, H, W, relu, st);
+        default: *handled = false; return 0;
+    }
+}
+
 // ConvTranspose2d k=3 s=3 (+bias, ReLU): out[b,co,3y+i,3x+j] = relu(bias[co] + sum_ci in[b,ci,y,x] * w[ci,co,i,j])
 template <int COUT>
 __global__ void __launch_bounds__(256)
@@ -137,7 +261,11 @@ static int launch(const float *x, const float *wpk, const float *bias, const flo
 using namespace decnet;
 using namespace decnet::conv2d;
 
+static thread_local int g_conv2d_variant = 0;     // 0 = auto (register/L1 kernel), 2 = shared-memory tiled kernel
+
 extern "C" {
+
+void decnet_conv2d_set_variant(int v) { g_conv2d_variant = v; }
 
 int decnet_conv2d_small_supported(int Cin, int Cout, int ksize) {
     if (ksize != 1 && ksize != 3) return 0;
@@ -156,6 +284,22 @@ int decnet_conv2d_small(const float *x, const float *w_packed, const float *bias
     DECNET_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0, "weights must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int taps = ksize * ksize;
+    // Shared-memory tiled kernel: opt-in (variant 2).  Measured SLOWER than the register/L1 kernel on B200 in
+    // round 1 (219 vs 200 us for 8->8, 726 vs ~350 us for 17->8 dil 3 at 4.2 M pixels: the halo re-loads and the
+    // two block barriers per channel round cost more than the per-tap bounds checks they remove).
+    if (ksize == 3 && (long long)H * W >= 64 * 64 && Cin * 9 * ((Cout + 3) & ~3) * 4 <= 24 * 1024 && g_conv2d_variant == 2) {
+        bool handled = false;
+        int rc = 0;
+        switch (Cout) {
+            case 1:  rc = launch_tiled_dil<1>(dilation, x, w_packed, bias, addend, out, B, Cin, H, W, relu, st, &handled); break;
+            case 3:  rc = launch_tiled_dil<3>(dilation, x, w_packed, bias, addend, out, B, Cin, H, W, relu, st, &handled); break;
+            case 4:  rc = launch_tiled_dil<4>(dilation, x, w_packed, bias, addend, out, B, Cin, H, W, relu, st, &handled); break;
+            case 8:  rc = launch_tiled_dil<8>(dilation, x, w_packed, bias, addend, out, B, Cin, H, W, relu, st, &handled); break;
+            case 12: rc = launch_tiled_dil<12>(dilation, x, w_packed, bias, addend, out, B, Cin, H, W, relu, st, &handled); break;
+            default: break;
+        }
+        if (handled) return rc;
+    }
     switch (Cout) {
         case 1:  return launch<1, 4>(x, w_packed, bias, addend, out, B, Cin, H, W, taps, dilation, relu, st);
         case 3:  return launch<3, 4>(x, w_packed, bias, addend, out, B, Cin, H, W, taps, dilation, relu, st);

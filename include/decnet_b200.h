@@ -237,6 +237,8 @@ int decnet_refine_pack_rows(const float *left_fea, const float *right_fea, const
  * Supported shapes: decnet_conv2d_small_supported(); `addend` (single-channel outputs only, may be
  * NULL) is added after the activation (Refinement: disp + residual, submodule.py:761). */
 int decnet_conv2d_small_supported(int Cin, int Cout, int ksize);
+/* 0 = auto (register/L1 kernel), 2 = shared-memory tiled kernel (correct, measured slower in round 1).  Per thread. */
+void decnet_conv2d_set_variant(int variant);
 int decnet_conv2d_small(const float *x, const float *w_packed, const float *bias, const float *addend, float *out,
                         int B, int Cin, int H, int W, int Cout, int ksize, int dilation, int relu, void *stream);
 

@@ -196,3 +196,30 @@ def test_extension_shim_reference_calling_convention():
     assert dL.abs().sum() > 0 and dR.abs().sum() > 0
     dL2, dR2, dd = torch.zeros_like(L), torch.zeros_like(R), torch.zeros_like(out)
     assert ext.SpaVar.sparse_var_cuda_backward(L, R, ml, mr, out, var, s2, m2, g, dL2, dR2, dd, 20) == 1
+
+
+@pytest.mark.parametrize("Cin,Cout,k,dil,H,W", [(17, 8, 3, 3, 70, 130), (8, 8, 3, 1, 65, 64), (8, 8, 3, 6, 96, 200),
+                                                (8, 4, 3, 1, 128, 70), (4, 4, 3, 9, 80, 90), (4, 1, 3, 1, 64, 67),
+                                                (12, 8, 3, 1, 33, 500), (8, 3, 3, 1, 90, 90), (3, 1, 1, 1, 70, 70),
+                                                (49, 12, 3, 2, 64, 64), (28, 8, 3, 1, 20, 36), (76, 8, 3, 1, 9, 11)])
+@pytest.mark.parametrize("variant", [0, 2])
+def test_conv2d_small_vs_torch(Cin, Cout, k, dil, H, W, variant):
+    """Direct fp32 conv kernels (register/L1 and shared-memory tiled) against F.conv2d in fp32 (TF32 off)."""
+    import torch.nn.functional as F
+    from decnet_b200 import _lib, ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B = 2
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (2.0 / (k * k * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    add = torch.randn(B, H, W, device="cuda", generator=g) if Cout == 1 else None
+    want = F.relu(F.conv2d(x, w, b, padding=dil * (k // 2), dilation=dil))
+    if add is not None:
+        want = want + add.unsqueeze(1)
+    _lib.lib().decnet_conv2d_set_variant(variant)
+    try:
+        got = ops.conv2d_small(x, ops.pack_conv2d_weights(w), b, Cout, k, dil, True, add)
+    finally:
+        _lib.lib().decnet_conv2d_set_variant(0)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-5), (got - want).abs().max()
