@@ -41,30 +41,65 @@ conv2d_small_kernel(const float *__restrict__ x, const float *__restrict__ wpk, 
 
     const size_t plane = (size_t)H * W;
     const float *xb = x + (size_t)b * Cin * plane;
-    const int t0 = (taps == 9) ? 0 : 1, t1 = (taps == 9) ? 3 : 2;     // 1x1: centre tap only
-    for (int ci = 0; ci < Cin; ++ci) {
-        const float *xc = xb + (size_t)ci * plane;
-        for (int ty = t0; ty < t1; ++ty) {
-            const int yy = y + (ty - 1) * dil;
-            const bool row_ok = yy >= 0 && yy < H;
-            const float *xr = xc + (size_t)(row_ok ? yy : 0) * W;
+    const int halo = (taps == 9) ? dil : 0;
+    // Interior threads (every tap of every owned pixel inside the image: > 98 % of a 540x972 map) take a
+    // path without bounds checks whose 9 tap addresses are one 64-bit add each and whose P loads per tap
+    // use immediate offsets (the first version executed 226 M warp instructions for 76 M warp-FFMA).
+    const bool interior = (y - halo >= 0) && (y + halo < H) && (x0 - halo >= 0) && (x0 + (P - 1) * kTX + halo < W);
+    if (interior && taps == 9) {
+        int toff[9];
 #pragma unroll
-            for (int tx = 0; tx < 3; ++tx) {
-                if (taps != 9 && tx != 1) continue;
-                const int tap = (taps == 9) ? ty * 3 + tx : 0;
-                const float4 *wv = reinterpret_cast<const float4 *>(ws + (ci * taps + tap) * COUTP);
+        for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < 3; ++tx) toff[ty * 3 + tx] = (ty - 1) * dil * W + (tx - 1) * dil;
+        const float *pc = xb + (size_t)y * W + x0;
+        const float *wc = ws;
+        for (int ci = 0; ci < Cin; ++ci, pc += plane, wc += 9 * COUTP) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float *pt = pc + toff[t];
+                float v[P];
+#pragma unroll
+                for (int k = 0; k < P; ++k) v[k] = __ldg(pt + k * kTX);
+                const float4 *wv = reinterpret_cast<const float4 *>(wc + t * COUTP);
                 float w[COUTP];
 #pragma unroll
                 for (int q = 0; q < COUTP / 4; ++q) {
-                    const float4 t = wv[q];
-                    w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+                    const float4 tt = wv[q];
+                    w[4 * q] = tt.x; w[4 * q + 1] = tt.y; w[4 * q + 2] = tt.z; w[4 * q + 3] = tt.w;
                 }
 #pragma unroll
-                for (int k = 0; k < P; ++k) {
-                    const int xx = x0 + k * kTX + (tx - 1) * dil;
-                    const float v = (row_ok && xx >= 0 && xx < W) ? __ldg(xr + xx) : 0.f;
+                for (int k = 0; k < P; ++k)
 #pragma unroll
-                    for (int co = 0; co < COUT; ++co) acc[k][co] = fmaf(v, w[co], acc[k][co]);
+                    for (int co = 0; co < COUT; ++co) acc[k][co] = fmaf(v[k], w[co], acc[k][co]);
+            }
+        }
+    } else {
+        const int t0 = (taps == 9) ? 0 : 1, t1 = (taps == 9) ? 3 : 2;     // 1x1: centre tap only
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float *xc = xb + (size_t)ci * plane;
+            for (int ty = t0; ty < t1; ++ty) {
+                const int yy = y + (ty - 1) * dil;
+                const bool row_ok = yy >= 0 && yy < H;
+                const float *xr = xc + (size_t)(row_ok ? yy : 0) * W;
+#pragma unroll
+                for (int tx = 0; tx < 3; ++tx) {
+                    if (taps != 9 && tx != 1) continue;
+                    const int tap = (taps == 9) ? ty * 3 + tx : 0;
+                    const float4 *wv = reinterpret_cast<const float4 *>(ws + (ci * taps + tap) * COUTP);
+                    float w[COUTP];
+#pragma unroll
+                    for (int q = 0; q < COUTP / 4; ++q) {
+                        const float4 t = wv[q];
+                        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const int xx = x0 + k * kTX + (tx - 1) * dil;
+                        const float v = (row_ok && xx >= 0 && xx < W) ? __ldg(xr + xx) : 0.f;
+#pragma unroll
+                        for (int co = 0; co < COUT; ++co) acc[k][co] = fmaf(v, w[co], acc[k][co]);
+                    }
                 }
             }
         }
