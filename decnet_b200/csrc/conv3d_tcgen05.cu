@@ -49,31 +49,12 @@ __device__ __forceinline__ uint32_t make_idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Warp-converged variants: every lane executes the statement with warp-uniform operands and
-// elect.sync picks the single issuing lane INSIDE the asm block.  This keeps the descriptors in
-// uniform registers; issuing from a divergent `if (lane == 0)` region makes nvcc wrap every
-// UTCHMMA in an ELECT/BRA.U.ANY loop with R2UR moves (~140 cycles per MMA instead of ~40).
-__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
+// The whole MMA warp stays converged and elect.sync picks the single issuing lane INSIDE the asm block:
+// the descriptors stay in uniform registers.  Issuing from a divergent `if (lane == 0)` region makes
+// nvcc wrap every UTCHMMA in an ELECT/BRA.U.ANY loop with R2UR moves (~140 cycles per MMA instead of ~40).
 // One stage = `KSTEPS` K-steps of 16 (32 bytes each inside the 128-byte swizzle row = +2 in the
-// descriptor's 16-byte address field) followed by the commit that releases the stage: a single
-// asm block with ONE elect.sync, so the issuing warp's dependent instruction chain per stage stays
-// well below the 4 x 112 cycles the tensor pipe needs for it.
+// descriptor's 16-byte address field) followed by the commit that releases the stage: a single asm
+// block with ONE elect.sync keeps the issuing warp's dependent instruction chain per stage short.
 #define DECNET_MMA_NEXT(OFF)                                                       \
         "add.u64 a, %1, " #OFF ";\n\t"                                              \
         "add.u64 b, %2, " #OFF ";\n\t"                                              \
@@ -104,23 +85,12 @@ __device__ __forceinline__ void umma_stage_elect(uint32_t tmem_d, uint64_t desc_
                      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
     }
 }
-__device__ __forceinline__ void umma_commit_addr_elect(uint32_t bar_addr) {
-    asm volatile(
-        "{\n\t.reg .pred e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-        ::"r"(bar_addr) : "memory");
-}
 __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
         "elect.sync _|e, 0xffffffff;\n\t"
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
         ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -184,7 +154,6 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    const int iters_per_tile = 27 * p.nchunks;
 
     // Persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and the
     // two TMEM accumulator slots keep rolling across tiles, so the epilogue of tile j overlaps the
