@@ -32,12 +32,15 @@ SIGNATURES = {
     "decnet_conv3d_bf16": (_i, [_f32p] * 5 + [_i] * 8 + [C.c_void_p]),
     "decnet_costvol_bf16_ndhwc_rows": (_i, [_f32p] * 3 + [_i] * 8 + [C.c_void_p]),
     "decnet_refine_pack_rows": (_i, [_f32p] * 4 + [_i] * 6 + [C.c_void_p]),
+    "decnet_conv2d_tf32_nhwc": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),
     "decnet_conv3d_debug_timing": (None, [C.c_void_p]),
     "decnet_conv3d_set_variant": (None, [_i]),
     "decnet_softargmin": (_i, [_f32p] * 2 + [_i] * 4 + [C.c_void_p]),
     "decnet_mask_threshold": (_i, [_f32p] * 2 + [C.c_float] + [_f32p] * 4 + [_i] * 3 + [C.c_void_p]),
     "decnet_dynup_pack": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
     "decnet_dynup_glue": (_i, [_f32p] * 3 + [_i] * 3 + [C.c_void_p]),
+    "decnet_dynup_pack_nhwc": (_i, [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
+    "decnet_dynup_glue_nhwc": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
     "decnet_attn_pack": (_i, [_f32p] * 6 + [_i] * 4 + [C.c_void_p]),
     "decnet_blend": (_i, [_f32p] * 5 + [_i] * 3 + [C.c_void_p]),
     "decnet_warp_bilinear": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),

@@ -34,8 +34,8 @@ namespace conv3d {
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
-constexpr int kChunkK = 64;                       // bf16 channels per stage row = 128 bytes
-constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KB
+constexpr int kRowBytes = 128;                    // one stage row = 128 bytes = 64 bf16 or 32 fp32 (tf32) channels
+constexpr int kABytes = kTileM * kRowBytes;       // 16 KB
 
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     // K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart
@@ -43,10 +43,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__device__ __forceinline__ uint32_t make_idesc_bf16_f32(int M, int N) {
-    // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
-    // n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int fmt, int M, int N) {
+    // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format (BF16 = 1, TF32 = 2) at bits 7 / 10,
+    // K-major A and B, n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // The whole MMA warp stays converged and elect.sync picks the single issuing lane INSIDE the asm block:
@@ -92,6 +92,13 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
         ::"r"(smem_u32(bar)) : "memory");
 }
+// kind::tf32 reads fp32 words and drops the low 13 mantissa bits; rounding to nearest beforehand
+// (what cuDNN's TF32 path does with cvt.rna) halves the error.
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -116,7 +123,11 @@ struct Params {
     int cp, np;                        // padded in / out channels
     int nchunks, last_ksteps;          // ceil(cp/64), K-steps of 16 in the last chunk
     int bw, bh, bd, tw, th, td;        // tile box and tiles per axis
-    int relu, mode, tmem_cols;         // tmem_cols = 2 accumulator slots
+    int relu, mode, tmem_cols;         // mode 0 bf16 [M][np], 1 fp32 [M] (channel 0), 2 fp32 [M][np]; 2 TMEM slots
+    int fmt, chunk_ch;                 // operand format (1 bf16 / 2 tf32) and channels per 128-byte stage row
+    int taps_d;                        // 3: 3x3x3 taps (Conv3d), 1: 3x3 taps on a D=1 volume (Conv2d)
+    float *out_f32_full;               // [M][np] (mode 2)
+    int round_tf32;                    // mode 2: round the stored activations to TF32 (nearest) for the next tf32 conv
     int num_tiles, stages;
     long long *dbg;                    // optional per-CTA timing (decnet_conv3d_debug_timing), else null
 };
@@ -134,7 +145,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *base = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = p.np * kChunkK * 2;
+    const int b_bytes = p.np * kRowBytes;
     const int stage_bytes = kABytes + b_bytes;
     const int kStages = p.stages;
     const int acc_stride = p.tmem_cols >> 1;              // two accumulator slots (double buffering)
@@ -169,15 +180,15 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const int d0 = (t % p.td) * p.bd; t /= p.td;
                 const int b = t;
                 int tap = 0;
-                for (int kd = 0; kd < 3; ++kd)
+                for (int kd = (p.taps_d == 3 ? 0 : 1); kd < (p.taps_d == 3 ? 3 : 2); ++kd)
                     for (int kh = 0; kh < 3; ++kh)
                         for (int kw = 0; kw < 3; ++kw, ++tap)
                             for (int ck = 0; ck < p.nchunks; ++ck) {
                                 mbar_wait(&empty_bar[s], ph ^ 1u);
                                 unsigned char *sa = base + (size_t)s * stage_bytes;
                                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                                tma_load_5d(sa, &tmA, ck * kChunkK, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, &full_bar[s]);
-                                tma_load_3d(sa + kABytes, &tmB, ck * kChunkK, 0, tap, &full_bar[s]);
+                                tma_load_5d(sa, &tmA, ck * p.chunk_ch, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, &full_bar[s]);
+                                tma_load_3d(sa + kABytes, &tmB, ck * p.chunk_ch, 0, tap, &full_bar[s]);
                                 if (++s == kStages) { s = 0; ph ^= 1u; }
                             }
             }
@@ -185,7 +196,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         {
-            const uint32_t idesc = make_idesc_bf16_f32(kTileM, p.np);
+            const uint32_t idesc = make_idesc(p.fmt, kTileM, p.np);
             int it = 0, j = 0;
             int s = 0; uint32_t ph = 0;                   // ring slot / phase, advanced without divisions
             const uint32_t smem_base = smem_u32(base);
@@ -200,7 +211,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
                 uint32_t first = 1u;
                 const int last_ck = p.nchunks - 1;
-                for (int tap = 0; tap < 27; ++tap) {
+                for (int tap = 0; tap < 9 * p.taps_d; ++tap) {
                     for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
                         // `ready` was probed one stage ahead (the probe's latency hides behind the MMA issue)
                         if (!ready) {
@@ -259,6 +270,23 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 float v[16];
                 tmem_ld16(trow, v);
                 if (valid) { float x = v[0] + p.bias[0]; if (p.relu) x = fmaxf(x, 0.f); p.out_f32[m] = x; }
+            } else if (p.mode == 2) {
+                for (int c0 = 0; c0 < p.np; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + (uint32_t)c0, v);
+                    if (valid) {
+                        const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
+                        float4 *op = reinterpret_cast<float4 *>(p.out_f32_full + m * p.np + c0);
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 bv = __ldg(bp + i4);
+                            float4 o = make_float4(v[4 * i4] + bv.x, v[4 * i4 + 1] + bv.y, v[4 * i4 + 2] + bv.z, v[4 * i4 + 3] + bv.w);
+                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            if (p.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                            op[i4] = o;
+                        }
+                    }
+                }
             } else {
                 for (int c0 = 0; c0 < p.np; c0 += 16) {
                     float v[16];
@@ -399,7 +427,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     unsigned char *base = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int half_n = p.np >> 1;
-    const int b_bytes = half_n * kChunkK * 2;             // this CTA's half of the weight tile
+    const int b_bytes = half_n * kRowBytes;               // this CTA's half of the weight tile
     const int stage_bytes = kABytes + b_bytes;
     const int kStages = p.stages;
     const int acc_stride = p.tmem_cols >> 1;
@@ -433,7 +461,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const int d0 = (t % p.td) * p.bd; t /= p.td;
                 const int b = t;
                 int tap = 0;
-                for (int kd = 0; kd < 3; ++kd)
+                for (int kd = (p.taps_d == 3 ? 0 : 1); kd < (p.taps_d == 3 ? 3 : 2); ++kd)
                     for (int kh = 0; kh < 3; ++kh)
                         for (int kw = 0; kw < 3; ++kw, ++tap)
                             for (int ck = 0; ck < p.nchunks; ++ck) {
@@ -442,8 +470,8 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                                 const uint32_t lbar = map_to_cta(smem_u32(&full_bar[s]), 0);
                                 if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));
                                 else remote_arrive(lbar);
-                                tma_load_5d_2sm(sa, &tmA, ck * kChunkK, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, lbar);
-                                tma_load_3d_2sm(sa + kABytes, &tmB, ck * kChunkK, (int)cta_rank * half_n, tap, lbar);
+                                tma_load_5d_2sm(sa, &tmA, ck * p.chunk_ch, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, lbar);
+                                tma_load_3d_2sm(sa + kABytes, &tmB, ck * p.chunk_ch, (int)cta_rank * half_n, tap, lbar);
                                 if (++s == kStages) { s = 0; ph ^= 1u; }
                             }
             }
@@ -451,7 +479,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only; whole warp converged) =====================
         if (leader) {
-            const uint32_t idesc = make_idesc_bf16_f32(2 * kTileM, p.np);
+            const uint32_t idesc = make_idesc(p.fmt, 2 * kTileM, p.np);
             int j = 0;
             int s = 0; uint32_t ph = 0;
             const uint32_t smem_base = smem_u32(base);
@@ -465,7 +493,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
                 uint32_t first = 1u;
                 const int last_ck = p.nchunks - 1;
-                for (int tap = 0; tap < 27; ++tap) {
+                for (int tap = 0; tap < 9 * p.taps_d; ++tap) {
                     for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
                         if (!ready) { const long long w0_ = clock64(); mbar_wait(&full_bar[s], ph); t_wait += clock64() - w0_; }
                         tc_fence_after();
@@ -595,28 +623,36 @@ static thread_local int g_conv3d_variant = 0;      // 0 = auto (1-CTA kernel), 1
 void decnet_conv3d_set_variant(int v) { g_conv3d_variant = v; }
 void decnet_conv3d_debug_timing(void *dbg_buffer) { g_conv3d_dbg = static_cast<long long *>(dbg_buffer); }
 
-int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *bias, const void *residual,
-                       void *out, int out_mode, int B, int D, int H, int W, int cp, int np, int relu, void *stream)
+// Common launcher.  esize 2 -> bf16 operands (kind::f16, K-step 16, 64 channels per stage row),
+//                  esize 4 -> fp32 operands read as tf32 (kind::tf32, K-step 8, 32 channels per row).
+static int launch_conv(const void *x, const void *w_packed, const float *bias, const void *residual, void *out,
+                       int out_mode, int esize, int taps_d, int B, int D, int H, int W, int cp, int np, int relu,
+                       void *stream, int round_out = 0)
 {
-    DECNET_REQUIRE(x_ndhwc && w_packed && bias && out, "null pointer");
+    DECNET_REQUIRE(x && w_packed && bias && out, "null pointer");
     DECNET_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "non-positive size");
-    DECNET_REQUIRE(cp % 16 == 0 && cp >= 16 && cp <= 1024, "cp=%d must be a multiple of 16", cp);
+    const int kstep = esize == 2 ? 16 : 8;
+    const int chunk_ch = kRowBytes / esize;
+    DECNET_REQUIRE(cp % kstep == 0 && cp >= kstep && cp <= 4096, "cp=%d must be a multiple of %d", cp, kstep);
     DECNET_REQUIRE(np % 16 == 0 && np >= 16 && np <= 256, "np=%d must be a multiple of 16 in [16,256]", np);
-    DECNET_REQUIRE(out_mode == 0 || out_mode == 1, "out_mode must be 0 (bf16 [M][np]) or 1 (fp32 [M], channel 0)");
-    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x_ndhwc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0 &&
-                   (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+    DECNET_REQUIRE(out_mode >= 0 && out_mode <= 2, "out_mode must be 0 (bf16 [M][np]), 1 (fp32 [M]) or 2 (fp32 [M][np])");
+    DECNET_REQUIRE(taps_d == 3 || (taps_d == 1 && D == 1), "taps_d=1 needs a D=1 volume");
+    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0 &&
                    (reinterpret_cast<uintptr_t>(residual) & 15u) == 0, "pointers must be 16-byte aligned");
     Params p{};
     p.bias = bias;
     p.residual = static_cast<const __nv_bfloat16 *>(residual);
     p.out_bf16 = out_mode == 0 ? static_cast<__nv_bfloat16 *>(out) : nullptr;
     p.out_f32 = out_mode == 1 ? static_cast<float *>(out) : nullptr;
+    p.out_f32_full = out_mode == 2 ? static_cast<float *>(out) : nullptr;
     p.B = B; p.D = D; p.H = H; p.W = W; p.cp = cp; p.np = np;
-    p.nchunks = (cp + kChunkK - 1) / kChunkK;
-    p.last_ksteps = (cp - (p.nchunks - 1) * kChunkK) / 16;
+    p.fmt = esize == 2 ? 1 : 2; p.chunk_ch = chunk_ch; p.taps_d = taps_d;
+    p.nchunks = (cp + chunk_ch - 1) / chunk_ch;
+    p.last_ksteps = (cp - (p.nchunks - 1) * chunk_ch) / kstep;
     pick_tile(W, H, D, p.bw, p.bh, p.bd);
     p.tw = (W + p.bw - 1) / p.bw; p.th = (H + p.bh - 1) / p.bh; p.td = (D + p.bd - 1) / p.bd;
-    p.relu = relu; p.mode = out_mode;
+    p.relu = relu; p.mode = out_mode; p.round_tf32 = round_out;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;   // 2 slots
 
     const long long tiles = (long long)B * p.tw * p.th * p.td;
@@ -626,28 +662,29 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
     const int sms = sm_count_cached();
     // The CTA-pair kernel is correct (same tests) but measured 2x slower than the single-CTA one in
     // round 1 (MMAs slow down 3x while TMA fills run): opt-in only.
-    const bool two_cta = g_conv3d_variant == 2 && tiles >= 2 && sms >= 2;
-    const size_t stage_bytes = kABytes + (size_t)(two_cta ? np / 2 : np) * kChunkK * 2;
+    const bool two_cta = g_conv3d_variant == 2 && tiles >= 2 && sms >= 2 && out_mode != 2;
+    const size_t stage_bytes = kABytes + (size_t)(two_cta ? np / 2 : np) * kRowBytes;
     p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     DECNET_REQUIRE(p.stages >= 2, "stage too large");
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    const CUtensorMapDataType dt = esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[5] = {(uint64_t)cp, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)B};
-        const uint64_t strides[4] = {(uint64_t)cp * 2, (uint64_t)W * cp * 2, (uint64_t)H * W * cp * 2,
-                                     (uint64_t)D * H * W * cp * 2};
-        const uint32_t box[5] = {(uint32_t)kChunkK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, 1u};
-        int rc = encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x_ndhwc, dims, strides, box,
-                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        const uint64_t strides[4] = {(uint64_t)cp * esize, (uint64_t)W * cp * esize, (uint64_t)H * W * cp * esize,
+                                     (uint64_t)D * H * W * cp * esize};
+        const uint32_t box[5] = {(uint32_t)chunk_ch, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, 1u};
+        int rc = encode_tensor_map(&tmA, dt, 5, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, 27ull};
-        const uint64_t strides[2] = {(uint64_t)cp * 2, (uint64_t)np * cp * 2};
-        const uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)(two_cta ? np / 2 : np), 1u};
-        int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_packed, dims, strides, box,
-                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, (uint64_t)(9 * taps_d)};
+        const uint64_t strides[2] = {(uint64_t)cp * esize, (uint64_t)np * cp * esize};
+        const uint32_t box[3] = {(uint32_t)chunk_ch, (uint32_t)(two_cta ? np / 2 : np), 1u};
+        int rc = encode_tensor_map(&tmB, dt, 3, w_packed, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
     if (two_cta) {
@@ -681,6 +718,19 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);       // persistent: one CTA per SM
     conv3d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
     return after_launch("conv3d_tcgen05_kernel");
+}
+
+int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *bias, const void *residual,
+                       void *out, int out_mode, int B, int D, int H, int W, int cp, int np, int relu, void *stream)
+{
+    DECNET_REQUIRE(out_mode == 0 || out_mode == 1, "out_mode must be 0 (bf16 [M][np]) or 1 (fp32 [M], channel 0)");
+    return launch_conv(x_ndhwc, w_packed, bias, residual, out, out_mode, 2, 3, B, D, H, W, cp, np, relu, stream);
+}
+
+int decnet_conv2d_tf32_nhwc(const float *x_nhwc, const float *w_packed, const float *bias, float *out,
+                            int B, int H, int W, int cp, int np, int relu, int round_out_tf32, void *stream)
+{
+    return launch_conv(x_nhwc, w_packed, bias, nullptr, out, 2, 4, 1, B, 1, H, W, cp, np, relu, stream, round_out_tf32);
 }
 
 }  // extern "C"

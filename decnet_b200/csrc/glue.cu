@@ -241,6 +241,85 @@ dynup_glue_kernel(const float *__restrict__ logits, const float *__restrict__ di
 }
 
 // ---------------------------------------------------------------------------------------------
+// a8, channels-last variants feeding / draining the TF32 tcgen05 convs (decnet_conv2d_tf32_nhwc):
+//   dynup_pack_nhwc : out[b,y,x,ch], ch 0 = disp, ch 1+c*9+ky*3+kx = Lf[b,c,3y+ky,3x+kx], ch >= 1+9C zero
+//   dynup_glue_nhwc : logits[b,y,x,sub*9+k] -> same output as dynup_glue_kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+dynup_pack_nhwc_kernel(const float *__restrict__ disp, const float *__restrict__ Lf, float *__restrict__ out,
+                       int C, int h, int w, int CP, int TX, int round_tf32)
+{
+    extern __shared__ float rows[];            // [C*3][3*TX]
+    const int x0 = blockIdx.x * TX, y = blockIdx.y, b = blockIdx.z;
+    const int nx = min(TX, w - x0);
+    const int W3 = 3 * w, seg = 3 * TX;
+    for (int r = 0; r < C * 3; ++r) {
+        const int c = r / 3, ky = r - 3 * c;
+        const float *src = Lf + (((size_t)b * C + c) * (3 * h) + 3 * y + ky) * W3 + 3 * x0;
+        for (int i = threadIdx.x; i < 3 * nx; i += kBlock) rows[r * seg + i] = src[i];
+    }
+    __syncthreads();
+    float *ob = out + (((size_t)b * h + y) * w + x0) * CP;
+    const float *db = disp + ((size_t)b * h + y) * w + x0;
+    const int total = nx * CP;
+    for (int i = threadIdx.x; i < total; i += kBlock) {
+        const int xl = i / CP, ch = i - xl * CP;
+        float v = 0.f;
+        if (ch == 0) v = db[xl];
+        else if (ch <= 9 * C) {
+            const int c = (ch - 1) / 9, k = (ch - 1) - 9 * c;
+            const int ky = k / 3, kx = k - 3 * ky;
+            v = rows[(c * 3 + ky) * seg + 3 * xl + kx];
+        }
+        if (round_tf32) {      // operands of a kind::tf32 MMA: round to nearest instead of the MMA's truncation
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+            v = __uint_as_float(r);
+        }
+        ob[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict__ disp, float *__restrict__ out,
+                       int B, int h, int w, int NP)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long n = (long long)B * h * w;
+    if (idx >= n) return;
+    const int x = (int)(idx % w), y = (int)((idx / w) % h), b = (int)(idx / ((long long)w * h));
+    const size_t plane = (size_t)h * w;
+    const float *db = disp + (size_t)b * plane;
+    float nb[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int yy = min(max(y + ky - 1, 0), h - 1), xx = min(max(x + kx - 1, 0), w - 1);
+            nb[ky * 3 + kx] = __ldg(db + (size_t)yy * w + xx);
+        }
+    const float *lg = logits + (size_t)idx * NP;
+    float *ob = out + (size_t)b * 9 * plane;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float res[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int sub = i * 3 + j;
+            float v[9], mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { v[k] = __ldg(lg + sub * 9 + k); mx = fmaxf(mx, v[k]); }
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { const float e = expf(v[k] - mx); s0 += e; s1 += e * nb[k]; }
+            res[j] = (s1 / s0) * 3.0f;
+        }
+        float *o = ob + (size_t)(3 * y + i) * (3 * w) + 3 * x;
+        o[0] = res[0]; o[1] = res[1]; o[2] = res[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // a13 (input side): cat(Lf, dense, sparse, lmask, -var) -> [B, C+4, H, W]
 // (SparseDenseNetRefinementMask.py:197).  Flat copy, float4 where aligned.
 // ---------------------------------------------------------------------------------------------
@@ -531,6 +610,30 @@ int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, voi
     if (rc) return rc;
     haar_mask_kernel<<<dim3(gx, B), kBlock, 0, st>>>(detail, minmax, counts, th, mask, n);
     return after_launch("haar_mask_kernel");
+}
+
+int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out, int B, int C, int h, int w, int CP,
+                           int round_tf32, void *stream) {
+    DECNET_REQUIRE(disp && left_fea && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && B <= 65535 && C > 0 && h > 0 && h <= 65535 && w > 0, "bad size");
+    DECNET_REQUIRE(CP >= 9 * C + 1, "CP=%d must hold 9*C+1=%d channels", CP, 9 * C + 1);
+    int TX = 1800 / C;
+    TX = TX > 128 ? 128 : (TX < 8 ? 8 : (TX & ~7));
+    if (TX > w) TX = w;
+    const size_t smem = (size_t)C * 9 * TX * sizeof(float);
+    DECNET_REQUIRE(smem <= 200 * 1024, "C too large");
+    if (smem > 48 * 1024)
+        DECNET_CUDA(cudaFuncSetAttribute(dynup_pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dynup_pack_nhwc_kernel<<<dim3((w + TX - 1) / TX, h, B), kBlock, smem, (cudaStream_t)stream>>>(disp, left_fea, out, C, h, w, CP, TX, round_tf32);
+    return after_launch("dynup_pack_nhwc_kernel");
+}
+
+int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out, int B, int h, int w, int NP, void *stream) {
+    DECNET_REQUIRE(logits && disp && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && h > 0 && w > 0 && NP >= 81, "bad size");
+    const long long n = (long long)B * h * w;
+    dynup_glue_nhwc_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(logits, disp, out, B, h, w, NP);
+    return after_launch("dynup_glue_nhwc_kernel");
 }
 
 }  // extern "C"

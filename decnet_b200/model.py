@@ -29,6 +29,8 @@ from .modules import SpaMat, SpaVar
 BN_EPS = 1e-5
 # direct sm_100a kernels for the tiny-channel 2-D convs (section 8f rank 1); False = cuDNN everywhere
 USE_NATIVE_CONV2D = True
+# TF32 tcgen05 implicit GEMM for the GEMM-sized 2-D convs whenever torch.backends.cudnn.allow_tf32 is on
+USE_TF32_TCGEN05 = True
 
 
 # --------------------------------------------------------------------------------------
@@ -247,12 +249,36 @@ class DynamicUpsampling(nn.Module):
         super().__init__()
         assert down_scale == 3, "the reference hard-codes x3 (SURVEY.md D1)"
         n = down_scale ** 2 * 9
+        self._packed = None
         self.weight_learning = nn.Sequential(Conv2dUnit(in_channels * 9 + 1, n, 3, padding=1),
                                              Conv2dUnit(n, n, 3, padding=1),
                                              Conv2dUnit(n, n, 3, padding=1, relu=False))
 
+    def _tf32_pack(self):
+        """Weights of the three convs for the TF32 tcgen05 implicit GEMM (cached; reset with the folds)."""
+        if getattr(self, "_packed", None) is None:
+            units = list(self.weight_learning)
+            cin0 = units[0].conv.in_channels
+            cp = (cin0 + 7) // 8 * 8
+            packed = []
+            for u in units:
+                w, b = u.folded()
+                wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp)
+                packed.append((wp, bp, u.relu))
+                cp = np_
+            self._packed = ((cin0 + 7) // 8 * 8, packed)
+        return self._packed
+
     def forward(self, disp_map, left_fea):
         disp_map = disp_map.contiguous()
+        if USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32:
+            # TF32 allowed (PyTorch's default for convolutions): the three 81-channel convs run as tcgen05
+            # implicit GEMMs on channels-last fp32, between channels-last pack / glue kernels
+            cp0, packed = self._tf32_pack()
+            x = ops.dynup_pack_nhwc(disp_map, left_fea.contiguous(), cp0)
+            for i, (wp, bp, relu) in enumerate(packed):
+                x = ops.conv2d_tf32_nhwc(x, wp, bp, relu, round_out=i + 1 < len(packed))
+            return ops.dynup_glue_nhwc(x, disp_map)
         x = ops.dynup_pack(disp_map, left_fea.contiguous())
         logits = self.weight_learning(x)
         return ops.dynup_glue(logits.contiguous(), disp_map)

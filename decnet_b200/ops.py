@@ -318,3 +318,53 @@ def deconv3x3s3(x, w, bias, relu=True):
     _call("decnet_deconv3x3s3", x, x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, cin, h, wd, cout,
           1 if relu else 0)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# GEMM-sized 3x3 Conv2d on tensor cores (TF32 tcgen05 implicit GEMM, channels-last)
+# --------------------------------------------------------------------------------------
+def pack_conv2d_tf32_weights(w, bias, cp):
+    """[Cout,Cin,3,3] (+ bias [Cout]) -> ([9][NP][cp] fp32, bias [NP]); NP = Cout rounded up to 16."""
+    cout, cin = w.shape[:2]
+    np_ = (cout + 15) // 16 * 16
+    out = torch.zeros((9, np_, cp), dtype=torch.float32, device=w.device)
+    out[:, :cout, :cin] = w.float().permute(2, 3, 0, 1).reshape(9, cout, cin)
+    # round to TF32 (nearest, ties away: cvt.rna) -- the MMA would truncate the low 13 mantissa bits
+    out = ((out.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    b = torch.zeros(np_, dtype=torch.float32, device=w.device)
+    b[:cout] = bias.float()
+    return out.contiguous(), b.contiguous(), np_
+
+
+def conv2d_tf32_nhwc(x_nhwc, w_packed, bias, relu, round_out=False):
+    """x fp32 [B,H,W,cp] channels-last -> fp32 [B,H,W,NP] (round_out: outputs rounded to TF32 for a following tf32 conv)."""
+    _chk("x_nhwc", x_nhwc)
+    B, H, W, cp = x_nhwc.shape
+    np_ = w_packed.shape[1]
+    out = torch.empty((B, H, W, np_), dtype=torch.float32, device=x_nhwc.device)
+    _call("decnet_conv2d_tf32_nhwc", x_nhwc, x_nhwc.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(),
+          B, H, W, cp, np_, 1 if relu else 0, 1 if round_out else 0)
+    return out
+
+
+def dynup_pack_nhwc(disp, left_fea, cp, round_tf32=True):
+    _chk("disp", disp)
+    B, h, w = disp.shape
+    _chk("left_fea", left_fea, disp)
+    Cc = left_fea.shape[1]
+    if tuple(left_fea.shape) != (B, Cc, 3 * h, 3 * w):
+        raise ValueError(f"left_fea {tuple(left_fea.shape)} is not 3x the disparity map {tuple(disp.shape)}")
+    out = torch.empty((B, h, w, int(cp)), dtype=torch.float32, device=disp.device)
+    _call("decnet_dynup_pack_nhwc", disp, disp.data_ptr(), left_fea.data_ptr(), out.data_ptr(), B, Cc, h, w, int(cp),
+          1 if round_tf32 else 0)
+    return out
+
+
+def dynup_glue_nhwc(logits_nhwc, disp):
+    _chk("disp", disp)
+    B, h, w = disp.shape
+    _chk("logits", logits_nhwc, disp)
+    NP = logits_nhwc.shape[-1]
+    out = torch.empty((B, 3 * h, 3 * w), dtype=torch.float32, device=disp.device)
+    _call("decnet_dynup_glue_nhwc", disp, logits_nhwc.data_ptr(), disp.data_ptr(), out.data_ptr(), B, h, w, NP)
+    return out

@@ -155,6 +155,17 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
                        const void *residual, void *out, int out_mode,
                        int B, int D, int H, int W, int cp, int np, int relu, void *stream);
 
+/* 3x3 Conv2d (pad 1, stride 1) + bias [+ ReLU] as a TF32 implicit GEMM on the same tcgen05 kernel
+ * (kind::tf32, fp32 operands in shared memory, fp32 accumulation): the 81-channel convs of
+ * DynamicUpsampling.weight_learning (modules/submodule.py:571-575), which are GEMM-sized.
+ *   x fp32 channels-last [B,H,W,cp] (cp multiple of 8), w_packed fp32 [9][np][cp] (tap = ky*3+kx, BN folded),
+ *   bias fp32 [np], out fp32 channels-last [B,H,W,np] (np multiple of 16).  Same precision class as
+ *   cuDNN's default TF32 convolutions.
+ *   round_out_tf32 != 0 rounds the stored outputs to TF32 (nearest) when they feed another tf32 conv
+ *   (the MMA itself truncates; callers should likewise pre-round x and w_packed). */
+int decnet_conv2d_tf32_nhwc(const float *x_nhwc, const float *w_packed, const float *bias, float *out,
+                            int B, int H, int W, int cp, int np, int relu, int round_out_tf32, void *stream);
+
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */
@@ -189,6 +200,13 @@ int decnet_dynup_pack(const float *disp, const float *left_fea, float *out,
  * pixel-shuffled.  Replaces softmax/unfold/mul/sum/pixel_shuffle (submodule.py:581-589). */
 int decnet_dynup_glue(const float *logits, const float *disp, float *out,
                       int B, int h, int w, void *stream);
+
+/* Channels-last variants around decnet_conv2d_tf32_nhwc: pack writes [B,h,w,CP] (CP >= 9C+1, padding
+ * channels zero), glue reads logits [B,h,w,NP] (NP >= 81, channel = sub*9+k). */
+int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
+                           int B, int C, int h, int w, int CP, int round_tf32, void *stream);
+int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out,
+                           int B, int h, int w, int NP, void *stream);
 
 /* SoftAttention conv input cat(left_fea, dense, sparse, left_mask, -var) -> [B,C+4,H,W]
  * (modules/SparseDenseNetRefinementMask.py:197). */

@@ -97,3 +97,32 @@ def test_cta_pair_variant_matches_single_cta(B, D, H, W, C, Cout):
     finally:
         _lib.lib().decnet_conv3d_set_variant(0)
     assert torch.equal(a, b_), (a.float() - b_.float()).abs().max()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 60, 108, 217, 81), (1, 20, 36, 649, 81), (2, 45, 50, 81, 81), (1, 180, 324, 73, 81),
+                                            (1, 7, 5, 16, 16)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv2d_tf32_tcgen05_vs_fp32(B, H, W, Cin, Cout, relu):
+    """kind::tf32 implicit GEMM (DynamicUpsampling's 81-channel convs) against cuDNN fp32: TF32 rounds the
+    operands to 10 mantissa bits, so the gate is the TF32 class (2e-3 of the output scale), like cuDNN's default."""
+    import torch.nn.functional as F
+    from decnet_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    want = F.conv2d(x, w, b, padding=1)
+    if relu:
+        want = F.relu(want)
+    cp = (Cin + 7) // 8 * 8
+    xn = torch.zeros(B, H, W, cp, device="cuda")
+    xn[..., :Cin] = x.permute(0, 2, 3, 1)
+    wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp)
+    xn = ((xn.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)      # operands pre-rounded to TF32
+    got = ops.conv2d_tf32_nhwc(xn.contiguous(), wp, bp, relu)
+    assert got.shape == (B, H, W, np_)
+    err = (got[..., :Cout].permute(0, 3, 1, 2) - want).abs().max().item()
+    assert err <= 2e-3 * want.abs().max().item() + 1e-4, (err, want.abs().max().item())
+    if np_ > Cout:
+        assert got[..., Cout:].abs().max().item() == 0

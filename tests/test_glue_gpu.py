@@ -223,3 +223,44 @@ def test_conv2d_small_vs_torch(Cin, Cout, k, dil, H, W, variant):
     finally:
         _lib.lib().decnet_conv2d_set_variant(0)
     assert torch.allclose(got, want, atol=2e-5, rtol=1e-5), (got - want).abs().max()
+
+
+@pytest.mark.parametrize("B,C,h,w", [(2, 8, 30, 54), (1, 24, 20, 36), (1, 72, 7, 12)])
+def test_dynamic_upsampling_tf32_tcgen05_path(B, C, h, w):
+    """Channels-last pack / glue are pure data movement (exact); the TF32 tcgen05 route (taken when
+    torch.backends.cudnn.allow_tf32 is on) stays within the TF32 class of the fp32 cuDNN route."""
+    from decnet_b200 import ops
+    from decnet_b200.model import DynamicUpsampling
+    from oracle import glue as og
+    g = torch.Generator(device="cuda").manual_seed(15)
+    disp = torch.rand(B, h, w, device="cuda", generator=g) * 30
+    Lf = torch.randn(B, C, 3 * h, 3 * w, device="cuda", generator=g) * 0.3
+    cp = (9 * C + 1 + 7) // 8 * 8
+    packed = ops.dynup_pack_nhwc(disp, Lf, cp, round_tf32=False)
+    want = og.dynup_pack(disp, Lf).permute(0, 2, 3, 1)
+    assert torch.equal(packed[..., : 9 * C + 1], want) and packed[..., 9 * C + 1:].abs().max().item() == 0
+    logits = torch.randn(B, h, w, 96, device="cuda", generator=g) * 3
+    a = ops.dynup_glue_nhwc(logits.contiguous(), disp)
+    b_ = ops.dynup_glue(logits[..., :81].permute(0, 3, 1, 2).contiguous(), disp)
+    assert torch.equal(a, b_)
+    m = DynamicUpsampling(C).cuda().eval()
+    for u in m.weight_learning:
+        torch.nn.init.normal_(u.conv.weight, 0, (2.0 / (9 * u.conv.out_channels)) ** 0.5)
+        u.bn.running_mean.normal_(0, 0.05, generator=g); u.bn.running_var.uniform_(0.5, 1.5, generator=g)
+    import decnet_b200.model as dm
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        ref = m(disp, Lf)                                   # cuDNN fp32
+        torch.backends.cudnn.allow_tf32 = True
+        got = m(disp, Lf)                                   # ours: TF32 tcgen05
+        dm.USE_TF32_TCGEN05 = False
+        cud = m(disp, Lf)                                   # cuDNN TF32 (PyTorch's default precision)
+    finally:
+        dm.USE_TF32_TCGEN05 = True
+        torch.backends.cudnn.allow_tf32 = old
+    # Same precision class as the library's default: our deviation from fp32 is gated by cuDNN-TF32's own
+    # deviation on the same (adversarial: iid random disparities, random-init logits) input.
+    ours_max, ours_mean = float((got - ref).abs().max()), float((got - ref).abs().mean())
+    lib_max, lib_mean = float((cud - ref).abs().max()), float((cud - ref).abs().mean())
+    assert ours_mean <= 2.0 * lib_mean + 1e-4 and ours_max <= 3.0 * lib_max + 1e-3, (ours_max, ours_mean, lib_max, lib_mean)
