@@ -1,0 +1,450 @@
+// decnet_b200/csrc/conv2d_tcgen05.cu -- the small 3x3 Conv2d layers of the fine stages (detail detection,
+// soft attention, refinement: modules/submodule.py:347-372, 593-604, 666-762) as TF32 implicit GEMMs on the
+// 5th-generation tensor cores, reading and writing the reference's own NCHW fp32 tensors.
+//
+// Why not the channels-last kernel of conv3d_tcgen05.cu: these layers have 1..24 channels, their
+// neighbours (pack / warp / blend kernels, SpaMat) are NCHW, and at 8 channels a channels-last row is
+// 32 bytes.  In NCHW the pixels of one image row are contiguous, so pixels become the GEMM M
+// dimension of an **MN-major** A operand:
+//
+//   D[m = pixel, n = (kw, cout)] += A[m, k = cin] * Wt[k, n]          per row tap kh
+//
+//   * A tile: ONE 4-D TMA box {32 px, 8 ch, RH rows, 1} of the view (W, C, H, B) of x, at signed
+//     coordinates (zero padding = TMA out-of-bounds fill).  TMA writes [row][ch][32 px] = one 1 KB
+//     block per image row, which is exactly two UMMA "MN-major, 128-byte swizzle with 32-byte
+//     atoms" k-atoms (4 ch x 128 B each; SBO = 512 B), image rows being the m-atoms (LBO = 1 KB).
+//     fp32 MN-major operands exist only in that layout (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B
+//     = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B on the TMA side; checked in scripts/micro/umma_tf32_mn.cu).
+//   * One MMA = M 128 (4 image rows x 32 px), K 8 (one channel chunk), N = 3*CP rounded up to 32.
+//     The row tap kh is a row offset into the same smem tile (dilation d: kh*d rows), so a tile of
+//     R = 4G output rows needs its R+2d input rows loaded ONCE.
+//   * The column tap kw cannot be an address offset (a 4-byte shift is below the descriptor's 16-byte
+//     granularity), so the three kw taps are three groups of N columns: D_kw[px] = x[px] * w[., kw]
+//     at the UNSHIFTED pixel, and the epilogue -- one warp per image row, lane = pixel -- adds
+//     D_0[lane-d] + D_1[lane] + D_2[lane+d] with two warp shuffles.  Lanes d..31-d are valid.  TMA needs
+//     the box's first column 16-byte aligned (measured: scripts/micro/tma4d_probe.cu), so tiles advance by
+//     S = (32-2d) rounded down to 4 columns (28 of 32 lanes useful at d = 1) from column -roundup4(d).
+//   * kind::tf32 truncates fp32 operands; four converter warps round every landed tile to TF32
+//     (cvt.rna, what cuDNN's TF32 path does) in place before the MMA warp reads it.  Weights are
+//     rounded on the host.
+//
+// Warp roles (704 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-5 = converters,
+// 6-21 = epilogue.  Persistent CTAs, smem ring of RH-KB stages, two TMEM accumulator slots, the
+// weights of the whole layer resident in smem.
+#include "common.cuh"
+#include "tma_utils.cuh"
+#include <mutex>
+
+namespace decnet {
+namespace conv2dtc {
+
+constexpr int kMaxStages = 8;
+constexpr int kConvWarps = 4;
+constexpr int kEpiWarps = 16;              // 4 per TMEM lane quarter
+constexpr int kThreads = 32 * (2 + kConvWarps + kEpiWarps);
+constexpr int kRowBlock = 1024;            // one image row of a stage: 8 channels x 32 pixels x 4 bytes
+constexpr int kWBox = 64;                  // weight rows (128 B each) per TMA box
+
+struct Params {
+    const float *bias;                     // [CP]
+    float *out;                            // [B][Cout][H][W]
+    int B, Cout, H, W;
+    int dil;                               // dilation = padding
+    int nck;                               // channel chunks of 8
+    int CP, N, natoms;                     // Cout rounded up to 4; MMA N = 3*CP rounded up to 32; N/32
+    int G, RH, vw, pad;                    // row groups per tile (R = 4G), input rows per stage, columns per tile, first box column = -pad
+    int tw, th, num_tiles, stages;
+    int relu;
+    int w_rows, w_bytes;                   // packed weight rows (of 128 B) and the smem reserved for them
+    int tmem_cols;
+    long long *prof;                       // tuning only: per-role cycle counters of CTA 0 (16 int64), or null
+    int dbg;                               // tuning only: 1 skip rounding, 2 skip epilogue math/stores, 4 skip MMAs
+};
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// MN-major, SWIZZLE_128B_BASE32B: start>>4 | LBO (mn-atom stride 1024 B)>>4 at 16 | SBO (k-atom stride 512 B)>>4
+// at 32 | version 1 at 46 | layout type 1 at 61
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (64ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32_mn(int N) {
+    // c_format F32, a/b format TF32 (2), a_major = b_major = MN (bits 15, 16), n_dim N>>3 at 17, m_dim 128>>4 at 24
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+}
+// whole warp converged; one elected lane issues (see conv3d_tcgen05.cu on why the election lives inside the asm)
+__device__ __forceinline__ void umma_tf32_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t rna_tf32(uint32_t x) {
+    // == cvt.rna.tf32.f32 for finite values (round to nearest, ties away), as two full-rate integer ops
+    return (x + 0x1000u) & 0xFFFFE000u;
+}
+
+template <int NC> struct TmemLd;
+template <> struct TmemLd<4> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[4]) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    }
+};
+template <> struct TmemLd<8> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[8]) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+    }
+};
+
+// Epilogue of one warp.  kEpiWarps/4 warps share each TMEM lane quarter (row groups g = part, part + 4, ...).
+// A work item is (row group g, NC output channels from c0): TMEM -> registers, the column taps by warp
+// shuffle (left neighbour's kw=0 product, own kw=1, right neighbour's kw=2), bias, ReLU, store.  This
+// warp's own instruction latency is the budget, so no divisions and no recomputed addresses in the loop.
+template <int NC>
+__device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, uint64_t *tmem_full_bar,
+                                         uint64_t *tmem_empty_bar, uint32_t tmem_base, int acc_stride,
+                                         int warp, int lane, long long (&prof_acc)[4])
+{
+    const int q = warp & 3;                                   // TMEM lane quarter = row within the group
+    const int half = (warp - (2 + kConvWarps)) >> 2;          // row groups half, half + kEpiWarps/4, ...
+    const int d = p.dil;
+    const bool lane_ok = lane >= d && lane < d + p.vw;        // d + vw <= 32 - d
+    const size_t plane = (size_t)p.H * p.W;
+    const int G = (p.dbg & 2) ? 0 : p.G, CP = p.CP, N = p.N;
+    const size_t gstride = (size_t)4 * p.W;
+    const float floor_ = p.relu ? 0.f : -INFINITY;            // ReLU as an unconditional max
+    // tile cursor without divisions: (tx, ty, b) advance by gridDim.x tiles
+    int tx, ty, tb;
+    { int t = blockIdx.x; tx = t % p.tw; t /= p.tw; ty = t % p.th; tb = t / p.th; }
+    const int dx = gridDim.x % p.tw, dy = (gridDim.x / p.tw) % p.th, db = gridDim.x / (p.tw * p.th);
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+        const int col = tx * p.vw - p.pad + lane;
+        const int h0 = ty * (4 * p.G);
+        const bool col_ok = lane_ok && col >= 0 && col < p.W;
+        const int slot = j & 1;
+        const long long tq0 = clock64();
+        mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
+        prof_acc[0] += clock64() - tq0;
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * acc_stride);
+        float *orow0 = p.out + (size_t)tb * p.Cout * plane + (size_t)(h0 + q) * p.W + col;
+        const int rows_left = p.H - (h0 + q);                 // row 4g+q is inside the image iff 4g < rows_left
+        uint32_t A[3][NC];
+        auto issue = [&](uint32_t (&v)[3][NC], int g, int c0) {
+            const uint32_t ta = trow + (uint32_t)(g * N + c0);
+            TmemLd<NC>::ld(ta, v[0]);
+            TmemLd<NC>::ld(ta + (uint32_t)CP, v[1]);
+            TmemLd<NC>::ld(ta + (uint32_t)(2 * CP), v[2]);
+        };
+        auto finish = [&](const uint32_t (&v)[3][NC], int g, int c0) {
+            float x[NC];
+#pragma unroll
+            for (int i4 = 0; i4 < NC; i4 += 4) {
+                const float4 bv = *reinterpret_cast<const float4 *>(bias_s + c0 + i4);
+                const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[0][i4 + i]), d);
+                    const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v[2][i4 + i]), d);
+                    x[i4 + i] = fmaxf((left + __uint_as_float(v[1][i4 + i])) + (right + bb[i]), floor_);
+                }
+            }
+            if (col_ok && 4 * g < rows_left) {
+                float *op = orow0 + (size_t)g * gstride + (size_t)c0 * plane;
+                if (c0 + NC <= p.Cout) {                      // full chunk: straight-line stores
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) { *op = x[i]; op += plane; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) { if (c0 + i < p.Cout) *op = x[i]; op += plane; }
+                }
+            }
+        };
+        // four warps per lane quarter: the other warps' items hide this warp's TMEM-load latency
+        for (int g = half; g < G; g += kEpiWarps / 4)
+            for (int c0 = 0; c0 < CP; c0 += NC) {
+                issue(A, g, c0);
+                tmem_ld_wait();
+                finish(A, g, c0);
+            }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
+        tx += dx; if (tx >= p.tw) { tx -= p.tw; ++ty; }
+        ty += dy; if (ty >= p.th) { ty -= p.th; ++tb; }
+        tb += db;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];       // TMA landed
+    __shared__ __align__(8) uint64_t ready_bar[kMaxStages];      // rounded to TF32
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];      // MMAs that read the stage retired
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t w_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float bias_s[96];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if (threadIdx.x < p.CP) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+    unsigned char *wsm = base;                                   // resident weights
+    unsigned char *ring = base + p.w_bytes;                      // stages
+    const int stage_bytes = p.RH * kRowBlock;
+    const int kStages = p.stages;
+    const int acc_stride = p.G * p.N;                            // TMEM columns per accumulator slot
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kEpiWarps); }
+        mbar_init(&w_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    long long prof_acc[4] = {0, 0, 0, 0};
+    const long long prof_t0 = clock64();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            // the layer's weights, once: rows of 128 B = [kh][chunk][n-atom][8 k][32 n], already TF32-rounded
+            const int nbox = (p.w_rows + kWBox - 1) / kWBox;
+            mbar_arrive_expect_tx(&w_bar, (uint32_t)(nbox * kWBox * 128));
+            for (int i = 0; i < nbox; ++i) tma_load_2d(wsm + (size_t)i * kWBox * 128, &tmW, 0, i * kWBox, &w_bar);
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int x0 = (t % p.tw) * p.vw - p.pad; t /= p.tw;      // multiple of 4 columns (TMA alignment)
+                const int h0 = (t % p.th) * (4 * p.G); t /= p.th;
+                const int b = t;
+                for (int ck = 0; ck < p.nck; ++ck) {
+                    const long long tq0 = clock64();
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    prof_acc[0] += clock64() - tq0;
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                    tma_load_4d(ring + (size_t)s * stage_bytes, &tmX, x0, ck * 8, h0 - p.dil, b, &full_bar[s]);
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_tf32_mn(p.N);
+        const uint32_t ring_base = smem_u32(ring);
+        const uint32_t w_base = smem_u32(wsm);
+        const uint32_t empty_base = smem_u32(&empty_bar[0]);
+        mbar_wait(&w_bar, 0);
+        int s = 0; uint32_t ph = 0; int j = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+            const int slot = j & 1;
+            long long tq0 = clock64();
+            mbar_wait(&tmem_empty_bar[slot], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            prof_acc[0] += clock64() - tq0;
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
+            for (int ck = 0; ck < p.nck; ++ck) {
+                tq0 = clock64();
+                mbar_wait(&ready_bar[s], ph);
+                prof_acc[1] += clock64() - tq0;
+                tc_fence_after();
+                const uint32_t sa = ring_base + (uint32_t)(s * stage_bytes);
+                for (int g = 0; g < ((p.dbg & 4) ? 0 : p.G); ++g) {
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t da = make_desc_mn(sa + (uint32_t)((4 * g + kh * p.dil) * kRowBlock));
+                        const uint64_t db = make_desc_mn(w_base + (uint32_t)(((kh * p.nck + ck) * p.natoms) * kRowBlock));
+                        umma_tf32_elect(acc + (uint32_t)(g * p.N), da, db, idesc, (ck | kh) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit_elect(empty_base + (uint32_t)(s * 8));
+                if (++s == kStages) { s = 0; ph ^= 1u; }
+            }
+            umma_commit_elect(smem_u32(&tmem_full_bar[slot]));
+        }
+    } else if (warp < 2 + kConvWarps) {
+        // ===================== converters: round the landed tile to TF32 in place =====================
+        const int ctid = threadIdx.x - 64;
+        const int n16 = stage_bytes >> 4;                         // 16-byte words in a stage (RH * 64)
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int ck = 0; ck < p.nck; ++ck) {
+                const long long tq0 = clock64();
+                mbar_wait(&full_bar[s], ph);
+                prof_acc[0] += clock64() - tq0;
+                uint4 *st = reinterpret_cast<uint4 *>(ring + (size_t)s * stage_bytes);
+#pragma unroll 4
+                for (int i = ctid; i < ((p.dbg & 1) ? 0 : n16); i += kConvWarps * 32) {
+                    uint4 v = st[i];
+                    v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
+                    st[i] = v;
+                }
+                fence_proxy_async_smem();                         // generic-proxy writes -> visible to the MMA's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready_bar[s]);
+                if (++s == kStages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 6..21): one warp per image row of a row group =====================
+        if (p.CP & 4) epilogue<4>(p, bias_s, tmem_full_bar, tmem_empty_bar, tmem_base, acc_stride, warp, lane, prof_acc);
+        else epilogue<8>(p, bias_s, tmem_full_bar, tmem_empty_bar, tmem_base, acc_stride, warp, lane, prof_acc);
+    }
+    if (p.prof && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6)) {
+        const int r = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : 3;      // producer, MMA, converter, epilogue
+        p.prof[4 * r + 0] = clock64() - prof_t0;       // cycles alive
+        p.prof[4 * r + 1] = prof_acc[0];               // waiting: empty stage | TMEM slot | landed stage | full accumulator
+        p.prof[4 * r + 2] = prof_acc[1];               // MMA warp: waiting for a rounded stage
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// Shape support and tile plan (host).  Returns false when the layer does not fit this kernel.
+static bool plan(int Cin, int Cout, int H, int W, int dil, int B, Params &p, size_t &smem)
+{
+    if (Cin < 1 || Cout < 1 || dil < 1 || dil > 12 || (W & 3) != 0) return false;   // TMA strides: multiples of 16 B
+    p.nck = (Cin + 7) / 8;
+    p.CP = Cout <= 4 ? 4 : (Cout + 7) / 8 * 8;
+    p.N = (3 * p.CP + 31) / 32 * 32;
+    if (p.N > 256) return false;
+    p.natoms = p.N / 32;
+    p.w_rows = 3 * p.nck * p.natoms * 8;
+    p.w_bytes = (int)round_up((size_t)p.w_rows * 128, (size_t)kWBox * 128);
+    if (p.w_bytes > 96 * 1024) return false;
+    p.dil = dil;
+    p.vw = (32 - 2 * dil) / 4 * 4;
+    p.pad = (dil + 3) / 4 * 4;
+    // tile t writes columns [t*vw - pad + dil, t*vw - pad + dil + vw)
+    p.tw = (W + p.pad - dil + p.vw - 1) / p.vw;
+    const int sms = sm_count_cached();
+    int gmax = 256 / p.N;                                        // two slots of G*N columns in 512
+    if (gmax > 8) gmax = 8;
+    if (gmax < 1) return false;
+    // tallest tile that still leaves every SM at least two tiles (small images: shorter tiles, more of them)
+    int G = gmax;
+    while (G > 1 && (long long)B * p.tw * ((H + 4 * G - 1) / (4 * G)) < 2ll * sms) G >>= 1;
+    p.G = G;
+    p.RH = 4 * G + 2 * dil;
+    if (p.RH > 256) return false;
+    p.th = (H + 4 * G - 1) / (4 * G);
+    const long long tiles = (long long)B * p.tw * p.th;
+    if (tiles >= (1ll << 31)) return false;
+    p.num_tiles = (int)tiles;
+    const size_t stage = (size_t)p.RH * kRowBlock;
+    const size_t avail = 226 * 1024 - 1024 - (size_t)p.w_bytes;
+    p.stages = (int)(avail / stage);
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    if (p.stages < 2) return false;
+    const int cols = 2 * G * p.N;
+    p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    smem = (size_t)p.w_bytes + (size_t)p.stages * stage + 1024;
+    return true;
+}
+
+}  // namespace conv2dtc
+}  // namespace decnet
+
+using namespace decnet;
+using namespace decnet::conv2dtc;
+
+extern "C" {
+
+static thread_local int g_conv2dtc_dbg = 0;
+static thread_local long long *g_conv2dtc_prof = nullptr;
+void decnet_conv2d_tf32_debug(int flags, void *prof16) { g_conv2dtc_dbg = flags; g_conv2dtc_prof = static_cast<long long *>(prof16); }
+
+int decnet_conv2d_tf32_supported(int Cin, int Cout, int H, int W, int dilation)
+{
+    Params p{};
+    size_t smem = 0;
+    return plan(Cin, Cout, H, W, dilation, 1, p, smem) ? 1 : 0;
+}
+
+int decnet_conv2d_tf32_packed_floats(int Cin, int Cout)
+{
+    const int nck = (Cin + 7) / 8, CP = Cout <= 4 ? 4 : (Cout + 7) / 8 * 8, N = (3 * CP + 31) / 32 * 32;
+    return 3 * nck * (N / 32) * 8 * 32;
+}
+
+int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *bias_padded, float *out,
+                            int B, int Cin, int Cout, int H, int W, int dilation, int relu, void *stream)
+{
+    DECNET_REQUIRE(x && w_packed && bias_padded && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && H > 0 && W > 0, "non-positive size");
+    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0,
+                   "x and w_packed must be 16-byte aligned");
+    Params p{};
+    size_t smem = 0;
+    DECNET_REQUIRE(plan(Cin, Cout, H, W, dilation, B, p, smem),
+                   "conv2d_tf32_nchw: unsupported shape Cin=%d Cout=%d H=%d W=%d dilation=%d (see decnet_conv2d_tf32_supported)",
+                   Cin, Cout, H, W, dilation);
+    p.dbg = g_conv2dtc_dbg; p.prof = g_conv2dtc_prof;
+    p.bias = bias_padded; p.out = out; p.B = B; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu;
+    CUtensorMap tmX, tmW;
+    {
+        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)Cin, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)H * W * 4, (uint64_t)W * 4, (uint64_t)Cin * H * W * 4};
+        const uint32_t box[4] = {32u, 8u, (uint32_t)p.RH, 1u};
+        int rc = encode_tensor_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box,
+                                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {32u, (uint64_t)p.w_rows};
+        const uint64_t strides[1] = {128u};
+        const uint32_t box[2] = {32u, (uint32_t)kWBox};
+        int rc = encode_tensor_map(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w_packed, dims, strides, box,
+                                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    {
+        static std::mutex mu;
+        static size_t set_for[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || set_for[dev] < smem) {
+            DECNET_CUDA(cudaFuncSetAttribute(conv2d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) set_for[dev] = smem;
+        }
+    }
+    const int sms = sm_count_cached();
+    const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
+    conv2d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+    return after_launch("conv2d_tcgen05_kernel");
+}
+
+}  // extern "C"

@@ -73,8 +73,32 @@ class Conv2dUnit(nn.Module):
             self._native = (self._folded, ops.pack_conv2d_weights(w), b.float().contiguous())
         return self._native
 
+    def tensor_core(self, x):
+        """Packed weights for the NCHW TF32 tcgen05 kernel when this layer / input is one of its shapes and
+        TF32 is allowed (PyTorch's default for cuDNN convolutions, i.e. what the reference runs), else None.
+        Thin layers (Cin < 8 with one output, or wide dilations on 4 channels) stay on the fp32 direct
+        kernel, which is faster there (scripts/exp_conv2d_tc.py)."""
+        c = self.conv
+        d = c.dilation[0]
+        cin, cout = c.in_channels, c.out_channels
+        ok = (USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32 and c.kernel_size == (3, 3) and c.stride == (1, 1)
+              and c.dilation == (d, d) and c.padding == (d, d) and c.groups == 1
+              and ((d <= 4 and (cin >= 8 or cout >= 3)) or (d <= 8 and cin >= 8))
+              and ops.conv2d_tf32_supported(cin, cout, x.shape[2], x.shape[3], d))
+        if not ok:
+            return None
+        if getattr(self, "_tc", None) is None or self._tc[0] is not self._folded:
+            w, b = self.folded()
+            self._tc = (self._folded,) + ops.pack_conv2d_tf32_nchw_weights(w, b)
+        return self._tc
+
     def forward(self, x, addend=None):
-        nat = self.native() if (x.is_cuda and x.dtype == torch.float32 and USE_NATIVE_CONV2D) else None
+        fast = x.is_cuda and x.dtype == torch.float32 and USE_NATIVE_CONV2D
+        tc = self.tensor_core(x) if (fast and addend is None) else None
+        if tc is not None:
+            c = self.conv
+            return ops.conv2d_tf32_nchw(x.contiguous(), tc[1], tc[2], c.out_channels, c.dilation[0], self.relu)
+        nat = self.native() if fast else None
         if nat is not None:
             c = self.conv
             return ops.conv2d_small(x.contiguous(), nat[1], nat[2], c.out_channels, c.kernel_size[0], c.dilation[0],
@@ -122,6 +146,8 @@ def _reset_folded(module):
             m._packed = None
         if hasattr(m, "_native"):
             m._native = None
+        if hasattr(m, "_tc"):
+            m._tc = None
 
 
 # --------------------------------------------------------------------------------------

@@ -347,6 +347,41 @@ def conv2d_tf32_nhwc(x_nhwc, w_packed, bias, relu, round_out=False):
     return out
 
 
+# --------------------------------------------------------------------------------------
+# small 3x3 Conv2d on NCHW fp32 tensors, TF32 tensor cores with pixels as the MN-major M dimension
+# --------------------------------------------------------------------------------------
+def conv2d_tf32_supported(cin, cout, H, W, dilation=1):
+    return bool(_lib.lib().decnet_conv2d_tf32_supported(int(cin), int(cout), int(H), int(W), int(dilation)))
+
+
+def pack_conv2d_tf32_nchw_weights(w, bias):
+    """[Cout,Cin,3,3] (+ bias [Cout]) -> (rows of 32 floats as include/decnet_b200.h describes, bias [CP])."""
+    cout, cin = w.shape[:2]
+    nck, cp = (cin + 7) // 8, (4 if cout <= 4 else (cout + 7) // 8 * 8)
+    natoms = (3 * cp + 31) // 32
+    # B[kh][ci][col = kw*CP + co]
+    bm = torch.zeros((3, nck * 8, natoms * 32), dtype=torch.float32, device=w.device)
+    wf = w.float()
+    for kw in range(3):
+        bm[:, :cin, kw * cp: kw * cp + cout] = wf[:, :, :, kw].permute(2, 1, 0)       # [kh][ci][co]
+    # -> [kh][chunk][atom][k][n]
+    out = bm.view(3, nck, 8, natoms, 32).permute(0, 1, 3, 2, 4).contiguous()
+    out = ((out.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)            # cvt.rna to TF32
+    assert out.numel() == _lib.lib().decnet_conv2d_tf32_packed_floats(int(cin), int(cout))
+    b = torch.zeros(cp, dtype=torch.float32, device=w.device)
+    b[:cout] = bias.float()
+    return out.contiguous(), b.contiguous()
+
+
+def conv2d_tf32_nchw(x, w_packed, bias_padded, cout, dilation=1, relu=False):
+    _chk("x", x)
+    B, cin, H, W = x.shape
+    out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x.device)
+    _call("decnet_conv2d_tf32_nchw", x, x.data_ptr(), w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(),
+          B, cin, int(cout), H, W, int(dilation), 1 if relu else 0)
+    return out
+
+
 def dynup_pack_nhwc(disp, left_fea, cp, round_tf32=True):
     _chk("disp", disp)
     B, h, w = disp.shape

@@ -166,6 +166,22 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
 int decnet_conv2d_tf32_nhwc(const float *x_nhwc, const float *w_packed, const float *bias, float *out,
                             int B, int H, int W, int cp, int np, int relu, int round_out_tf32, void *stream);
 
+/* 3x3 Conv2d (stride 1, padding = dilation) + bias [+ ReLU] on NCHW fp32 tensors as a TF32 implicit GEMM
+ * with pixels as the MN-major M dimension (conv2d_tcgen05.cu): the 1..24-channel layers of
+ * GenerateSparseMask / SoftAttention / Refinement (modules/submodule.py:347-372, 593-604, 666-762), which the
+ * reference runs through cuDNN (TF32 by default).  Operands are rounded to TF32 (nearest) in the kernel.
+ *   x fp32 [B,Cin,H,W]; out fp32 [B,Cout,H,W]; bias_padded fp32 [CP] (CP = 4 when Cout <= 4, else Cout rounded up to 8);
+ *   w_packed fp32, decnet_conv2d_tf32_packed_floats(Cin,Cout) values laid out as rows of 32:
+ *     row = ((kh*nck + chunk)*natoms + atom)*8 + k,  column n  <->  input channel chunk*8+k, GEMM column
+ *     atom*32+n = kw*CP + cout  (nck = ceil(Cin/8), natoms = ceil(3*CP/32));
+ *     BN folded in, TF32-rounded, zero padded.
+ * decnet_conv2d_tf32_supported: 1 when the shape fits (W % 4 == 0, dilation 1..12, 3*CP <= 256,
+ * resident weights <= 96 KB). */
+int decnet_conv2d_tf32_supported(int Cin, int Cout, int H, int W, int dilation);
+int decnet_conv2d_tf32_packed_floats(int Cin, int Cout);
+int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *bias_padded, float *out,
+                            int B, int Cin, int Cout, int H, int W, int dilation, int relu, void *stream);
+
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */

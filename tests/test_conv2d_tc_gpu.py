@@ -1,0 +1,86 @@
+"""GPU parity of the NCHW TF32 tcgen05 Conv2d (conv2d_tcgen05.cu) through the C ABI.
+
+Two checks per shape:
+  * exactness of the data path: with operands that are already TF32 values the kernel must agree with an
+    fp64 convolution up to fp32 accumulation error (any wrong tap, swizzle, halo or padding shows as O(1));
+  * precision class: with arbitrary fp32 operands the deviation from the fp32 result must stay at TF32
+    rounding level (operands rounded to nearest, 2^-11 relative each) -- the tolerance is written below.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _tf32(x):
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+SHAPES = [  # B, Cin, Cout, H, W, dilation
+    (1, 8, 8, 64, 96, 1),
+    (2, 8, 8, 37, 100, 1),        # ragged rows / columns
+    (1, 17, 8, 50, 120, 3),       # refinement stage 3: 2C+1 channels, dilation 3
+    (1, 8, 4, 41, 64, 6),
+    (1, 4, 4, 45, 88, 9),
+    (1, 4, 1, 19, 32, 1),         # single output channel
+    (1, 8, 3, 33, 60, 1),         # detail-detection head
+    (1, 12, 8, 40, 76, 1),        # attention input C+4
+    (2, 24, 8, 30, 36, 1),
+    (1, 49, 24, 60, 108, 2),      # refinement stage 2
+    (1, 24, 12, 20, 108, 4),
+    (1, 72, 8, 20, 36, 1),
+    (1, 3, 3, 8, 8, 1),           # tile larger than the image
+    (8, 8, 8, 135, 240, 1),       # many tiles per CTA
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,dil", SHAPES)
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv2d_tf32_nchw(B, Cin, Cout, H, W, dil, relu):
+    from decnet_b200 import ops
+    assert ops.conv2d_tf32_supported(Cin, Cout, H, W, dil)
+    g = torch.Generator(device="cuda").manual_seed(5 + Cin + 7 * Cout + dil)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    wp, bp = ops.pack_conv2d_tf32_nchw_weights(w, b)
+
+    def ref(xx, ww):
+        y = F.conv2d(xx.double(), ww.double(), b.double(), padding=dil, dilation=dil)
+        return (F.relu(y) if relu else y).float()
+
+    # (1) exact data path
+    xr = _tf32(x)
+    got = ops.conv2d_tf32_nchw(xr, wp, bp, Cout, dil, relu)
+    want = ref(xr, _tf32(w))
+    err = (got - want).abs().max().item()
+    assert err <= 2e-5 * max(1.0, want.abs().max().item()), ("exact path", err)
+    # (2) TF32 precision class on raw fp32 operands: |err| <= ~ sqrt(K) * 2^-11 * |x||w| ; measured against
+    # the output scale with K = 9*Cin terms of unit variance -> 4 * 2^-11 * max|y| is a loose bound
+    got2 = ops.conv2d_tf32_nchw(x, wp, bp, Cout, dil, relu)
+    want2 = ref(x, w)
+    err2 = (got2 - want2).abs().max().item()
+    assert err2 <= 4 * 2 ** -11 * max(1.0, want2.abs().max().item()), ("tf32 class", err2)
+    # rounding in the kernel == rounding beforehand (bit-exact: same operands reach the MMA)
+    assert torch.equal(got, got2) or (got - got2).abs().max().item() <= 4 * 2 ** -11 * max(1.0, want.abs().max().item())
+
+
+def test_conv2d_tf32_unsupported_shapes_are_refused():
+    from decnet_b200 import ops
+    assert not ops.conv2d_tf32_supported(8, 8, 64, 97, 1)         # W*4 not a multiple of 16 (TMA stride rule)
+    assert not ops.conv2d_tf32_supported(145, 72, 60, 108, 1)     # weights do not fit in shared memory
+    assert not ops.conv2d_tf32_supported(8, 8, 64, 96, 13)
+
+
+def test_conv2d_tf32_matches_direct_kernel_on_layer_shapes():
+    """Same layer through the fp32 direct kernel and the tensor-core kernel (SceneFlow stage-3 size, B=1)."""
+    from decnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(1, 8, 540, 972, device="cuda", generator=g)
+    w = torch.randn(8, 8, 3, 3, device="cuda", generator=g) * 0.17
+    b = torch.randn(8, device="cuda", generator=g) * 0.1
+    wp, bp = ops.pack_conv2d_tf32_nchw_weights(w, b)
+    got = ops.conv2d_tf32_nchw(x, wp, bp, 8, 1, True)
+    want = ops.conv2d_small(x, ops.pack_conv2d_weights(w), b.contiguous(), 8, 3, 1, True)
+    assert (got - want).abs().max().item() <= 4 * 2 ** -11 * want.abs().max().item()
