@@ -51,6 +51,7 @@ struct Params {
     int B, Cout, H, W;
     int dil;                               // dilation = padding
     int nck;                               // channel chunks of 8
+    int ck1, ck2;                          // chunks [0,ck1) come from source 0, [ck1,ck2) from source 1, [ck2,nck) from source 2
     int CP, N, natoms;                     // Cout rounded up to 4; MMA N = 3*CP rounded up to 32; N/32
     int G, RH, vw, pad;                    // row groups per tile (R = 4G), input rows per stage, columns per tile, first box column = -pad
     int tw, th, num_tiles, stages;
@@ -192,7 +193,8 @@ __device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, u
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p)
+conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX1,
+                      const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmW, const Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];       // TMA landed
@@ -215,7 +217,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int acc_stride = p.G * p.N;                            // TMEM columns per accumulator slot
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmX2); tma_prefetch_desc(&tmW);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kEpiWarps); }
         mbar_init(&w_bar, 1);
@@ -251,7 +253,10 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     prof_acc[0] += clock64() - tq0;
                     mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                    tma_load_4d(ring + (size_t)s * stage_bytes, &tmX, x0, ck * 8, h0 - p.dil, b, &full_bar[s]);
+                    // the input is the channel concatenation of up to three tensors (each padded to whole chunks)
+                    const CUtensorMap *tm = ck < p.ck1 ? &tmX : (ck < p.ck2 ? &tmX1 : &tmX2);
+                    const int cl = ck < p.ck1 ? ck : (ck < p.ck2 ? ck - p.ck1 : ck - p.ck2);
+                    tma_load_4d(ring + (size_t)s * stage_bytes, tm, x0, cl * 8, h0 - p.dil, b, &full_bar[s]);
                     if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -399,26 +404,37 @@ int decnet_conv2d_tf32_packed_floats(int Cin, int Cout)
     return 3 * nck * (N / 32) * 8 * 32;
 }
 
-int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *bias_padded, float *out,
-                            int B, int Cin, int Cout, int H, int W, int dilation, int relu, void *stream)
+int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
+                                const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
+                                int relu, void *stream)
 {
-    DECNET_REQUIRE(x && w_packed && bias_padded && out, "null pointer");
+    DECNET_REQUIRE(srcs && src_channels && w_packed && bias_padded && out, "null pointer");
+    DECNET_REQUIRE(nsrc >= 1 && nsrc <= 3, "1..3 concatenated sources, got %d", nsrc);
     DECNET_REQUIRE(B > 0 && H > 0 && W > 0, "non-positive size");
-    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0,
-                   "x and w_packed must be 16-byte aligned");
+    int cin_pad = 0, cks[3] = {0, 0, 0};
+    for (int i = 0; i < nsrc; ++i) {
+        DECNET_REQUIRE(srcs[i] && src_channels[i] >= 1, "source %d: null pointer or no channels", i);
+        DECNET_REQUIRE((reinterpret_cast<uintptr_t>(srcs[i]) & 15u) == 0, "source %d must be 16-byte aligned", i);
+        cks[i] = (src_channels[i] + 7) / 8;
+        cin_pad += 8 * cks[i];
+    }
+    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0, "w_packed must be 16-byte aligned");
     Params p{};
     size_t smem = 0;
-    DECNET_REQUIRE(plan(Cin, Cout, H, W, dilation, B, p, smem),
-                   "conv2d_tf32_nchw: unsupported shape Cin=%d Cout=%d H=%d W=%d dilation=%d (see decnet_conv2d_tf32_supported)",
-                   Cin, Cout, H, W, dilation);
+    DECNET_REQUIRE(plan(cin_pad, Cout, H, W, dilation, B, p, smem),
+                   "conv2d_tf32_nchw: unsupported shape Cin=%d (padded per source) Cout=%d H=%d W=%d dilation=%d "
+                   "(see decnet_conv2d_tf32_supported)", cin_pad, Cout, H, W, dilation);
+    p.ck1 = cks[0]; p.ck2 = cks[0] + cks[1];
     p.dbg = g_conv2dtc_dbg; p.prof = g_conv2dtc_prof;
     p.bias = bias_padded; p.out = out; p.B = B; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu;
-    CUtensorMap tmX, tmW;
-    {
-        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)Cin, (uint64_t)H, (uint64_t)B};
-        const uint64_t strides[3] = {(uint64_t)H * W * 4, (uint64_t)W * 4, (uint64_t)Cin * H * W * 4};
+    CUtensorMap tmX[3], tmW;
+    for (int i = 0; i < 3; ++i) {
+        if (i >= nsrc) { tmX[i] = tmX[0]; continue; }
+        const int Ci = src_channels[i];
+        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)Ci, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)H * W * 4, (uint64_t)W * 4, (uint64_t)Ci * H * W * 4};
         const uint32_t box[4] = {32u, 8u, (uint32_t)p.RH, 1u};
-        int rc = encode_tensor_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box,
+        int rc = encode_tensor_map(&tmX[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, srcs[i], dims, strides, box,
                                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
@@ -443,8 +459,14 @@ int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *
     }
     const int sms = sm_count_cached();
     const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
-    conv2d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+    conv2d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX[0], tmX[1], tmX[2], tmW, p);
     return after_launch("conv2d_tcgen05_kernel");
+}
+
+int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *bias_padded, float *out,
+                            int B, int Cin, int Cout, int H, int W, int dilation, int relu, void *stream)
+{
+    return decnet_conv2d_tf32_nchw_cat(&x, &Cin, 1, w_packed, bias_padded, out, B, Cout, H, W, dilation, relu, stream);
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 // coalesced along W, no temporaries.  Reference sites: SURVEY.md section 8 rows a2, a4, a6, a8,
 // a13, a14 (file:line quoted at each kernel).
 #include "common.cuh"
+#include <algorithm>
 #include <cuda_bf16.h>
 
 namespace decnet {
@@ -323,24 +324,26 @@ dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict
 // a13 (input side): cat(Lf, dense, sparse, lmask, -var) -> [B, C+4, H, W]
 // (SparseDenseNetRefinementMask.py:197).  Flat copy, float4 where aligned.
 // ---------------------------------------------------------------------------------------------
+// grid.y = output plane (b, c): one source plane -> one destination plane, no index arithmetic per element
+template <typename V>
 __global__ void __launch_bounds__(kBlock)
 attn_pack_kernel(const float *__restrict__ Lf, const float *__restrict__ dense, const float *__restrict__ sparse,
                  const float *__restrict__ lmask, const float *__restrict__ var, float *__restrict__ out,
-                 int C, long long HW, long long total)
+                 int C, long long HWv)
 {
-    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
-        const long long per = (long long)(C + 4) * HW;
-        const int b = (int)(i / per);
-        const long long r = i - (long long)b * per;
-        const int c = (int)(r / HW);
-        const long long p = r - (long long)c * HW;
-        float v;
-        if (c < C) v = Lf[((long long)b * C + c) * HW + p];
-        else if (c == C) v = dense[(long long)b * HW + p];
-        else if (c == C + 1) v = sparse[(long long)b * HW + p];
-        else if (c == C + 2) v = lmask[(long long)b * HW + p];
-        else v = -var[(long long)b * HW + p];
-        out[i] = v;
+    const int b = blockIdx.y / (C + 4), c = blockIdx.y - b * (C + 4);
+    const float *src = c < C ? Lf + ((long long)b * C + c) * HWv * (sizeof(V) / 4)
+                             : (c == C ? dense : c == C + 1 ? sparse : c == C + 2 ? lmask : var) + (long long)b * HWv * (sizeof(V) / 4);
+    const V *s = reinterpret_cast<const V *>(src);
+    V *d = reinterpret_cast<V *>(out + (long long)blockIdx.y * HWv * (sizeof(V) / 4));
+    const bool neg = c == C + 3;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < HWv; i += (long long)gridDim.x * kBlock) {
+        V v = __ldg(s + i);
+        if (neg) {
+            if constexpr (sizeof(V) == 16) { v.x = -v.x; v.y = -v.y; v.z = -v.z; v.w = -v.w; }
+            else v = -v;
+        }
+        d[i] = v;
     }
 }
 
@@ -363,6 +366,9 @@ blend_kernel(const float *__restrict__ logit, const float *__restrict__ dense, c
 // submodule.py:719-745) and, when `packed` is given, build the refinement conv input
 // cat(Lf, warped, disp) -> [B, 2C+1, H, W] (:758-759) in the same pass.
 // ---------------------------------------------------------------------------------------------
+// grid.y = (b, group of CG channels): one thread = one pixel x CG channels, all 5*CG loads independent and
+// issued before the first use (the kernel is HBM/L2-latency bound: memory-level parallelism is what matters).
+template <int CG>
 __global__ void __launch_bounds__(kBlock)
 warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const float *__restrict__ disp,
             float *__restrict__ warped, float *__restrict__ packed, int B, int C, int H, int W,
@@ -370,29 +376,64 @@ warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const fl
 {
     // H rows are the window [row0, row0 + H) of an H_total-row image (row-band mode): the vertical
     // coordinate follows the reference's formula on GLOBAL rows; taps outside the window read 0
-    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const long long n = (long long)B * H * W;
-    if (idx >= n) return;
-    const int w = (int)(idx % W), h = (int)((idx / W) % H), b = (int)(idx / ((long long)W * H));
-    const float dv = disp[idx];
+    const int groups = (C + CG - 1) / CG;
+    const int b = blockIdx.y / groups, c0 = (blockIdx.y - b * groups) * CG;
+    const size_t plane = (size_t)H * W;
+    const size_t pix = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (pix >= plane) return;
+    const int h = (int)(pix / W), w = (int)(pix - (size_t)h * W);
+    const float dv = __ldg(disp + (size_t)b * plane + pix);
     const float ix = sample_coord((float)w - dv, (float)W);
     const float iy = sample_coord((float)(row0 + h), (float)H_total) - (float)row0;
     const Taps t = make_taps(ix, iy, H, W);
-    const size_t plane = (size_t)H * W;
-    const size_t pix = (size_t)h * W + w;
-    const float *Rb = Rf + (size_t)b * C * plane;
+    const int x0 = min(max(t.x0, 0), W - 1), x1 = min(max(t.x0 + 1, 0), W - 1);
+    const int y0 = min(max(t.y0, 0), H - 1), y1 = min(max(t.y0 + 1, 0), H - 1);
+    const size_t o00 = (size_t)y0 * W + x0, o01 = (size_t)y0 * W + x1, o10 = (size_t)y1 * W + x0, o11 = (size_t)y1 * W + x1;
+    const float *Rb = Rf + ((size_t)b * C + c0) * plane;
+    float v00[CG], v01[CG], v10[CG], v11[CG], lv[CG];
+#pragma unroll
+    for (int i = 0; i < CG; ++i) {
+        const bool ok = c0 + i < C;
+        const float *rp = Rb + (size_t)i * plane;
+        v00[i] = ok ? __ldg(rp + o00) : 0.f;
+        v01[i] = ok ? __ldg(rp + o01) : 0.f;
+        v10[i] = ok ? __ldg(rp + o10) : 0.f;
+        v11[i] = ok ? __ldg(rp + o11) : 0.f;
+        lv[i] = (packed && ok) ? __ldg(Lf + ((size_t)b * C + c0 + i) * plane + pix) : 0.f;
+    }
     if (packed) {
         float *pb = packed + (size_t)b * (2 * C + 1) * plane + pix;
-        const float *Lb = Lf + (size_t)b * C * plane + pix;
-        for (int c = 0; c < C; ++c) {
-            pb[(size_t)c * plane] = __ldg(Lb + (size_t)c * plane);
-            pb[(size_t)(C + c) * plane] = sample_plane(Rb + (size_t)c * plane, t, H, W);
-        }
-        pb[(size_t)(2 * C) * plane] = dv;
+#pragma unroll
+        for (int i = 0; i < CG; ++i)
+            if (c0 + i < C) {
+                float v = 0.f;                                  // same summation order as sample_plane()
+                v += v00[i] * t.w00; v += v01[i] * t.w01; v += v10[i] * t.w10; v += v11[i] * t.w11;
+                pb[(size_t)(c0 + i) * plane] = lv[i];
+                pb[(size_t)(C + c0 + i) * plane] = v;
+            }
+        if (c0 == 0) pb[(size_t)(2 * C) * plane] = dv;
     } else {
-        float *wb = warped + (size_t)b * C * plane + pix;
-        for (int c = 0; c < C; ++c) wb[(size_t)c * plane] = sample_plane(Rb + (size_t)c * plane, t, H, W);
+        float *wb = warped + ((size_t)b * C + c0) * plane + pix;
+#pragma unroll
+        for (int i = 0; i < CG; ++i)
+            if (c0 + i < C) {
+                float v = 0.f;
+                v += v00[i] * t.w00; v += v01[i] * t.w01; v += v10[i] * t.w10; v += v11[i] * t.w11;
+                wb[(size_t)i * plane] = v;
+            }
     }
+}
+
+static int launch_warp(const float *Lf, const float *Rf, const float *disp, float *warped, float *packed,
+                       int B, int C, int H, int W, int H_total, int row0, cudaStream_t st, const char *name)
+{
+    constexpr int CG = 8;
+    const long long plane = (long long)H * W;
+    const long long gy = (long long)B * ((C + CG - 1) / CG);
+    DECNET_REQUIRE(gy <= 65535, "B * ceil(C/8) = %lld exceeds the grid limit", gy);
+    warp_kernel<CG><<<dim3((unsigned)((plane + kBlock - 1) / kBlock), (unsigned)gy), kBlock, 0, st>>>(
+        Lf, Rf, disp, warped, packed, B, C, H, W, H_total, row0);
+    return after_launch(name);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -545,11 +586,19 @@ int decnet_dynup_glue(const float *logits, const float *disp, float *out, int B,
 
 int decnet_attn_pack(const float *left_fea, const float *dense, const float *sparse, const float *left_mask,
                      const float *var, float *out, int B, int C, int H, int W, void *stream) {
-    DECNET_REQUIRE(left_fea && dense && sparse && left_mask && var && out, "null pointer");
-    DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
-    const long long total = (long long)B * (C + 4) * H * W;
-    attn_pack_kernel<<<grid_for(total, 148 * 32), kBlock, 0, (cudaStream_t)stream>>>(left_fea, dense, sparse, left_mask, var, out,
-                                                                                   C, (long long)H * W, total);
+    DECNET_REQUIRE(dense && sparse && left_mask && var && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && C >= 0 && H > 0 && W > 0 && (C == 0 || left_fea), "bad size or null left_fea with C=%d", C);
+    const long long HW = (long long)H * W;
+    DECNET_REQUIRE((long long)B * (C + 4) <= 65535, "B*(C+4) too large");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(left_fea) | reinterpret_cast<uintptr_t>(dense) |
+                         reinterpret_cast<uintptr_t>(sparse) | reinterpret_cast<uintptr_t>(left_mask) |
+                         reinterpret_cast<uintptr_t>(var) | reinterpret_cast<uintptr_t>(out);
+    const dim3 grid_v((unsigned)std::min<long long>((HW / 4 + kBlock - 1) / kBlock, 64), (unsigned)(B * (C + 4)));
+    if ((HW & 3) == 0 && (al & 15u) == 0)
+        attn_pack_kernel<float4><<<grid_v, kBlock, 0, (cudaStream_t)stream>>>(left_fea, dense, sparse, left_mask, var, out, C, HW / 4);
+    else
+        attn_pack_kernel<float><<<dim3((unsigned)std::min<long long>((HW + kBlock - 1) / kBlock, 64), (unsigned)(B * (C + 4))),
+                                  kBlock, 0, (cudaStream_t)stream>>>(left_fea, dense, sparse, left_mask, var, out, C, HW);
     return after_launch("attn_pack_kernel");
 }
 
@@ -565,10 +614,7 @@ int decnet_blend(const float *logit, const float *dense, const float *sparse, fl
 int decnet_warp_bilinear(const float *right_fea, const float *disp, float *warped, int B, int C, int H, int W, void *stream) {
     DECNET_REQUIRE(right_fea && disp && warped, "null pointer");
     DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
-    const long long n = (long long)B * H * W;
-    warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(nullptr, right_fea, disp, warped, nullptr,
-                                                                                          B, C, H, W, H, 0);
-    return after_launch("warp_kernel");
+    return launch_warp(nullptr, right_fea, disp, warped, nullptr, B, C, H, W, H, 0, (cudaStream_t)stream, "warp_kernel");
 }
 
 int decnet_refine_pack_rows(const float *left_fea, const float *right_fea, const float *disp, float *out,
@@ -576,10 +622,7 @@ int decnet_refine_pack_rows(const float *left_fea, const float *right_fea, const
     DECNET_REQUIRE(left_fea && right_fea && disp && out, "null pointer");
     DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "non-positive size");
     DECNET_REQUIRE(row0 >= 0 && row0 + H <= H_total, "row window [%d,%d) outside the %d-row image", row0, row0 + H, H_total);
-    const long long n = (long long)B * H * W;
-    warp_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(left_fea, right_fea, disp, nullptr, out,
-                                                                                          B, C, H, W, H_total, row0);
-    return after_launch("warp_kernel<pack>");
+    return launch_warp(left_fea, right_fea, disp, nullptr, out, B, C, H, W, H_total, row0, (cudaStream_t)stream, "warp_kernel<pack>");
 }
 
 int decnet_refine_pack(const float *left_fea, const float *right_fea, const float *disp, float *out,

@@ -92,6 +92,26 @@ class Conv2dUnit(nn.Module):
             self._tc = (self._folded,) + ops.pack_conv2d_tf32_nchw_weights(w, b)
         return self._tc
 
+    def forward_cat(self, srcs):
+        """forward(torch.cat(srcs, 1)) with single-channel maps given as [B,H,W]; on the tensor-core path the
+        concatenation is never materialised (the kernel reads each source through its own tensor map)."""
+        x0 = srcs[0]
+        chans = tuple(1 if t.dim() == 3 else t.shape[1] for t in srcs)
+        c = self.conv
+        d = c.dilation[0]
+        ok = (len(srcs) <= 3 and x0.is_cuda and x0.dtype == torch.float32 and USE_NATIVE_CONV2D and USE_TF32_TCGEN05
+              and torch.backends.cudnn.allow_tf32 and c.kernel_size == (3, 3) and c.stride == (1, 1)
+              and c.dilation == (d, d) and c.padding == (d, d) and c.groups == 1 and sum(chans) == c.in_channels
+              and ops.conv2d_tf32_supported(ops.padded_cat_channels(chans), c.out_channels, x0.shape[-2], x0.shape[-1], d))
+        if not ok:
+            return self.forward(torch.cat([t.unsqueeze(1) if t.dim() == 3 else t for t in srcs], 1))
+        cache = getattr(self, "_tc_cat", None)
+        if cache is None or cache[0] is not self._folded or cache[1] != chans:
+            w, b = self.folded()
+            self._tc_cat = (self._folded, chans) + ops.pack_conv2d_tf32_nchw_weights(w, b, chans)
+        return ops.conv2d_tf32_nchw_cat([t.contiguous() for t in srcs], self._tc_cat[2], self._tc_cat[3],
+                                        c.out_channels, d, self.relu)
+
     def forward(self, x, addend=None):
         fast = x.is_cuda and x.dtype == torch.float32 and USE_NATIVE_CONV2D
         tc = self.tensor_core(x) if (fast and addend is None) else None
@@ -148,6 +168,8 @@ def _reset_folded(module):
             m._native = None
         if hasattr(m, "_tc"):
             m._tc = None
+        if hasattr(m, "_tc_cat"):
+            m._tc_cat = None
 
 
 # --------------------------------------------------------------------------------------
@@ -326,6 +348,11 @@ class SoftAttention(nn.Module):
     def logits(self, x):
         return self.conv(x)
 
+    def logits_cat(self, left_fea, aux):
+        """logits(cat(left_fea, aux)) with aux = [dense, sparse, left_mask, -var] as one [B,4,H,W] tensor."""
+        x = self.conv[0].forward_cat([left_fea, aux])
+        return self.conv[2](self.conv[1](x))
+
     def forward(self, x):
         return torch.sigmoid(self.conv(x))
 
@@ -350,8 +377,18 @@ class Refinement(nn.Module):
 
     def forward(self, left_fea, right_fea, disp_map):
         disp_map = disp_map.contiguous()
-        x = ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map)
-        for unit in list(self.conv)[:-1]:
+        units = list(self.conv)
+        c0 = units[0].conv
+        C = left_fea.shape[1]
+        if (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32
+                and ops.conv2d_tf32_supported(ops.padded_cat_channels((C, C, 1)), c0.out_channels, left_fea.shape[2],
+                                              left_fea.shape[3], c0.dilation[0])):
+            # first conv reads (left, warped right, disparity) as three sources: only the warp is materialised
+            warped = ops.warp_bilinear(right_fea.contiguous(), disp_map)
+            x = units[0].forward_cat([left_fea.contiguous(), warped, disp_map])
+        else:
+            x = units[0](ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map))
+        for unit in units[1:-1]:
             x = unit(x)
         residual = self.conv[-1](x).squeeze(1)
         return disp_map + residual, residual
@@ -436,8 +473,8 @@ class DecompMatching(nn.Module):
                     lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
                 dense = self.dynamic_upsampling[l](pred, Lf)
                 sparse, var, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm, rm, D)     # SpaMat + SpaVar, one pass
-                x = ops.attn_pack(Lf, dense, sparse, lm, var)
-                logit = self.soft_attention[l].logits(x).squeeze(1).contiguous()
+                aux = ops.attn_pack(None, dense, sparse, lm, var)                  # [dense, sparse, mask, -var]
+                logit = self.soft_attention[l].logits_cat(Lf, aux).squeeze(1).contiguous()
                 soft, fused = ops.blend(logit, dense, sparse, want_mask=is_check)
                 pred, residual = self.refinement[l](Lf, Rf, fused)
                 if is_check:

@@ -217,13 +217,20 @@ def dynup_glue(logits, disp):
 
 
 def attn_pack(left_fea, dense, sparse, left_mask, var):
-    _chk("left_fea", left_fea)
-    B, Cc, H, W = left_fea.shape
-    for n, t in (("dense", dense), ("sparse", sparse), ("left_mask", left_mask), ("var", var)):
-        _chk(n, t, left_fea, (B, H, W))
-    out = torch.empty((B, Cc + 4, H, W), dtype=torch.float32, device=left_fea.device)
-    _call("decnet_attn_pack", left_fea, left_fea.data_ptr(), dense.data_ptr(), sparse.data_ptr(),
-          left_mask.data_ptr(), var.data_ptr(), out.data_ptr(), B, Cc, H, W)
+    """cat(left_fea, dense, sparse, left_mask, -var) -> [B,C+4,H,W]; left_fea=None packs the four maps only."""
+    _chk("dense", dense)
+    B, H, W = dense.shape
+    Cc = 0
+    if left_fea is not None:
+        _chk("left_fea", left_fea, dense)
+        Cc = left_fea.shape[1]
+        if tuple(left_fea.shape) != (B, Cc, H, W):
+            raise ValueError(f"left_fea {tuple(left_fea.shape)} does not match dense {tuple(dense.shape)}")
+    for n, t in (("sparse", sparse), ("left_mask", left_mask), ("var", var)):
+        _chk(n, t, dense, (B, H, W))
+    out = torch.empty((B, Cc + 4, H, W), dtype=torch.float32, device=dense.device)
+    _call("decnet_attn_pack", dense, left_fea.data_ptr() if left_fea is not None else None, dense.data_ptr(),
+          sparse.data_ptr(), left_mask.data_ptr(), var.data_ptr(), out.data_ptr(), B, Cc, H, W)
     return out
 
 
@@ -354,14 +361,29 @@ def conv2d_tf32_supported(cin, cout, H, W, dilation=1):
     return bool(_lib.lib().decnet_conv2d_tf32_supported(int(cin), int(cout), int(H), int(W), int(dilation)))
 
 
-def pack_conv2d_tf32_nchw_weights(w, bias):
-    """[Cout,Cin,3,3] (+ bias [Cout]) -> (rows of 32 floats as include/decnet_b200.h describes, bias [CP])."""
+def padded_cat_channels(src_channels):
+    return sum((c + 7) // 8 * 8 for c in src_channels)
+
+
+def pack_conv2d_tf32_nchw_weights(w, bias, src_channels=None):
+    """[Cout,Cin,3,3] (+ bias [Cout]) -> (rows of 32 floats as include/decnet_b200.h describes, bias [CP]).
+    src_channels: the input is a concatenation of tensors with these channel counts (sum = Cin), each
+    padded to whole 8-channel chunks for decnet_conv2d_tf32_nchw_cat."""
     cout, cin = w.shape[:2]
+    wf = w.float()
+    if src_channels is not None and len(src_channels) > 1:
+        assert sum(src_channels) == cin, (src_channels, cin)
+        wp_ = torch.zeros((cout, padded_cat_channels(src_channels), 3, 3), dtype=torch.float32, device=w.device)
+        o = i = 0
+        for c in src_channels:
+            wp_[:, o:o + c] = wf[:, i:i + c]
+            o += (c + 7) // 8 * 8
+            i += c
+        wf, cin = wp_, wp_.shape[1]
     nck, cp = (cin + 7) // 8, (4 if cout <= 4 else (cout + 7) // 8 * 8)
     natoms = (3 * cp + 31) // 32
     # B[kh][ci][col = kw*CP + co]
     bm = torch.zeros((3, nck * 8, natoms * 32), dtype=torch.float32, device=w.device)
-    wf = w.float()
     for kw in range(3):
         bm[:, :cin, kw * cp: kw * cp + cout] = wf[:, :, :, kw].permute(2, 1, 0)       # [kh][ci][co]
     # -> [kh][chunk][atom][k][n]
@@ -379,6 +401,28 @@ def conv2d_tf32_nchw(x, w_packed, bias_padded, cout, dilation=1, relu=False):
     out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x.device)
     _call("decnet_conv2d_tf32_nchw", x, x.data_ptr(), w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(),
           B, cin, int(cout), H, W, int(dilation), 1 if relu else 0)
+    return out
+
+
+def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=False):
+    """Conv over torch.cat(srcs, 1) without building it; srcs: 1..3 tensors [B,Ci,H,W] or [B,H,W] (one channel)."""
+    import ctypes
+    x0 = srcs[0]
+    _chk("srcs[0]", x0)
+    B, H, W = x0.shape[0], x0.shape[-2], x0.shape[-1]
+    chans = []
+    for i, t in enumerate(srcs):
+        _chk(f"srcs[{i}]", t, x0)
+        c = 1 if t.dim() == 3 else t.shape[1]
+        if (t.shape[0], t.shape[-2], t.shape[-1]) != (B, H, W):
+            raise ValueError(f"srcs[{i}] {tuple(t.shape)} does not match srcs[0] {tuple(x0.shape)}")
+        chans.append(int(c))
+    n = len(srcs)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    cs = (ctypes.c_int * n)(*chans)
+    out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x0.device)
+    _call("decnet_conv2d_tf32_nchw_cat", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
+          w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(), B, int(cout), H, W, int(dilation), 1 if relu else 0)
     return out
 
 

@@ -181,6 +181,14 @@ int decnet_conv2d_tf32_supported(int Cin, int Cout, int H, int W, int dilation);
 int decnet_conv2d_tf32_packed_floats(int Cin, int Cout);
 int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *bias_padded, float *out,
                             int B, int Cin, int Cout, int H, int W, int dilation, int relu, void *stream);
+/* Same convolution over the channel concatenation of `nsrc` (1..3) NCHW tensors, without materialising the
+ * cat (torch.cat((left, dense, sparse, mask, -var)) before SoftAttention, SparseDenseNetRefinementMask.py:197;
+ * cat((left, warped_right, disp)) in Refinement, modules/submodule.py:758-759).  Source i has src_channels[i]
+ * channels and occupies ceil(src_channels[i]/8) whole chunks of the packed weights: pack as if the input had
+ * sum(8*ceil(C_i/8)) channels with zero weights in each source's padding. */
+int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
+                                const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
+                                int relu, void *stream);
 
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
@@ -225,7 +233,8 @@ int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out,
                            int B, int h, int w, int NP, void *stream);
 
 /* SoftAttention conv input cat(left_fea, dense, sparse, left_mask, -var) -> [B,C+4,H,W]
- * (modules/SparseDenseNetRefinementMask.py:197). */
+ * (modules/SparseDenseNetRefinementMask.py:197).  C = 0 (left_fea may be NULL) packs only the four
+ * single-channel maps -> [B,4,H,W], the second source of decnet_conv2d_tf32_nchw_cat. */
 int decnet_attn_pack(const float *left_fea, const float *dense, const float *sparse,
                      const float *left_mask, const float *var, float *out,
                      int B, int C, int H, int W, void *stream);

@@ -84,3 +84,47 @@ def test_conv2d_tf32_matches_direct_kernel_on_layer_shapes():
     got = ops.conv2d_tf32_nchw(x, wp, bp, 8, 1, True)
     want = ops.conv2d_small(x, ops.pack_conv2d_weights(w), b.contiguous(), 8, 3, 1, True)
     assert (got - want).abs().max().item() <= 4 * 2 ** -11 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("chans,Cout,H,W,dil", [((8, 4), 8, 45, 64, 1), ((24, 4), 24, 30, 36, 1), ((8, 8, 1), 8, 50, 120, 3),
+                                                ((24, 24, 1), 24, 36, 108, 2), ((5, 1, 3), 4, 20, 32, 1)])
+def test_conv2d_tf32_cat_equals_conv_of_concatenation(chans, Cout, H, W, dil):
+    """decnet_conv2d_tf32_nchw_cat: each source occupies whole 8-channel chunks; the result must equal the
+    single-source kernel run on the materialised torch.cat (same TF32 operands -> same accumulation)."""
+    from decnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(17)
+    srcs = [torch.randn(2, c, H, W, device="cuda", generator=g) if c > 1 else torch.randn(2, H, W, device="cuda", generator=g)
+            for c in chans]
+    cin = sum(chans)
+    w = torch.randn(Cout, cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    wp, bp = ops.pack_conv2d_tf32_nchw_weights(w, b, chans)
+    got = ops.conv2d_tf32_nchw_cat(srcs, wp, bp, Cout, dil, True)
+    x = torch.cat([t.unsqueeze(1) if t.dim() == 3 else t for t in srcs], 1).contiguous()
+    want = F.relu(F.conv2d(_tf32(x).double(), _tf32(w).double(), b.double(), padding=dil, dilation=dil)).float()
+    err = (got - want).abs().max().item()
+    assert err <= 2e-5 * max(1.0, want.abs().max().item()), err
+
+
+def test_model_units_use_the_cat_path_and_match_packed_path():
+    """SoftAttention.logits_cat / Refinement (three-source first conv) against the packed-tensor route."""
+    from decnet_b200 import model as dm, ops
+    torch.manual_seed(0)
+    B, C, H, W = 2, 8, 48, 64
+    att = dm.SoftAttention(C + 4, C).cuda().eval()
+    ref = dm.Refinement(C, stage_id=3).cuda().eval()
+    L, R = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    dense, sparse = torch.rand(B, H, W, device="cuda") * 20, torch.rand(B, H, W, device="cuda") * 20
+    mask, var = (torch.rand(B, H, W, device="cuda") > 0.5).float(), torch.rand(B, H, W, device="cuda")
+    with torch.no_grad():
+        a = att.logits_cat(L, ops.attn_pack(None, dense, sparse, mask, var))
+        b = att.logits(ops.attn_pack(L, dense, sparse, mask, var))
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+        p1, r1 = ref(L, R, dense)
+        old = dm.USE_TF32_TCGEN05
+        try:
+            dm.USE_TF32_TCGEN05 = False          # packed route, fp32 direct kernels
+            p0, r0 = ref(L, R, dense)
+        finally:
+            dm.USE_TF32_TCGEN05 = old
+        assert (r1 - r0).abs().max().item() <= 4e-3 * max(1.0, r0.abs().max().item())     # TF32 vs fp32 through 7 layers
