@@ -246,35 +246,51 @@ static int launch_tiled_dil(int dil, const float *x, const float *wpk, const flo
 
 // ConvTranspose2d k=3 s=3 (+bias, ReLU): out[b,co,3y+i,3x+j] = relu(bias[co] + sum_ci in[b,ci,y,x] * w[ci,co,i,j])
 template <int COUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 deconv3x3s3_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
                    float *__restrict__ out, int Cin, int h, int wd, int relu)
 {
-    extern __shared__ __align__(16) float ws[];          // [Cin][COUT][9] (PyTorch's ConvTranspose2d layout)
-    for (int i = threadIdx.x; i < Cin * COUT * 9; i += 256) ws[i] = w[i];
+    // One thread = one coarse pixel of output row Y = 3*yy + i: its 3 fine pixels x COUT channels (24
+    // accumulators) from ONE load of x per input channel; the row's weights [ci][j][co] are broadcast
+    // reads from shared memory (6 LDS.128 per 24 FMAs).
+    extern __shared__ __align__(16) float ws[];          // [Cin][3 j][COUT] for this block's row phase i
+    const int Y = blockIdx.y, yy = Y / 3, i = Y - 3 * yy;
+    for (int t = threadIdx.x; t < Cin * 3 * COUT; t += 128) {
+        const int ci = t / (3 * COUT), r = t - ci * 3 * COUT, j = r / COUT, co = r - j * COUT;
+        ws[t] = w[(ci * COUT + co) * 9 + i * 3 + j];     // PyTorch ConvTranspose2d layout [Cin][Cout][3][3]
+    }
     __syncthreads();
     const int b = blockIdx.z;
-    const int H = 3 * h, W = 3 * wd;
-    const int Y = blockIdx.y;
-    const int X = blockIdx.x * 256 + threadIdx.x;
-    if (X >= W) return;
-    const int yy = Y / 3, i = Y - 3 * yy, xx = X / 3, j = X - 3 * xx;
-    const int tap = i * 3 + j;
-    float acc[COUT];
+    const int xx = blockIdx.x * 128 + threadIdx.x;
+    if (xx >= wd) return;
+    float acc[3 * COUT];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = __ldg(bias + co);
+    for (int k = 0; k < 3 * COUT; ++k) acc[k] = __ldg(bias + (k % COUT));
     const size_t cplane = (size_t)h * wd;
     const float *xp = x + (size_t)b * Cin * cplane + (size_t)yy * wd + xx;
+#pragma unroll 4
     for (int ci = 0; ci < Cin; ++ci) {
         const float v = __ldg(xp + (size_t)ci * cplane);
-        const float *wr = ws + ci * COUT * 9 + tap;
+        const float4 *wr = reinterpret_cast<const float4 *>(ws + ci * 3 * COUT);
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wr[co * 9], acc[co]);
+        for (int k4 = 0; k4 < 3 * COUT / 4; ++k4) {
+            const float4 wv = wr[k4];
+            acc[4 * k4 + 0] = fmaf(v, wv.x, acc[4 * k4 + 0]);
+            acc[4 * k4 + 1] = fmaf(v, wv.y, acc[4 * k4 + 1]);
+            acc[4 * k4 + 2] = fmaf(v, wv.z, acc[4 * k4 + 2]);
+            acc[4 * k4 + 3] = fmaf(v, wv.w, acc[4 * k4 + 3]);
+        }
     }
-    const size_t plane = (size_t)H * W;
-    float *ob = out + (size_t)b * COUT * plane + (size_t)Y * W + X;
+    const int W = 3 * wd;
+    const size_t plane = (size_t)(3 * h) * W;
+    float *ob = out + (size_t)b * COUT * plane + (size_t)Y * W + 3 * xx;
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) ob[(size_t)co * plane] = relu ? fmaxf(acc[co], 0.f) : acc[co];
+    for (int co = 0; co < COUT; ++co)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float a = acc[j * COUT + co];
+            ob[(size_t)co * plane + j] = relu ? fmaxf(a, 0.f) : a;
+        }
 }
 
 template <int COUT, int P>
@@ -351,12 +367,13 @@ int decnet_deconv3x3s3(const float *x, const float *w, const float *bias, float 
     DECNET_REQUIRE(x && w && bias && out, "null pointer");
     DECNET_REQUIRE(B > 0 && B <= 65535 && Cin > 0 && h > 0 && w_in > 0, "bad size");
     DECNET_REQUIRE(Cout == 8, "deconv3x3s3 is instantiated for 8 output channels (GenerateSparseMask.deconv.0)");
-    const size_t smem = (size_t)Cin * Cout * 9 * sizeof(float);
+    const size_t smem = (size_t)Cin * Cout * 3 * sizeof(float);
     DECNET_REQUIRE(smem <= 200 * 1024, "Cin too large");
     auto kern = deconv3x3s3_kernel<8>;
     if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((3 * w_in + 255) / 256, 3 * h, B);
-    kern<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
+    DECNET_REQUIRE(3 * h <= 65535, "too many rows");
+    dim3 grid((w_in + 127) / 128, 3 * h, B);
+    kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
     return after_launch("deconv3x3s3_kernel");
 }
 

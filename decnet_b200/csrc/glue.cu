@@ -250,46 +250,84 @@ __global__ void __launch_bounds__(kBlock)
 dynup_pack_nhwc_kernel(const float *__restrict__ disp, const float *__restrict__ Lf, float *__restrict__ out,
                        int C, int h, int w, int CP, int TX, int round_tf32)
 {
-    extern __shared__ float rows[];            // [C*3][3*TX]
+    // Block = TX coarse pixels of one row.  Phase 1: the 3C fine-row segments land in shared memory, one warp
+    // per segment (coalesced).  Phase 2: channels-last float4 stores; the channel -> (segment, kx) mapping is a
+    // per-block table, and the (pixel, channel) cursor advances by add/compare (no divisions per element).
+    extern __shared__ float rows[];            // [C*3][3*TX] then int lut[CP]
     const int x0 = blockIdx.x * TX, y = blockIdx.y, b = blockIdx.z;
     const int nx = min(TX, w - x0);
     const int W3 = 3 * w, seg = 3 * TX;
-    for (int r = 0; r < C * 3; ++r) {
+    int *lut = reinterpret_cast<int *>(rows + (size_t)C * 3 * seg);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < C * 3; r += kBlock / 32) {
         const int c = r / 3, ky = r - 3 * c;
         const float *src = Lf + (((size_t)b * C + c) * (3 * h) + 3 * y + ky) * W3 + 3 * x0;
-        for (int i = threadIdx.x; i < 3 * nx; i += kBlock) rows[r * seg + i] = src[i];
+        for (int i = lane; i < 3 * nx; i += 32) rows[r * seg + i] = __ldg(src + i);
+    }
+    for (int ch = threadIdx.x; ch < CP; ch += kBlock) {
+        int v = -1;                            // zero padding
+        if (ch == 0) v = -2;                   // the disparity itself
+        else if (ch <= 9 * C) {
+            const int c = (ch - 1) / 9, k = (ch - 1) - 9 * c, ky = k / 3, kx = k - 3 * ky;
+            v = (c * 3 + ky) * seg + kx;
+        }
+        lut[ch] = v;
     }
     __syncthreads();
-    float *ob = out + (((size_t)b * h + y) * w + x0) * CP;
+    float4 *ob = reinterpret_cast<float4 *>(out + (((size_t)b * h + y) * w + x0) * CP);
     const float *db = disp + ((size_t)b * h + y) * w + x0;
-    const int total = nx * CP;
-    for (int i = threadIdx.x; i < total; i += kBlock) {
-        const int xl = i / CP, ch = i - xl * CP;
-        float v = 0.f;
-        if (ch == 0) v = db[xl];
-        else if (ch <= 9 * C) {
-            const int c = (ch - 1) / 9, k = (ch - 1) - 9 * c;
-            const int ky = k / 3, kx = k - 3 * ky;
-            v = rows[(c * 3 + ky) * seg + 3 * xl + kx];
+    const int cp4 = CP >> 2, total4 = nx * cp4;
+    int xl = threadIdx.x / cp4, c4 = threadIdx.x - xl * cp4;          // one division per thread
+    const int dxl = kBlock / cp4, dc4 = kBlock - dxl * cp4;
+    for (int i = threadIdx.x; i < total4; i += kBlock) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int l = lut[4 * c4 + e];
+            float v = l >= 0 ? rows[l + 3 * xl] : (l == -2 ? __ldg(db + xl) : 0.f);
+            if (round_tf32) v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);   // == cvt.rna.tf32
+            o[e] = v;
         }
-        if (round_tf32) {      // operands of a kind::tf32 MMA: round to nearest instead of the MMA's truncation
-            uint32_t r;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-            v = __uint_as_float(r);
-        }
-        ob[i] = v;
+        ob[i] = make_float4(o[0], o[1], o[2], o[3]);
+        xl += dxl; c4 += dc4;
+        if (c4 >= cp4) { c4 -= cp4; ++xl; }
     }
 }
 
-__global__ void __launch_bounds__(kBlock)
+// Block = 32 coarse pixels of one row x 9 sub-pixels (288 threads).  The 32 x NP logits are staged through
+// shared memory with coalesced float4 loads (a thread-per-pixel walk over its own 324-byte row is
+// uncoalesced); thread (i, px, j) then owns fine pixel (3y+i, 3x+j): 9 logits -> softmax -> weighted sum of
+// the 3x3 coarse neighbourhood, and the block writes three contiguous 96-float runs.
+constexpr int kGluePx = 32;
+__global__ void __launch_bounds__(9 * kGluePx)
 dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict__ disp, float *__restrict__ out,
                        int B, int h, int w, int NP)
 {
-    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const long long n = (long long)B * h * w;
-    if (idx >= n) return;
-    const int x = (int)(idx % w), y = (int)((idx / w) % h), b = (int)(idx / ((long long)w * h));
+    extern __shared__ __align__(16) float lg_s[];          // [32][NP + 1] (odd stride: conflict-free 9-float reads)
+    const int x0 = blockIdx.x * kGluePx, y = blockIdx.y, b = blockIdx.z;
+    const int nx = min(kGluePx, w - x0);
+    const int stride = NP + 1;
     const size_t plane = (size_t)h * w;
+    const float *src = logits + (((size_t)b * h + y) * w + x0) * NP;
+    if ((NP & 3) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        const int np4 = NP >> 2;
+        for (int t = threadIdx.x; t < nx * np4; t += 9 * kGluePx) {
+            const int px = t / np4, c4 = t - px * np4;
+            const float4 v = __ldg(s4 + t);
+            float *d = lg_s + px * stride + 4 * c4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int t = threadIdx.x; t < nx * NP; t += 9 * kGluePx) {
+            const int px = t / NP, c = t - px * NP;
+            lg_s[px * stride + c] = __ldg(src + t);
+        }
+    }
+    __syncthreads();
+    const int i = threadIdx.x / (3 * kGluePx), r = threadIdx.x - i * 3 * kGluePx, px = r / 3, j = r - 3 * px;
+    if (px >= nx) return;
+    const int x = x0 + px;
     const float *db = disp + (size_t)b * plane;
     float nb[9];
 #pragma unroll
@@ -299,25 +337,14 @@ dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict
             const int yy = min(max(y + ky - 1, 0), h - 1), xx = min(max(x + kx - 1, 0), w - 1);
             nb[ky * 3 + kx] = __ldg(db + (size_t)yy * w + xx);
         }
-    const float *lg = logits + (size_t)idx * NP;
-    float *ob = out + (size_t)b * 9 * plane;
+    const float *lg = lg_s + px * stride + (i * 3 + j) * 9;
+    float v[9], mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        float res[3];
+    for (int k = 0; k < 9; ++k) { v[k] = lg[k]; mx = fmaxf(mx, v[k]); }
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int sub = i * 3 + j;
-            float v[9], mx = -INFINITY;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { v[k] = __ldg(lg + sub * 9 + k); mx = fmaxf(mx, v[k]); }
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { const float e = expf(v[k] - mx); s0 += e; s1 += e * nb[k]; }
-            res[j] = (s1 / s0) * 3.0f;
-        }
-        float *o = ob + (size_t)(3 * y + i) * (3 * w) + 3 * x;
-        o[0] = res[0]; o[1] = res[1]; o[2] = res[2];
-    }
+    for (int k = 0; k < 9; ++k) { const float e = expf(v[k] - mx); s0 += e; s1 += e * nb[k]; }
+    out[(size_t)b * 9 * plane + (size_t)(3 * y + i) * (3 * w) + 3 * x + j] = (s1 / s0) * 3.0f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -660,10 +687,11 @@ int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
     DECNET_REQUIRE(disp && left_fea && out, "null pointer");
     DECNET_REQUIRE(B > 0 && B <= 65535 && C > 0 && h > 0 && h <= 65535 && w > 0, "bad size");
     DECNET_REQUIRE(CP >= 9 * C + 1, "CP=%d must hold 9*C+1=%d channels", CP, 9 * C + 1);
-    int TX = 1800 / C;
+    int TX = 1200 / C;                            // <= 43 KB of shared memory: 5 blocks per SM
     TX = TX > 128 ? 128 : (TX < 8 ? 8 : (TX & ~7));
     if (TX > w) TX = w;
-    const size_t smem = (size_t)C * 9 * TX * sizeof(float);
+    DECNET_REQUIRE((CP & 3) == 0, "CP must be a multiple of 4");
+    const size_t smem = (size_t)C * 9 * TX * sizeof(float) + (size_t)CP * sizeof(int);
     DECNET_REQUIRE(smem <= 200 * 1024, "C too large");
     if (smem > 48 * 1024)
         DECNET_CUDA(cudaFuncSetAttribute(dynup_pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -674,8 +702,10 @@ int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
 int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out, int B, int h, int w, int NP, void *stream) {
     DECNET_REQUIRE(logits && disp && out, "null pointer");
     DECNET_REQUIRE(B > 0 && h > 0 && w > 0 && NP >= 81, "bad size");
-    const long long n = (long long)B * h * w;
-    dynup_glue_nhwc_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(logits, disp, out, B, h, w, NP);
+    DECNET_REQUIRE(h <= 65535 && B <= 65535, "grid limit");
+    const size_t smem = (size_t)kGluePx * (NP + 1) * sizeof(float);
+    DECNET_REQUIRE(smem <= 48 * 1024, "NP too large");
+    dynup_glue_nhwc_kernel<<<dim3((w + kGluePx - 1) / kGluePx, h, B), 9 * kGluePx, smem, (cudaStream_t)stream>>>(logits, disp, out, B, h, w, NP);
     return after_launch("dynup_glue_nhwc_kernel");
 }
 
