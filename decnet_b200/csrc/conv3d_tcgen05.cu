@@ -126,6 +126,7 @@ struct Params {
     int relu, mode, tmem_cols;         // mode 0 bf16 [M][np], 1 fp32 [M] (channel 0), 2 fp32 [M][np]; 2 TMEM slots
     int fmt, chunk_ch;                 // operand format (1 bf16 / 2 tf32) and channels per 128-byte stage row
     int taps_d;                        // 3: 3x3x3 taps (Conv3d), 1: 3x3 taps on a D=1 volume (Conv2d)
+    int skip_tma;                      // tuning only (variant 3): after the first ring fill, signal stages without loading
     float *out_f32_full;               // [M][np] (mode 2)
     int round_tf32;                    // mode 2: round the stored activations to TF32 (nearest) for the next tf32 conv
     int num_tiles, stages;
@@ -186,9 +187,12 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             for (int ck = 0; ck < p.nchunks; ++ck) {
                                 mbar_wait(&empty_bar[s], ph ^ 1u);
                                 unsigned char *sa = base + (size_t)s * stage_bytes;
+                                if (p.skip_tma && (ph || tile != (int)blockIdx.x)) { mbar_arrive(&full_bar[s]); }
+                                else {
                                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
                                 tma_load_5d(sa, &tmA, ck * p.chunk_ch, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, &full_bar[s]);
                                 tma_load_3d(sa + kABytes, &tmB, ck * p.chunk_ch, 0, tap, &full_bar[s]);
+                                }
                                 if (++s == kStages) { s = 0; ph ^= 1u; }
                             }
             }
@@ -225,7 +229,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         const uint32_t ebar = empty_base + (uint32_t)(s * 8);
                         int sn = s + 1; uint32_t phn = ph;
                         if (sn == kStages) { sn = 0; phn ^= 1u; }
-                        ready = mbar_try_wait(&full_bar[sn], phn);       // probe the NEXT stage now
+                        ready = mbar_test_wait(&full_bar[sn], phn);       // probe the NEXT stage now
                         // K-steps of the stage + the commit that frees it: one asm block, one elect.sync
                         if (ck != last_ck) umma_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar);
                         else switch (p.last_ksteps) {
@@ -503,7 +507,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                         const uint32_t ebar = empty_base + (uint32_t)(s * 8);
                         int sn = s + 1; uint32_t phn = ph;
                         if (sn == kStages) { sn = 0; phn ^= 1u; }
-                        ready = mbar_try_wait(&full_bar[sn], phn);
+                        ready = mbar_test_wait(&full_bar[sn], phn);
                         if (ck != last_ck) umma2_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar);
                         else switch (p.last_ksteps) {
                             case 4: umma2_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar); break;
@@ -659,6 +663,7 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
     DECNET_REQUIRE(tiles < (1ll << 31), "too many tiles");
     p.num_tiles = (int)tiles;
     p.dbg = g_conv3d_dbg;
+    p.skip_tma = g_conv3d_variant == 3 ? 1 : 0;
     const int sms = sm_count_cached();
     // The CTA-pair kernel is correct (same tests) but measured 2x slower than the single-CTA one in
     // round 1 (MMAs slow down 3x while TMA fills run): opt-in only.

@@ -52,7 +52,9 @@ def run(B, Cin, Cout, H, W, dil, relu=True, check=True, iters=0):
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "check"
-    if mode == "check":
+    if mode == "l2":
+        pass
+    elif mode == "check":
         run(1, 8, 8, 64, 96, 1)
         run(1, 8, 8, 37, 100, 1)
         run(1, 17, 8, 50, 120, 3)
@@ -80,3 +82,32 @@ if __name__ == "__main__":
                                         (8, 24, 12, 180, 324, 4), (8, 28, 24, 180, 324, 1), (8, 72, 8, 60, 108, 1),
                                         (8, 36, 36, 60, 108, 1)]:
             run(B, Cin, Cout, H, W, d, check=False, iters=20)
+
+
+def l2_resident_test():
+    """Is a chain of 8->8 layers faster per pair when the batch chunk keeps activations in the 126 MB L2?"""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    w = torch.randn(8, 8, 3, 3, device="cuda", generator=g) * 0.1
+    b = torch.zeros(8, device="cuda")
+    wp, bp = ops.pack_conv2d_tf32_nchw_weights(w, b)
+    for B in (8, 4, 2, 1):
+        x = torch.randn(B, 8, 540, 972, device="cuda", generator=g)
+        y = torch.empty_like(x)
+        bufs = [x, y]
+        def chain(n=6):
+            for i in range(n):
+                src, dst = bufs[i & 1], bufs[(i + 1) & 1]
+                ops._call("decnet_conv2d_tf32_nchw", src, src.data_ptr(), wp.data_ptr(), bp.data_ptr(), dst.data_ptr(),
+                          B, 8, 8, 540, 972, 1, 1)
+        chain(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            chain()
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 60
+        print(f"B={B}: {us:.1f} us per layer launch, {us / B:.2f} us per pair-layer ({B * 8 * 540 * 972 * 8 / us / 1e3:.0f} GB/s)")
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "l2":
+    l2_resident_test()
