@@ -139,7 +139,7 @@ __device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, u
         const bool col_ok = lane_ok && col >= 0 && col < p.W;
         const int slot = j & 1;
         const long long tq0 = clock64();
-        mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
+        mbar_wait_relaxed(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
         prof_acc[0] += clock64() - tq0;
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * acc_stride);
@@ -250,7 +250,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 const int b = t;
                 for (int ck = 0; ck < p.nck; ++ck) {
                     const long long tq0 = clock64();
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);
                     prof_acc[0] += clock64() - tq0;
                     mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
                     // the input is the channel concatenation of up to three tensors (each padded to whole chunks)
