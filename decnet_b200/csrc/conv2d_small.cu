@@ -366,14 +366,21 @@ int decnet_deconv3x3s3(const float *x, const float *w, const float *bias, float 
 {
     DECNET_REQUIRE(x && w && bias && out, "null pointer");
     DECNET_REQUIRE(B > 0 && B <= 65535 && Cin > 0 && h > 0 && w_in > 0, "bad size");
-    DECNET_REQUIRE(Cout == 8, "deconv3x3s3 is instantiated for 8 output channels (GenerateSparseMask.deconv.0)");
+    DECNET_REQUIRE(Cout == 8 || Cout == 24, "deconv3x3s3 is instantiated for 8 and 24 output channels "
+                   "(GenerateSparseMask.deconv.0, feature extractor deconv1 / deconv2)");
     const size_t smem = (size_t)Cin * Cout * 3 * sizeof(float);
     DECNET_REQUIRE(smem <= 200 * 1024, "Cin too large");
-    auto kern = deconv3x3s3_kernel<8>;
-    if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DECNET_REQUIRE(3 * h <= 65535, "too many rows");
     dim3 grid((w_in + 127) / 128, 3 * h, B);
-    kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
+    if (Cout == 8) {
+        auto kern = deconv3x3s3_kernel<8>;
+        if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
+    } else {
+        auto kern = deconv3x3s3_kernel<24>;
+        if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
+    }
     return after_launch("deconv3x3s3_kernel");
 }
 

@@ -130,18 +130,33 @@ class Conv2dUnit(nn.Module):
 
 
 class Deconv2dUnit(nn.Module):
-    """ConvTranspose2d(bias) + ReLU; keys as modules/submodule.py:52-87 with bn=False."""
+    """ConvTranspose2d [+ BN(eval)] + ReLU; keys as modules/submodule.py:52-87 (bn=False: bias, as in
+    GenerateSparseMask.deconv.0; bn=True: no bias, as in Deconv2dBlock.deconv of the feature extractor)."""
 
-    def __init__(self, in_channels, out_channels, kernel_size, stride):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, bn=False):
         super().__init__()
-        self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=stride, bias=True)
+        self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=stride, bias=not bn)
+        self.bn = nn.BatchNorm2d(out_channels) if bn else None
+        self._folded = None
+
+    def folded(self):
+        if self._folded is None:
+            w = self.conv.weight.detach()                       # [Cin, Cout, k, k]
+            b = self.conv.bias.detach() if self.conv.bias is not None else torch.zeros(w.shape[1], device=w.device)
+            if self.bn is not None:
+                scale = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + BN_EPS)
+                w = w * scale.view(1, -1, 1, 1)
+                b = (b - self.bn.running_mean) * scale + self.bn.bias.detach()
+            self._folded = (w.contiguous(), b.contiguous())
+        return self._folded
 
     def forward(self, x):
         c = self.conv
+        w, b = self.folded()
         if (USE_NATIVE_CONV2D and x.is_cuda and x.dtype == torch.float32 and c.kernel_size == (3, 3)
-                and c.stride == (3, 3) and c.out_channels == 8 and c.padding == (0, 0)):
-            return ops.deconv3x3s3(x.contiguous(), c.weight.detach().contiguous(), c.bias.detach().contiguous(), True)
-        return F.relu_(self.conv(x))
+                and c.stride == (3, 3) and c.padding == (0, 0) and ops.deconv3x3s3_supported(c.out_channels)):
+            return ops.deconv3x3s3(x.contiguous(), w, b, True)
+        return F.relu_(F.conv_transpose2d(x, w, b, stride=c.stride))
 
 
 class Conv3dUnit(nn.Module):

@@ -317,6 +317,10 @@ def conv2d_small(x, w_packed, bias, cout, ksize, dilation=1, relu=False, addend=
     return out
 
 
+def deconv3x3s3_supported(cout):
+    return int(cout) in (8, 24)
+
+
 def deconv3x3s3(x, w, bias, relu=True):
     _chk("x", x)
     B, cin, h, wd = x.shape

@@ -100,3 +100,46 @@ def make_features(B: int, H: int, W: int, seed: int = 17, scale: float = 0.3, ch
         left[f"stage{s}"] = (torch.randn(shape, generator=g) * scale).to(device).contiguous()
         right[f"stage{s}"] = (torch.randn(shape, generator=g) * scale).to(device).contiguous()
     return left, right
+
+
+# --------------------------------------------------------------------------------------
+# feature extractor (SURVEY.md section 8f rank 2): keys and shapes of FeatExtNetChannelPlus(8, 4, 3)
+# (modules/submodule.py:245-309), listed explicitly so this file does not depend on any module class
+# --------------------------------------------------------------------------------------
+def featext_layout(base_channels: int = 8):
+    """[(key prefix, kind, shape)]: kind 'conv' (Conv2d weight [out,in,k,k] + BN) or 'deconv'
+    (ConvTranspose2d weight [in,out,k,k] + BN)."""
+    c = base_channels
+    c1, c2, c3 = 3 * c, 9 * c, 27 * c
+    L = [("conv0.0", "conv", (c, 3, 3, 3)), ("conv0.1", "conv", (c, c, 3, 3)), ("addition_trans0", "conv", (c, c, 1, 1)),
+         ("conv1.0", "conv", (c1, c, 3, 3)), ("conv1.1", "conv", (c1, c1, 3, 3)), ("conv1.2", "conv", (c1, c1, 3, 3)),
+         ("addition_trans1", "conv", (c1, c1, 1, 1)),
+         ("deconv1.deconv", "deconv", (c1, c, 3, 3)), ("deconv1.conv.0", "conv", (c, 2 * c, 3, 3)), ("deconv1.conv.1", "conv", (c, c, 3, 3)),
+         ("conv2.0", "conv", (c2, c1, 3, 3)), ("conv2.1", "conv", (c2, c2, 3, 3)), ("conv2.2", "conv", (c2, c2, 3, 3)),
+         ("addition_trans2", "conv", (c2, c2, 1, 1)),
+         ("deconv2.deconv", "deconv", (c2, c1, 3, 3)), ("deconv2.conv.0", "conv", (c1, 2 * c1, 3, 3)), ("deconv2.conv.1", "conv", (c1, c1, 3, 3)),
+         ("conv3_1", "conv", (c3, c2, 3, 3)), ("conv3_2.0", "conv", (c3, c3, 3, 3)), ("conv3_2.1", "conv", (c3, c3, 3, 3)),
+         ("addition_ctx_collection.0.stages.c0", "conv", (c3, c3, 1, 1)),
+         ("addition_ctx_collection.0.stages.c1", "conv", (c3, c3, 3, 3)),
+         ("addition_ctx_collection.0.stages.c2", "conv", (c3, c3, 3, 3)),
+         ("addition_ctx_collection.0.stages.c3", "conv", (c3, c3, 3, 3)),
+         ("addition_ctx_collection.1", "conv", (c3, 4 * c3, 1, 1)),
+         ("addition_fusion", "conv", (c3, 2 * c3, 1, 1)),
+         ("deconv3.deconv", "deconv", (c3, c2, 3, 3)), ("deconv3.conv.0", "conv", (c2, 2 * c2, 3, 3)), ("deconv3.conv.1", "conv", (c2, c2, 3, 3))]
+    return L
+
+
+def make_featext_state(seed: int = 17, base_channels: int = 8, randomize_bn: bool = True) -> dict:
+    """state_dict (CPU fp32) of the reference's `feature_extractor` sub-module (keys WITHOUT that prefix)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for prefix, kind, shape in featext_layout(base_channels):
+        if kind == "conv":
+            sd[prefix + ".conv.weight"] = _conv(g, shape)
+            n = shape[0]
+        else:
+            k = shape[2] * shape[3]
+            sd[prefix + ".conv.weight"] = torch.randn(shape, generator=g) * math.sqrt(2.0 / (k * shape[1]))
+            n = shape[1]
+        _bn(sd, prefix + ".bn", n, g, randomize_bn)
+    return sd

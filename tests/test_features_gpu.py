@@ -1,0 +1,64 @@
+"""GPU parity of the feature-extractor drop-in against the golden outputs of
+the unmodified reference module, and of its tensor-core route against its fp32 route at SceneFlow size."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+
+from decnet_b200.params import make_featext_state  # noqa: E402
+from make_golden_features import make_image  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = ROOT / "tests" / "golden" / "features.npz"
+
+
+def _model(seed):
+    from decnet_b200.features import FeatExtNetChannelPlus
+    m = FeatExtNetChannelPlus(8)
+    m.load_state_dict(make_featext_state(seed), strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("tf32", [False, True])
+def test_features_match_reference_golden(tf32):
+    """fp32 route: <= 1e-4 of the map's scale (accumulation order only).  TF32 route (PyTorch's default for
+    convolutions, what the reference runs on a GPU): 10-bit mantissa operands through up to 14 layers,
+    tolerance 1e-2 of the scale (measured ~2e-3)."""
+    z = np.load(GOLD)
+    seed, B, H, W = (int(v) for v in z["meta"])
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        out = _model(seed)(make_image(seed, B, H, W).cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    tol = 1e-2 if tf32 else 1e-4
+    for k in ("stage0", "stage1", "stage2", "stage3"):
+        want = torch.from_numpy(z[k]).cuda()
+        assert out[k].shape == want.shape
+        err = float((out[k] - want).abs().max())
+        assert err <= tol * max(1.0, float(want.abs().max())), (k, err)
+
+
+def test_features_full_size_tensor_core_route_vs_fp32_route():
+    """540x972 (SceneFlow padded), B=2: every level of the pyramid, TF32 tensor-core route vs fp32 route."""
+    m = _model(5)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(2, 3, 540, 972, device="cuda", generator=g)
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        a = m(x)
+        torch.backends.cudnn.allow_tf32 = False
+        b = m(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    for k, shape in (("stage0", (2, 216, 20, 36)), ("stage1", (2, 72, 60, 108)), ("stage2", (2, 24, 180, 324)),
+                     ("stage3", (2, 8, 540, 972))):
+        assert tuple(a[k].shape) == shape
+        assert float((a[k] - b[k]).abs().max()) <= 1e-2 * max(1.0, float(b[k].abs().max())), k
