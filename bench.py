@@ -44,6 +44,8 @@ def parse():
                          "with halo exchange over NCCL (strong scaling, BASELINE.json configs[3])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-from-images", action="store_true",
+                    help="skip the extra leg that starts from images (feature extractor + hot path, SURVEY.md 8f rank 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="host time of the bounded CPU sample")
     return ap.parse_args()
 
@@ -177,6 +179,83 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def run_from_images(args, info, dev, timed):
+    """Feature extractor (both views) + hot path from synthetic images; returns the `from_images` object."""
+    import torch
+    from decnet_b200.features import FeatExtNetChannelPlus
+    from decnet_b200.model import DecompMatching
+    from decnet_b200.params import make_featext_state, make_hotpath_state
+    from decnet_b200.synthetic import calibrate_mask_density
+    B, H, W = args.batch, info["H"], info["W"]
+    fe = FeatExtNetChannelPlus(8)
+    fe.load_state_dict(make_featext_state(17))
+    fe = fe.to(dev)
+    model = DecompMatching(max_disp=info["max_disp"], skip_stage_id=info["skip_stage_id"], use_detail=True, thold=0.9,
+                           conv3d_impl=args.conv3d)
+    model.load_state_dict(make_hotpath_state(17))
+    model = model.to(dev)
+    g = torch.Generator(device=dev).manual_seed(99)
+    sets = []
+    for _ in range(2):
+        sets.append({"l": torch.randn(B, 3, H, W, device=dev, generator=g), "r": torch.randn(B, 3, H, W, device=dev, generator=g)})
+    dens = calibrate_mask_density(model, fe(sets[0]["l"]), fe(sets[0]["r"]), args.rho)
+
+    def step_eager(st):
+        return model(fe(st["l"]), fe(st["r"]))[0]
+
+    for st in sets:
+        step_eager(st)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step_eager(st)
+            with torch.cuda.graph(graph, stream=side):
+                st["out"] = step_eager(st)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        st["graph"] = graph
+    for _ in range(3):
+        sets[0]["graph"].replay()
+    ms = timed(lambda: sets[0]["graph"].replay(), args.steps)
+    value = B * args.steps / (ms * 1e-3)
+    # end to end: pinned images -> device (copy stream, double-buffered), graph, disparity -> pinned host
+    host = {k: sets[0][k].cpu().pin_memory() for k in ("l", "r")}
+    host_out = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    copy_stream, main = torch.cuda.Stream(), torch.cuda.current_stream()
+
+    def upload(buf, after):
+        with torch.cuda.stream(copy_stream):
+            if after is not None:
+                copy_stream.wait_event(after)
+            for k in ("l", "r"):
+                sets[buf][k].copy_(host[k], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        return ev
+
+    def run(n):
+        computed = [None, None]
+        copied = upload(0, None)
+        for i in range(n):
+            buf = i & 1
+            main.wait_event(copied)
+            sets[buf]["graph"].replay()
+            host_out.copy_(sets[buf]["out"], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(main); computed[buf] = ev
+            if i + 1 < n:
+                copied = upload(1 - buf, computed[1 - buf])
+        main.synchronize()
+
+    run(3)
+    n = max(4, args.steps)
+    ms_e2e = timed(lambda: run(n), 1)
+    return {"what": "feature extractor on both views (FeatExtNetChannelPlus drop-in) + hot path, one CUDA graph",
+            "value": value, "unit": UNIT, "ms_per_step": ms / args.steps,
+            "e2e": {"value": B * n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / n,
+                    "h2d_bytes_per_step": 2 * B * 3 * H * W * 4, "d2h_bytes_per_step": B * H * W * 4},
+            "left_mask_density": [round(d, 4) for d in dens]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -411,6 +490,16 @@ def run_ours(args):
         except Exception as e:  # not built yet / cudnn bring-up path
             roof_tensor = {"bound": "tensor", "note": f"conv3d impl '{args.conv3d}': {type(e).__name__}: {e}"}
 
+    # ---- extra leg: the same step fed from IMAGES -- feature extractor on both
+    # views + hot path in one CUDA graph; its end-to-end form uploads 2 x B images (a quarter of the bytes of
+    # the feature pyramids) from pinned host memory and reads the disparity back, every step.
+    from_images = None
+    if rank == 0 and world == 1 and use_graph and not args.no_from_images:
+        try:
+            from_images = run_from_images(args, info, dev, timed)
+        except Exception as e:      # the headline line must not depend on the extra leg
+            from_images = {"error": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         v, cores, sec, npairs = cpu_port_pairs_per_s(args.workload, args.rho, min_seconds=args.cpu_seconds)
@@ -439,7 +528,8 @@ def run_ours(args):
                         "note": e2e_note},
                 "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step,
-                "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu,
+                "from_images": from_images}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -30,6 +30,7 @@ BN_EPS = 1e-5
 # direct sm_100a kernels for the tiny-channel 2-D convs (section 8f rank 1); False = cuDNN everywhere
 USE_NATIVE_CONV2D = True
 # TF32 tcgen05 implicit GEMM for the GEMM-sized 2-D convs whenever torch.backends.cudnn.allow_tf32 is on
+_CUDNN_FUSED_RELU = True
 USE_TF32_TCGEN05 = True
 
 
@@ -124,6 +125,13 @@ class Conv2dUnit(nn.Module):
             return ops.conv2d_small(x.contiguous(), nat[1], nat[2], c.out_channels, c.kernel_size[0], c.dilation[0],
                                     self.relu, addend)
         w, b = self.folded()
+        global _CUDNN_FUSED_RELU
+        if _CUDNN_FUSED_RELU and self.relu and addend is None and x.is_cuda:
+            # library layers (strided / 1x1 / wide convs): cuDNN's fused conv + bias + ReLU, one kernel instead of three
+            try:
+                return torch.cudnn_convolution_relu(x, w, b, self.conv.stride, self.conv.padding, self.conv.dilation, 1)
+            except RuntimeError:
+                _CUDNN_FUSED_RELU = False
         x = F.conv2d(x, w, b, stride=self.conv.stride, padding=self.conv.padding, dilation=self.conv.dilation)
         x = F.relu_(x) if self.relu else x
         return x if addend is None else x + addend.unsqueeze(1)
