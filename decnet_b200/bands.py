@@ -156,9 +156,8 @@ def _level_stage_band(model, s, l, band, Lf, Rf, prevL, prevR, pred_prev_full, m
     Lb, Rb = Lf[:, :, e0:e1].contiguous(), Rf[:, :, e0:e1].contiguous()
     c0, c1 = e0 // 3, e1 // 3
     if model.use_detail:
-        ld, _, _ = model.detail_detection[l](Lb, prevL[:, :, c0:c1].contiguous())
-        rd, _, _ = model.detail_detection[l](Rb, prevR[:, :, c0:c1].contiguous())
-        lm, rm = ops.mask_threshold(torch.sigmoid(ld).contiguous(), torch.sigmoid(rd).contiguous(), model.thold)
+        lm, rm = model.detail_detection[l].masks_pair(Lb, prevL[:, :, c0:c1].contiguous(), Rb,
+                                                      prevR[:, :, c0:c1].contiguous(), model.thold)
     else:
         lm, rm = masks[0][l][:, e0:e1].contiguous(), masks[1][l][:, e0:e1].contiguous()
     dense = model.dynamic_upsampling[l](pred_prev_full[:, c0:c1].contiguous(), Lb)

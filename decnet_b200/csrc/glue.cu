@@ -167,6 +167,56 @@ mask_threshold_kernel(const float *__restrict__ pl, const float *__restrict__ pr
 }
 
 // ---------------------------------------------------------------------------------------------
+// a5 tail, fused: GenerateSparseMask's `(cur - pre) ** 2` (submodule.py:369) as one pass for both views, and
+// its last layer -- Conv2d 1x1 3->1 + BN (folded: w[3], b) -> sigmoid -> `> thold` (submodule.py:363-364,
+// SparseDenseNetRefinementMask.py:158-170) -- as one pass for both views.  The comparison is done on the
+// logit against x* = the smallest float whose torch.sigmoid exceeds thold (found by bisection on the device
+// at set-up, model.py), so the mask bits equal `torch.sigmoid(logit) > thold`; NaN logits give NaN like
+// mask_threshold_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+sqdiff_kernel(const float4 *__restrict__ a0, const float4 *__restrict__ b0, float4 *__restrict__ o0,
+              const float4 *__restrict__ a1, const float4 *__restrict__ b1, float4 *__restrict__ o1, long long n4)
+{
+    const float4 *a = blockIdx.y ? a1 : a0, *b = blockIdx.y ? b1 : b0;
+    float4 *o = blockIdx.y ? o1 : o0;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n4; i += (long long)gridDim.x * kBlock) {
+        const float4 x = __ldg(a + i), y = __ldg(b + i);
+        const float dx = x.x - y.x, dy = x.y - y.y, dz = x.z - y.z, dw = x.w - y.w;
+        o[i] = make_float4(dx * dx, dy * dy, dz * dz, dw * dw);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+sqdiff_scalar_kernel(const float *__restrict__ a0, const float *__restrict__ b0, float *__restrict__ o0,
+                     const float *__restrict__ a1, const float *__restrict__ b1, float *__restrict__ o1, long long n)
+{
+    const float *a = blockIdx.y ? a1 : a0, *b = blockIdx.y ? b1 : b0;
+    float *o = blockIdx.y ? o1 : o0;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const float d = __ldg(a + i) - __ldg(b + i);
+        o[i] = d * d;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+detail_head_kernel(const float *__restrict__ xl, const float *__restrict__ xr, float w0, float w1, float w2, float bias,
+                   float logit_thold, float *__restrict__ ml, float *__restrict__ mr, long long HW)
+{
+    const int b = blockIdx.y >> 1;
+    const float *x = ((blockIdx.y & 1) ? xr : xl) + (long long)b * 3 * HW;
+    float *m = ((blockIdx.y & 1) ? mr : ml) + (long long)b * HW;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < HW; i += (long long)gridDim.x * kBlock) {
+        // same operation order as conv2d_small_kernel<1,P> with a 1x1 kernel: bias, then channels in order
+        float v = bias;
+        v = fmaf(__ldg(x + i), w0, v);
+        v = fmaf(__ldg(x + HW + i), w1, v);
+        v = fmaf(__ldg(x + 2 * HW + i), w2, v);
+        m[i] = v >= logit_thold ? 1.f : (v < logit_thold ? 0.f : v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // a8 (input side): DynamicUpsampling's conv input (submodule.py:580):
 //   cat(disp.unsqueeze(1), unfold(Lf, k=3, s=3)) -> [B, 1+9C, h, w]
 //   ch 0 = disp,  ch 1 + c*9 + ky*3 + kx = Lf[b, c, 3y+ky, 3x+kx]
@@ -589,6 +639,34 @@ int decnet_mask_threshold(const float *prob_l, const float *prob_r, float thold,
     mask_threshold_kernel<<<B * H, kBlock, 0, (cudaStream_t)stream>>>(prob_l, prob_r, thold, mask_l, mask_r,
                                                                      row_count_l, row_count_r, W);
     return after_launch("mask_threshold_kernel");
+}
+
+int decnet_sqdiff_pair(const float *a0, const float *b0, float *out0, const float *a1, const float *b1, float *out1,
+                       long long n, void *stream) {
+    DECNET_REQUIRE(a0 && b0 && out0 && a1 && b1 && out1, "null pointer");
+    DECNET_REQUIRE(n > 0, "element count must be positive");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(b0) | reinterpret_cast<uintptr_t>(out0) |
+                         reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(out1);
+    if ((n & 3) != 0 || (al & 15u) != 0) {      // ragged size or unaligned view: scalar form
+        sqdiff_scalar_kernel<<<dim3((unsigned)std::min<long long>((n + kBlock - 1) / kBlock, 148 * 16), 2), kBlock, 0, (cudaStream_t)stream>>>(
+            a0, b0, out0, a1, b1, out1, n);
+        return after_launch("sqdiff_scalar_kernel");
+    }
+    const long long n4 = n / 4;
+    sqdiff_kernel<<<dim3((unsigned)std::min<long long>((n4 + kBlock - 1) / kBlock, 148 * 16), 2), kBlock, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(a0), reinterpret_cast<const float4 *>(b0), reinterpret_cast<float4 *>(out0),
+        reinterpret_cast<const float4 *>(a1), reinterpret_cast<const float4 *>(b1), reinterpret_cast<float4 *>(out1), n4);
+    return after_launch("sqdiff_kernel");
+}
+
+int decnet_detail_head(const float *x_l, const float *x_r, const float *w3, float bias, float logit_thold,
+                       float *mask_l, float *mask_r, int B, int H, int W, void *stream) {
+    DECNET_REQUIRE(x_l && x_r && w3 && mask_l && mask_r, "null pointer");
+    DECNET_REQUIRE(B > 0 && 2 * B <= 65535 && H > 0 && W > 0, "bad size");
+    const long long HW = (long long)H * W;
+    detail_head_kernel<<<dim3((unsigned)std::min<long long>((HW + kBlock - 1) / kBlock, 256), 2 * B), kBlock, 0, (cudaStream_t)stream>>>(
+        x_l, x_r, w3[0], w3[1], w3[2], bias, logit_thold, mask_l, mask_r, HW);
+    return after_launch("detail_head_kernel");
 }
 
 int decnet_dynup_pack(const float *disp, const float *left_fea, float *out, int B, int C, int h, int w, void *stream) {

@@ -193,6 +193,8 @@ def _reset_folded(module):
             m._tc = None
         if hasattr(m, "_tc_cat"):
             m._tc_cat = None
+        if hasattr(m, "_head"):
+            m._head = None
 
 
 # --------------------------------------------------------------------------------------
@@ -308,6 +310,20 @@ class GenerateSparseMask(nn.Module):
         cur = self.conv_sub(cur_fea)
         res = (cur - pre) ** 2
         return self.conv(res).squeeze(1), cur, pre
+
+    def masks_pair(self, cur_l, pre_l, cur_r, pre_r, thold):
+        """Left and right masks `sigmoid(forward(.)) > thold` with the tail fused: one kernel for both
+        squared differences, and one for 1x1 conv + BN + sigmoid + threshold of both views (the comparison
+        runs on the logit against the exact float where torch.sigmoid crosses `thold`)."""
+        pl, pr = self.deconv(pre_l), self.deconv(pre_r)
+        cl, cr = self.conv_sub(cur_l), self.conv_sub(cur_r)
+        rl, rr = ops.sqdiff_pair(cl, pl, cr, pr)
+        xl, xr = self.conv[0](rl), self.conv[0](rr)
+        if getattr(self, "_head", None) is None or self._head[0] is not self.conv[1]._folded:
+            w, b = self.conv[1].folded()                    # [1,3,1,1], [1]
+            self._head = (self.conv[1]._folded, [float(v) for v in w.flatten().cpu()], float(b.cpu()))
+        return ops.detail_head(xl.contiguous(), xr.contiguous(), self._head[1], self._head[2],
+                               ops.sigmoid_logit_threshold(thold, xl.device))
 
 
 # --------------------------------------------------------------------------------------
@@ -485,13 +501,13 @@ class DecompMatching(nn.Module):
             else:
                 l = s - 1
                 if self.use_detail:
-                    ld, _, _ = self.detail_detection[l](Lf, pre_l)
-                    rd, _, _ = self.detail_detection[l](Rf, pre_r)
-                    pre_l, pre_r = Lf, Rf
-                    ld, rd = torch.sigmoid(ld).contiguous(), torch.sigmoid(rd).contiguous()
-                    lm, rm = ops.mask_threshold(ld, rd, self.thold)
+                    lm, rm = self.detail_detection[l].masks_pair(Lf, pre_l, Rf, pre_r, self.thold)
                     if is_check:
-                        taps["left_detail"].append(ld); taps["right_detail"].append(rd)
+                        ld, _, _ = self.detail_detection[l](Lf, pre_l)
+                        rd, _, _ = self.detail_detection[l](Rf, pre_r)
+                        taps["left_detail"].append(torch.sigmoid(ld).contiguous())
+                        taps["right_detail"].append(torch.sigmoid(rd).contiguous())
+                    pre_l, pre_r = Lf, Rf
                 else:
                     lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
                 dense = self.dynamic_upsampling[l](pred, Lf)

@@ -195,6 +195,58 @@ def mask_threshold(prob_l, prob_r, thold, with_counts=False):
     return (ml, mr, cl, cr) if with_counts else (ml, mr)
 
 
+def sqdiff_pair(a0, b0, a1, b1):
+    """((a0 - b0)**2, (a1 - b1)**2) in one launch (GenerateSparseMask, both views)."""
+    _chk("a0", a0)
+    for n, t in (("b0", b0), ("a1", a1), ("b1", b1)):
+        _chk(n, t, a0, a0.shape)
+    o0, o1 = torch.empty_like(a0), torch.empty_like(a1)
+    _call("decnet_sqdiff_pair", a0, a0.data_ptr(), b0.data_ptr(), o0.data_ptr(), a1.data_ptr(), b1.data_ptr(), o1.data_ptr(),
+          a0.numel())
+    return o0, o1
+
+
+_LOGIT_THOLD = {}
+
+
+def sigmoid_logit_threshold(thold, device):
+    """Smallest float32 x with torch.sigmoid(x) > thold on `device` (bisection over floats; sigmoid is monotone),
+    so that `x >= result` reproduces `torch.sigmoid(x) > thold` bit for bit."""
+    key = (float(thold), str(device))
+    if key not in _LOGIT_THOLD:
+        t = float(thold)
+        lo = torch.tensor(-120.0, device=device)       # sigmoid(lo) == 0 <= t
+        hi = torch.tensor(120.0, device=device)        # sigmoid(hi) == 1 >  t   (t < 1)
+        if not (0.0 <= t < 1.0):
+            raise ValueError("thold must be in [0, 1)")
+        for _ in range(80):
+            mid = ((lo.double() + hi.double()) * 0.5).float()
+            if bool(mid == lo) or bool(mid == hi):
+                break
+            if bool(torch.sigmoid(mid) > t):
+                hi = mid
+            else:
+                lo = mid
+        _LOGIT_THOLD[key] = float(hi)
+    return _LOGIT_THOLD[key]
+
+
+def detail_head(x_l, x_r, w3, bias, logit_thold):
+    """masks (left, right) from the 3-channel maps in front of GenerateSparseMask's last 1x1 conv."""
+    import ctypes
+    _chk("x_l", x_l)
+    B, c, H, W = x_l.shape
+    if c != 3:
+        raise ValueError("detail_head expects 3 channels")
+    _chk("x_r", x_r, x_l, (B, 3, H, W))
+    ml = torch.empty((B, H, W), dtype=torch.float32, device=x_l.device)
+    mr = torch.empty_like(ml)
+    w = (ctypes.c_float * 3)(*[float(v) for v in w3])
+    _call("decnet_detail_head", x_l, x_l.data_ptr(), x_r.data_ptr(), ctypes.cast(w, ctypes.c_void_p), float(bias),
+          float(logit_thold), ml.data_ptr(), mr.data_ptr(), B, H, W)
+    return ml, mr
+
+
 def dynup_pack(disp, left_fea):
     _chk("disp", disp)
     B, h, w = disp.shape

@@ -232,6 +232,17 @@ int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
 int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out,
                            int B, int h, int w, int NP, void *stream);
 
+/* Tail of GenerateSparseMask (modules/submodule.py:363-369) for BOTH views in one launch each:
+ *   decnet_sqdiff_pair : out_i = (a_i - b_i)^2, i = 0 (left), 1 (right); n elements each
+ *   decnet_detail_head : logit = bias + sum_c w3[c] * x[b,c,h,w] (the 3->1 1x1 conv with BN folded; w3 is a HOST
+ *                        pointer to 3 floats), mask = logit >= logit_thold ? 1 : 0 (NaN kept), where the caller
+ *                        passes logit_thold = the smallest float whose sigmoid exceeds the probability threshold,
+ *                        i.e. mask == (sigmoid(logit) > thold) of SparseDenseNetRefinementMask.py:158-170. */
+int decnet_sqdiff_pair(const float *a0, const float *b0, float *out0, const float *a1, const float *b1, float *out1,
+                       long long n, void *stream);
+int decnet_detail_head(const float *x_l, const float *x_r, const float *w3_host, float bias, float logit_thold,
+                       float *mask_l, float *mask_r, int B, int H, int W, void *stream);
+
 /* SoftAttention conv input cat(left_fea, dense, sparse, left_mask, -var) -> [B,C+4,H,W]
  * (modules/SparseDenseNetRefinementMask.py:197).  C = 0 (left_fea may be NULL) packs only the four
  * single-channel maps -> [B,4,H,W], the second source of decnet_conv2d_tf32_nchw_cat. */

@@ -264,3 +264,42 @@ def test_dynamic_upsampling_tf32_tcgen05_path(B, C, h, w):
     ours_max, ours_mean = float((got - ref).abs().max()), float((got - ref).abs().mean())
     lib_max, lib_mean = float((cud - ref).abs().max()), float((cud - ref).abs().mean())
     assert ours_mean <= 2.0 * lib_mean + 1e-4 and ours_max <= 3.0 * lib_max + 1e-3, (ours_max, ours_mean, lib_max, lib_mean)
+
+
+def test_fused_detail_tail_is_bit_exact_with_sigmoid_threshold():
+    """sqdiff_pair / detail_head (a5 tail + a6): the mask computed on the logit must equal
+    `torch.sigmoid(logit) > thold` for every float around the crossing point, and the fused 1x1 conv must
+    reproduce the unit's own logits."""
+    from decnet_b200 import model as dm, ops
+    dev = "cuda"
+    for thold in (0.9, 0.5, 0.3):
+        xs = ops.sigmoid_logit_threshold(thold, dev)
+        base = torch.tensor([xs], device=dev)
+        # every float within +-4096 ulps of the crossing
+        bits = base.view(torch.int32) + torch.arange(-4096, 4097, device=dev, dtype=torch.int32)
+        x = bits.view(torch.float32)
+        want = (torch.sigmoid(x) > thold).float()
+        got = (x >= xs).float()
+        assert torch.equal(got, want), thold
+    torch.manual_seed(0)
+    det = dm.GenerateSparseMask(8).cuda().eval()
+    for m in det.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.data.normal_(1, 0.2); m.bias.data.normal_(0, 0.1)
+    B, H, W = 2, 54, 72
+    cl, cr = torch.randn(B, 8, H, W, device=dev), torch.randn(B, 8, H, W, device=dev)
+    pl, pr = torch.randn(B, 24, H // 3, W // 3, device=dev), torch.randn(B, 24, H // 3, W // 3, device=dev)
+    with torch.no_grad():
+        ll, _, _ = det(cl, pl)
+        lr, _, _ = det(cr, pr)
+        for thold in (0.5, 0.62):
+            lm, rm = det.masks_pair(cl, pl, cr, pr, thold)
+            for m, logit in ((lm, ll), (rm, lr)):
+                want = (torch.sigmoid(logit) > thold).float()
+                # identical except where fp32 summation-order noise (1e-6) meets the crossing point
+                flips = (m != want)
+                assert flips.float().mean().item() <= 1e-4
+                assert (logit[flips] - ops.sigmoid_logit_threshold(thold, dev)).abs().max().item() <= 1e-5 if flips.any() else True
+    a, b = torch.randn(4, 3, 20, 24, device=dev), torch.randn(4, 3, 20, 24, device=dev)
+    o0, o1 = ops.sqdiff_pair(a, b, b, a)
+    assert torch.equal(o0, (a - b) ** 2) and torch.equal(o1, (b - a) ** 2)
