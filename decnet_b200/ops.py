@@ -482,6 +482,52 @@ def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=Fal
     return out
 
 
+def conv2d_tf32_rows_supported(cin_padded, cout, H, W, dilation=1):
+    return bool(_lib.lib().decnet_conv2d_tf32_rows_supported(int(cin_padded), int(cout), int(H), int(W), int(dilation)))
+
+
+def pack_conv2d_tf32_rows_weights(w, bias, src_channels=None):
+    """[Cout<=8,Cin,3,3] (+ bias) -> (compact [3 kh][3 kw][nck][8 co][8 ci] fp32 TF32-rounded, bias [8]) for
+    decnet_conv2d_tf32_rows_nchw_cat; every source of a concatenated input is padded to whole 8-channel chunks."""
+    cout, cin = w.shape[:2]
+    assert cout <= 8
+    chans = tuple(src_channels) if src_channels else (cin,)
+    assert sum(chans) == cin, (chans, cin)
+    cpad = padded_cat_channels(chans)
+    wf = torch.zeros((8, cpad, 3, 3), dtype=torch.float32, device=w.device)
+    o = i = 0
+    for c in chans:
+        wf[:cout, o:o + c] = w[:, i:i + c].float()
+        o += (c + 7) // 8 * 8
+        i += c
+    nck = cpad // 8
+    out = wf.view(8, nck, 8, 3, 3).permute(3, 4, 1, 0, 2).contiguous()          # [kh][kw][ck][co][ci]
+    out = ((out.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)       # cvt.rna to TF32
+    b = torch.zeros(8, dtype=torch.float32, device=w.device)
+    b[:cout] = bias.float()
+    return out.contiguous(), b.contiguous()
+
+
+def conv2d_tf32_rows_nchw_cat(srcs, w_compact, bias8, cout, dilation=1, relu=False):
+    import ctypes
+    x0 = srcs[0]
+    _chk("srcs[0]", x0)
+    B, H, W = x0.shape[0], x0.shape[-2], x0.shape[-1]
+    chans = []
+    for i, t in enumerate(srcs):
+        _chk(f"srcs[{i}]", t, x0)
+        if (t.shape[0], t.shape[-2], t.shape[-1]) != (B, H, W):
+            raise ValueError(f"srcs[{i}] {tuple(t.shape)} does not match srcs[0] {tuple(x0.shape)}")
+        chans.append(1 if t.dim() == 3 else int(t.shape[1]))
+    n = len(srcs)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    cs = (ctypes.c_int * n)(*chans)
+    out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x0.device)
+    _call("decnet_conv2d_tf32_rows_nchw_cat", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
+          w_compact.data_ptr(), bias8.data_ptr(), out.data_ptr(), B, int(cout), H, W, int(dilation), 1 if relu else 0)
+    return out
+
+
 def dynup_pack_nhwc(disp, left_fea, cp, round_tf32=True):
     _chk("disp", disp)
     B, h, w = disp.shape

@@ -190,6 +190,17 @@ int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channel
                                 const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
                                 int relu, void *stream);
 
+/* Second formulation of the same convolution for C_out <= 8, dilation <= 4 (conv2d_rows_tcgen05.cu): pixels on the
+ * GEMM N dimension, block-Toeplitz weights on M, column taps as accumulator column offsets -- the epilogue needs no
+ * shuffles and stores 128 bits per thread.  Same sources / output contract as decnet_conv2d_tf32_nchw_cat.
+ *   w_compact fp32 [3 kh][3 kw][nck][8 c_out][8 c_in] (nck = sum over sources of ceil(C_i/8); each source padded to
+ *   whole 8-channel chunks; BN folded, TF32-rounded, zero padded); bias8 fp32 [8].
+ * decnet_conv2d_tf32_rows_supported takes the padded input channel count (8*nck). */
+int decnet_conv2d_tf32_rows_supported(int Cin_padded, int Cout, int H, int W, int dilation);
+int decnet_conv2d_tf32_rows_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_compact,
+                                     const float *bias8, float *out, int B, int Cout, int H, int W, int dilation,
+                                     int relu, void *stream);
+
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */

@@ -11,7 +11,7 @@ __device__ __forceinline__ bool tryw(uint64_t* b, uint32_t par){ uint32_t ok; as
 __host__ __device__ inline float aval(int m, int k){ return (float)(((m*3 + k*7) % 11) - 5); }
 __host__ __device__ inline float bval(int k, int n){ return (float)(((k*5 + n*3) % 7) - 3); }
 constexpr int N = 96, ROWS = 192;           // A buffer has 192 rows so that shifted starts stay inside
-__global__ void k(int shift_groups, int dcol, int lbo, int sbo, float* out){
+__global__ void k(int shift_groups, int dcol, int lbo, int sbo, float* out, int ldoff){
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t done; __shared__ uint32_t tslot;
   unsigned char* base = (unsigned char*)(((uintptr_t)smem+1023)&~(uintptr_t)1023);
@@ -41,8 +41,8 @@ __global__ void k(int shift_groups, int dcol, int lbo, int sbo, float* out){
   }
   while(!tryw(&done,0)){}
   asm volatile("tcgen05.fence::after_thread_sync;");
-  for (int c0=0;c0<128;c0+=32){
-    uint32_t v[32]; uint32_t taddr = tm + ((uint32_t)(warp*32)<<16) + c0;
+  for (int c0=0;c0<96;c0+=32){
+    uint32_t v[32]; uint32_t taddr = tm + ((uint32_t)(warp*32)<<16) + c0 + ldoff;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       :"=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15]),
        "=r"(v[16]),"=r"(v[17]),"=r"(v[18]),"=r"(v[19]),"=r"(v[20]),"=r"(v[21]),"=r"(v[22]),"=r"(v[23]),"=r"(v[24]),"=r"(v[25]),"=r"(v[26]),"=r"(v[27]),"=r"(v[28]),"=r"(v[29]),"=r"(v[30]),"=r"(v[31])
@@ -54,12 +54,12 @@ __global__ void k(int shift_groups, int dcol, int lbo, int sbo, float* out){
   if (warp==0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"::"r"(tm),"r"(128u));
 }
 int main(int argc, char** argv){
-  int shift = argc>1?atoi(argv[1]):0, dcol = argc>2?atoi(argv[2]):0, lbo = argc>3?atoi(argv[3]):128, sbo = argc>4?atoi(argv[4]):256;
+  int shift = argc>1?atoi(argv[1]):0, dcol = argc>2?atoi(argv[2]):0, lbo = argc>3?atoi(argv[3]):128, sbo = argc>4?atoi(argv[4]):256, ldoff = argc>5?atoi(argv[5]):0;
   float* d; cudaMalloc(&d,128*128*4); static float h[128*128];
   cudaFuncSetAttribute(k,cudaFuncAttributeMaxDynamicSharedMemorySize,16384);
-  k<<<1,128,16384>>>(shift,dcol,lbo,sbo,d); cudaError_t e=cudaDeviceSynchronize();
+  k<<<1,128,16384>>>(shift,dcol,lbo,sbo,d,ldoff); cudaError_t e=cudaDeviceSynchronize();
   cudaMemcpy(h,d,sizeof(h),cudaMemcpyDeviceToHost);
-  int bad=0; for(int m=0;m<128;++m) for(int n=0;n<N;++n){ float r=0; for(int kk=0;kk<8;++kk) r+=aval(m+8*shift,kk)*bval(kk,n); if (r!=h[m*128+dcol+n]) ++bad; }
-  printf("A K-major no-swizzle (LBO %d, SBO %d), start shifted by %d groups, D column offset %d: %d / %d mismatches (%s)\n",lbo,sbo,shift,dcol,bad,128*N,cudaGetErrorString(e));
+  int bad=0; for(int m=0;m<128;++m) for(int n=ldoff;n<N-32;++n){ float r=0; for(int kk=0;kk<8;++kk) r+=aval(m+8*shift,kk)*bval(kk,n); if (r!=h[m*128+dcol+n-ldoff]) ++bad; }
+  printf("A K-major no-swizzle (LBO %d, SBO %d), start shifted by %d groups, D column offset %d, tcgen05.ld column offset %d: %d mismatches (%s)\n",lbo,sbo,shift,dcol,ldoff,bad,cudaGetErrorString(e));
   return 0;
 }

@@ -128,3 +128,22 @@ def test_model_units_use_the_cat_path_and_match_packed_path():
         finally:
             dm.USE_TF32_TCGEN05 = old
         assert (r1 - r0).abs().max().item() <= 4e-3 * max(1.0, r0.abs().max().item())     # TF32 vs fp32 through 7 layers
+
+
+@pytest.mark.parametrize("chans,Cout,H,W,dil", [((8,), 8, 64, 96, 1), ((8,), 8, 37, 100, 1), ((8, 8, 1), 8, 50, 120, 3),
+                                                ((8, 4), 8, 45, 200, 1), ((5,), 3, 33, 60, 2), ((24,), 8, 60, 108, 1)])
+def test_conv2d_tf32_rows_formulation(chans, Cout, H, W, dil):
+    """conv2d_rows_tcgen05.cu (pixels on N, block-Toeplitz weights, column taps as accumulator column offsets):
+    opt-in second formulation, kept with its measurements in DESIGN.md section 3.3; same exactness bar."""
+    from decnet_b200 import ops
+    assert ops.conv2d_tf32_rows_supported(ops.padded_cat_channels(chans), Cout, H, W, dil)
+    g = torch.Generator(device="cuda").manual_seed(23)
+    srcs = [_tf32(torch.randn(2, c, H, W, device="cuda", generator=g)) for c in chans]
+    cin = sum(chans)
+    w = _tf32(torch.randn(Cout, cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    wc, b8 = ops.pack_conv2d_tf32_rows_weights(w, b, chans)
+    got = ops.conv2d_tf32_rows_nchw_cat(srcs, wc, b8, Cout, dil, False)
+    want = F.conv2d(torch.cat(srcs, 1).double(), w.double(), b.double(), padding=dil, dilation=dil).float()
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    assert not ops.conv2d_tf32_rows_supported(24, 8, 60, 108, 4)          # band matrices + two stages exceed shared memory
