@@ -451,6 +451,7 @@ def run_ours(args):
     # live with CUDA events on the launching stream; inputs (370 MB at B=8) exceed the 126 MB L2.
     roof = None
     roof_tensor = None
+    roof_conv2d = None
     if rank == 0:
         pk = peaks()
         s = 3 if info["skip_stage_id"] > 3 else 2
@@ -483,6 +484,36 @@ def run_ours(args):
                 roof["traffic"] = json.loads(tr.read_text()).get("sparse_row_kernel_bytes_per_launch")
             except Exception:
                 pass
+        # the thin 3x3 Conv2d layers (conv2d_tcgen05_kernel, 31 % of the step): the 8->8 layer at the finest level,
+        # algorithmic bytes = input + output once
+        try:
+            Bq, Cq, Hq, Wq = left["stage3"].shape
+            if ops.conv2d_tf32_supported(Cq, 8, Hq, Wq, 1):
+                gq = torch.Generator(device=dev).manual_seed(7)
+                wq = torch.randn(8, Cq, 3, 3, device=dev, generator=gq) * 0.1
+                wpk, bpk = ops.pack_conv2d_tf32_nchw_weights(wq, torch.zeros(8, device=dev))
+                xq = left["stage3"]
+                for _ in range(3):
+                    ops.conv2d_tf32_nchw(xq, wpk, bpk, 8, 1, True)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    ops.conv2d_tf32_nchw(xq, wpk, bpk, 8, 1, True)
+                e1.record(); torch.cuda.synchronize()
+                t_c = e0.elapsed_time(e1) * 1e-3 / 20
+                alg_c = 4.0 * Bq * Hq * Wq * (Cq + 8)
+                roof_conv2d = {"bound": "hbm", "kernel": "conv2d_tcgen05_kernel (3x3, 8->8 channels, finest level, TF32)",
+                               "achieved": alg_c / t_c / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": alg_c / t_c / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes": alg_c,
+                               "us_per_launch": t_c * 1e6}
+                if tr.exists():
+                    try:
+                        roof_conv2d["traffic"] = json.loads(tr.read_text()).get("conv2d_tcgen05_kernel_bytes_per_launch")
+                    except Exception:
+                        pass
+        except Exception as e:
+            roof_conv2d = {"bound": "hbm", "note": f"{type(e).__name__}: {e}"}
         # tensor roofline of the coarse 3-D aggregation (a3), timed inside the step
         try:
             from decnet_b200 import conv3d as c3
@@ -528,7 +559,8 @@ def run_ours(args):
                         "note": e2e_note},
                 "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step,
-                "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tensor, "roofline_conv2d": roof_conv2d,
+                "cpu_baseline": cpu,
                 "from_images": from_images}
         print(json.dumps(line), flush=True)
     if world > 1:
