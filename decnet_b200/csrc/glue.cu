@@ -110,6 +110,48 @@ costvol_kernel(const float *__restrict__ L, const float *__restrict__ R, void *_
     }
 }
 
+// LAYOUT 1 at full parallelism: one thread = one voxel x 8 channels (one 16-byte store; the octets of a voxel are
+// consecutive threads, so the channels-last rows are written coalesced).  The per-voxel thread of costvol_kernel<1>
+// walks 224 channels serially with only B*D*H*W = 46 080 threads at SceneFlow size: latency-bound, 10x off.
+__global__ void __launch_bounds__(kBlock)
+costvol_bf16_kernel(const float *__restrict__ L, const float *__restrict__ R, __nv_bfloat16 *__restrict__ out,
+                    int B, int C, int H, int W, int D, int Cpad, int row0, int nrows)
+{
+    const int octs = Cpad >> 3;
+    const long long n = (long long)B * D * nrows * W * octs;
+    const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (tid >= n) return;
+    const int oct = (int)(tid % octs);
+    const long long idx = tid / octs;
+    const int w = (int)(idx % W);
+    const int hl = (int)((idx / W) % nrows);
+    const int d = (int)((idx / ((long long)W * nrows)) % D);
+    const int b = (int)(idx / ((long long)W * nrows * D));
+    const int h = row0 + hl;
+    const bool in_img = h >= 0 && h < H;
+    const int hc = min(max(h, 0), H - 1);
+    const float ix = sample_coord((float)w - (float)d, (float)W);
+    const float iy = sample_coord((float)hc, (float)H);
+    const Taps t = make_taps(ix, iy, H, W);
+    const bool left_on = (w >= d) && in_img;
+    const size_t plane = (size_t)H * W;
+    const float *Lb = L + (size_t)b * C * plane + (size_t)hc * W + w;
+    const float *Rb = R + (size_t)b * C * plane;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = oct * 8 + k;
+        float val = 0.f;
+        if (c < C) {
+            const float r = sample_plane(Rb + (size_t)c * plane, t, H, W);
+            const float l = left_on ? __ldg(Lb + (size_t)c * plane) : 0.f;
+            val = l * r;
+        }
+        v[k] = __float2bfloat16(val);
+    }
+    *reinterpret_cast<uint4 *>(out + (size_t)idx * Cpad + oct * 8) = *reinterpret_cast<const uint4 *>(v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // a4: soft-argmin (disparity_regression, submodule.py:766-777): pred = sum_d softmax_d(cost) * d
 // ---------------------------------------------------------------------------------------------
@@ -613,10 +655,11 @@ int decnet_costvol_bf16_ndhwc_rows(const float *L, const float *R, void *vol, in
     DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0 && nrows > 0, "non-positive size");
     DECNET_REQUIRE(Cpad >= C && Cpad % 8 == 0, "Cpad=%d must be >= C=%d and a multiple of 8", Cpad, C);
     DECNET_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15u) == 0, "volume must be 16-byte aligned");
-    const long long n = (long long)B * D * nrows * W;
-    costvol_kernel<1><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(L, R, vol, B, C, H, W, D, Cpad,
-                                                                                               row0, nrows);
-    return after_launch("costvol_kernel<bf16>");
+    const long long n = (long long)B * D * nrows * W * (Cpad / 8);
+    DECNET_REQUIRE((n + kBlock - 1) / kBlock < (1ll << 31), "volume too large for one launch");
+    costvol_bf16_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        L, R, static_cast<__nv_bfloat16 *>(vol), B, C, H, W, D, Cpad, row0, nrows);
+    return after_launch("costvol_bf16_kernel");
 }
 
 int decnet_costvol_bf16_ndhwc(const float *L, const float *R, void *vol, int B, int C, int Cpad, int H, int W, int D,
