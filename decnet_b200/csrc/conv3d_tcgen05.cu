@@ -417,7 +417,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];       // this CTA's operands landed (local TMA completion)
+    __shared__ __align__(8) uint64_t peer_full_bar[kMaxStages];  // leader only: the peer's operands landed (relayed)
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
@@ -439,7 +440,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&peer_full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
         fence_mbar_init();
     }
@@ -471,11 +472,12 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                             for (int ck = 0; ck < p.nchunks; ++ck) {
                                 mbar_wait(&empty_bar[s], ph ^ 1u);
                                 unsigned char *sa = base + (size_t)s * stage_bytes;
-                                const uint32_t lbar = map_to_cta(smem_u32(&full_bar[s]), 0);
-                                if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));
-                                else remote_arrive(lbar);
-                                tma_load_5d_2sm(sa, &tmA, ck * p.chunk_ch, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, lbar);
-                                tma_load_3d_2sm(sa + kABytes, &tmB, ck * p.chunk_ch, (int)cta_rank * half_n, tap, lbar);
+                                // every CTA completes its OWN barrier (signalling the leader's barrier from the peer's TMA
+                                // made the loads 2-3x slower); the peer's idle MMA warp relays "landed" to the leader
+                                const bool la = !(p.skip_tma & 2), lb = !(p.skip_tma & 4);
+                                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)((la ? kABytes : 0) + (lb ? b_bytes : 0)));
+                                if (la) tma_load_5d(sa, &tmA, ck * p.chunk_ch, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, &full_bar[s]);
+                                if (lb) tma_load_3d(sa + kABytes, &tmB, ck * p.chunk_ch, (int)cta_rank * half_n, tap, &full_bar[s]);
                                 if (++s == kStages) { s = 0; ph ^= 1u; }
                             }
             }
@@ -499,7 +501,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const int last_ck = p.nchunks - 1;
                 for (int tap = 0; tap < 9 * p.taps_d; ++tap) {
                     for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
-                        if (!ready) { const long long w0_ = clock64(); mbar_wait(&full_bar[s], ph); t_wait += clock64() - w0_; }
+                        if (!ready) { const long long w0_ = clock64(); mbar_wait(&full_bar[s], ph); mbar_wait(&peer_full_bar[s], ph); t_wait += clock64() - w0_; }
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
                         const uint64_t da = make_smem_desc_sw128(sa);
@@ -507,7 +509,7 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                         const uint32_t ebar = empty_base + (uint32_t)(s * 8);
                         int sn = s + 1; uint32_t phn = ph;
                         if (sn == kStages) { sn = 0; phn ^= 1u; }
-                        ready = mbar_test_wait(&full_bar[sn], phn);
+                        ready = mbar_test_wait(&full_bar[sn], phn) && mbar_test_wait(&peer_full_bar[sn], phn);
                         if (ck != last_ck) umma2_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar);
                         else switch (p.last_ksteps) {
                             case 4: umma2_stage_elect<4>(acc, da, db, idesc, first ^ 1u, ebar); break;
@@ -527,6 +529,16 @@ conv3d_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 p.dbg[4 * blockIdx.x + 2] = t_wait_acc;
                 p.dbg[4 * blockIdx.x + 3] = it;
             }
+        } else if (lane == 0) {
+            // ===================== peer CTA: relay "my operands landed" to the leader, stage by stage =====================
+            int s = 0; uint32_t ph = 0;
+            const int per_unit = 9 * p.taps_d * p.nchunks;
+            for (int u = cluster_id; u < num_units; u += num_clusters)
+                for (int i = 0; i < per_unit; ++i) {
+                    mbar_wait(&full_bar[s], ph);
+                    remote_arrive(map_to_cta(smem_u32(&peer_full_bar[s]), 0));
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
+                }
         }
     } else {
         // ===================== epilogue (warps 2..5 of both CTAs) =====================
@@ -663,11 +675,11 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
     DECNET_REQUIRE(tiles < (1ll << 31), "too many tiles");
     p.num_tiles = (int)tiles;
     p.dbg = g_conv3d_dbg;
-    p.skip_tma = g_conv3d_variant == 3 ? 1 : 0;
+    p.skip_tma = g_conv3d_variant == 3 ? 1 : (g_conv3d_variant >= 10 ? (g_conv3d_variant / 10) * 2 : 0);
     const int sms = sm_count_cached();
     // The CTA-pair kernel is correct (same tests) but measured 2x slower than the single-CTA one in
     // round 1 (MMAs slow down 3x while TMA fills run): opt-in only.
-    const bool two_cta = g_conv3d_variant == 2 && tiles >= 2 && sms >= 2 && out_mode != 2;
+    const bool two_cta = (g_conv3d_variant % 10) == 2 && tiles >= 2 && sms >= 2 && out_mode != 2;
     const size_t stage_bytes = kABytes + (size_t)(two_cta ? np / 2 : np) * kRowBytes;
     p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
