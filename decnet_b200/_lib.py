@@ -49,6 +49,8 @@ SIGNATURES = {
     "decnet_dynup_glue_nhwc": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
     "decnet_sqdiff_pair": (_i, [_f32p] * 6 + [C.c_longlong, C.c_void_p]),
     "decnet_detail_head": (_i, [_f32p] * 3 + [C.c_float, C.c_float] + [_f32p] * 2 + [_i] * 3 + [C.c_void_p]),
+    "decnet_detail_level_scratch_floats": (C.c_longlong, [_i] * 3),
+    "decnet_detail_level": (_i, [_f32p] * 4 + [C.c_float] + [_i] * 3 + [C.c_void_p]),
     "decnet_attn_pack": (_i, [_f32p] * 6 + [_i] * 4 + [C.c_void_p]),
     "decnet_blend": (_i, [_f32p] * 5 + [_i] * 3 + [C.c_void_p]),
     "decnet_warp_bilinear": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),

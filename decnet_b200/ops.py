@@ -247,6 +247,26 @@ def detail_head(x_l, x_r, w3, bias, logit_thold):
     return ml, mr
 
 
+def detail_detection(img, iters=3, thold=0.3):
+    """Image-space lost-detail masks (reference: utils.detailDetection, demo.py:161-162) for images already padded
+    to a multiple of 3**iters: img [B,3,H,W] in [0,1] -> [mask_full, mask_1/3, ...] fp32 {0,1} [B,H/3^i,W/3^i]."""
+    _chk("img", img)
+    B, c, H, W = img.shape
+    if c != 3 or H % 3 ** iters or W % 3 ** iters:
+        raise ValueError(f"img must be [B,3,H,W] with H, W multiples of {3 ** iters}, got {tuple(img.shape)}")
+    scratch = torch.empty(int(_lib.lib().decnet_detail_level_scratch_floats(B, H, W)), dtype=torch.float32, device=img.device)
+    masks, data = [], img
+    for _ in range(iters):
+        h, w = data.shape[2], data.shape[3]
+        down = torch.empty((B, 3, h // 3, w // 3), dtype=torch.float32, device=img.device)
+        mask = torch.empty((B, h, w), dtype=torch.float32, device=img.device)
+        _call("decnet_detail_level", data, data.data_ptr(), down.data_ptr(), mask.data_ptr(), scratch.data_ptr(),
+              float(thold), B, h, w)
+        masks.append(mask)
+        data = down
+    return masks
+
+
 def dynup_pack(disp, left_fea):
     _chk("disp", disp)
     B, h, w = disp.shape

@@ -254,6 +254,14 @@ int decnet_sqdiff_pair(const float *a0, const float *b0, float *out0, const floa
 int decnet_detail_head(const float *x_l, const float *x_r, const float *w3_host, float bias, float logit_thold,
                        float *mask_l, float *mask_r, int B, int H, int W, void *stream);
 
+/* one pyramid level of the image-space lost-detail detector `detailDetection`
+ * (utils/utils.py:447-534, called with scale 3, three levels, thold 0.3 in demo.py:161-162), cv2's float32
+ * arithmetic restated on the device.  data fp32 [B,3,H,W] in [0,1] (H, W multiples of 3), down fp32 [B,3,H/3,W/3]
+ * (the next level's data), mask fp32 [B,H,W] in {0,1}; scratch holds decnet_detail_level_scratch_floats floats. */
+long long decnet_detail_level_scratch_floats(int B, int H, int W);
+int decnet_detail_level(const float *data, float *down, float *mask, float *scratch, float thold,
+                        int B, int H, int W, void *stream);
+
 /* SoftAttention conv input cat(left_fea, dense, sparse, left_mask, -var) -> [B,C+4,H,W]
  * (modules/SparseDenseNetRefinementMask.py:197).  C = 0 (left_fea may be NULL) packs only the four
  * single-channel maps -> [B,4,H,W], the second source of decnet_conv2d_tf32_nchw_cat. */
