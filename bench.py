@@ -180,13 +180,16 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_from_images(args, info, dev, timed):
-    """Feature extractor (both views) + hot path from synthetic images; returns the `from_images` object."""
+    """demo.py's device work from the decoded images on: uint8 RGB pairs -> pad / scale / normalise -> feature extractor
+    (both views) -> hot path -> 16-bit disparity image, one CUDA graph; returns the `from_images` object."""
     import torch
+    from decnet_b200 import ops
     from decnet_b200.features import FeatExtNetChannelPlus
     from decnet_b200.model import DecompMatching
     from decnet_b200.params import make_featext_state, make_hotpath_state
     from decnet_b200.synthetic import calibrate_mask_density
     B, H, W = args.batch, info["H"], info["W"]
+    oh, ow = (540, 960) if args.workload == "sceneflow" else (H, W)          # unpadded image size (demo.py pads top/left)
     fe = FeatExtNetChannelPlus(8)
     fe.load_state_dict(make_featext_state(17))
     fe = fe.to(dev)
@@ -197,11 +200,16 @@ def run_from_images(args, info, dev, timed):
     g = torch.Generator(device=dev).manual_seed(99)
     sets = []
     for _ in range(2):
-        sets.append({"l": torch.randn(B, 3, H, W, device=dev, generator=g), "r": torch.randn(B, 3, H, W, device=dev, generator=g)})
-    dens = calibrate_mask_density(model, fe(sets[0]["l"]), fe(sets[0]["r"]), args.rho)
+        sets.append({"l": torch.randint(0, 256, (B, oh, ow, 3), device=dev, generator=g, dtype=torch.uint8),
+                     "r": torch.randint(0, 256, (B, oh, ow, 3), device=dev, generator=g, dtype=torch.uint8)})
+
+    def feats(u8):
+        return fe(ops.image_prepare_u8(u8, want01=False)[1])
+
+    dens = calibrate_mask_density(model, feats(sets[0]["l"]), feats(sets[0]["r"]), args.rho)
 
     def step_eager(st):
-        return model(fe(st["l"]), fe(st["r"]))[0]
+        return ops.disp_to_u16(model(feats(st["l"]), feats(st["r"]))[0], oh, ow)
 
     for st in sets:
         step_eager(st)
@@ -219,9 +227,9 @@ def run_from_images(args, info, dev, timed):
         sets[0]["graph"].replay()
     ms = timed(lambda: sets[0]["graph"].replay(), args.steps)
     value = B * args.steps / (ms * 1e-3)
-    # end to end: pinned images -> device (copy stream, double-buffered), graph, disparity -> pinned host
+    # end to end: pinned uint8 images -> device (copy stream, double-buffered), graph, uint16 disparity -> pinned host
     host = {k: sets[0][k].cpu().pin_memory() for k in ("l", "r")}
-    host_out = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((B, oh, ow), dtype=torch.uint16).pin_memory()
     copy_stream, main = torch.cuda.Stream(), torch.cuda.current_stream()
 
     def upload(buf, after):
@@ -249,10 +257,11 @@ def run_from_images(args, info, dev, timed):
     run(3)
     n = max(4, args.steps)
     ms_e2e = timed(lambda: run(n), 1)
-    return {"what": "feature extractor on both views (FeatExtNetChannelPlus drop-in) + hot path, one CUDA graph",
+    return {"what": "uint8 RGB pairs -> pad/scale/normalise -> feature extractor on both views (FeatExtNetChannelPlus drop-in) "
+                    "-> hot path -> uint16 disparity image (x256, cropped), one CUDA graph",
             "value": value, "unit": UNIT, "ms_per_step": ms / args.steps,
             "e2e": {"value": B * n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / n,
-                    "h2d_bytes_per_step": 2 * B * 3 * H * W * 4, "d2h_bytes_per_step": B * H * W * 4},
+                    "h2d_bytes_per_step": 2 * B * 3 * oh * ow, "d2h_bytes_per_step": B * oh * ow * 2},
             "left_mask_density": [round(d, 4) for d in dens]}
 
 

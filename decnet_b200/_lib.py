@@ -51,6 +51,9 @@ SIGNATURES = {
     "decnet_detail_head": (_i, [_f32p] * 3 + [C.c_float, C.c_float] + [_f32p] * 2 + [_i] * 3 + [C.c_void_p]),
     "decnet_detail_level_scratch_floats": (C.c_longlong, [_i] * 3),
     "decnet_detail_level": (_i, [_f32p] * 4 + [C.c_float] + [_i] * 3 + [C.c_void_p]),
+    "decnet_image_prepare_u8": (_i, [_f32p] * 5 + [_i] * 5 + [C.c_void_p]),
+    "decnet_disp_to_u16": (_i, [_f32p] * 2 + [_i] * 5 + [C.c_void_p]),
+    "decnet_epe_3px": (_i, [_f32p] * 2 + [C.c_float, _f32p, C.c_longlong, C.c_void_p]),
     "decnet_attn_pack": (_i, [_f32p] * 6 + [_i] * 4 + [C.c_void_p]),
     "decnet_blend": (_i, [_f32p] * 5 + [_i] * 3 + [C.c_void_p]),
     "decnet_warp_bilinear": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),

@@ -247,6 +247,45 @@ def detail_head(x_l, x_r, w3, bias, logit_thold):
     return ml, mr
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)       # demo.py:85-86
+
+
+def image_prepare_u8(img_u8, multiple=27, want01=True, want_norm=True, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """uint8 RGB [B,h,w,3] (CUDA) -> (img01, img_norm) fp32 [B,3,H,W], top/left zero-padded to multiples of
+    `multiple` like demo.py:75-81; img01 = v/255, img_norm = (v/255 - mean)/std (demo.py:82-88)."""
+    import ctypes
+    if not (isinstance(img_u8, torch.Tensor) and img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+            and img_u8.dim() == 4 and img_u8.shape[3] == 3):
+        raise ValueError("img_u8 must be a contiguous CUDA uint8 tensor [B,h,w,3]")
+    B, h, w, _ = img_u8.shape
+    H, W = -(-h // multiple) * multiple, -(-w // multiple) * multiple
+    o01 = torch.empty((B, 3, H, W), dtype=torch.float32, device=img_u8.device) if want01 else None
+    onm = torch.empty((B, 3, H, W), dtype=torch.float32, device=img_u8.device) if want_norm else None
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    _call("decnet_image_prepare_u8", img_u8, img_u8.data_ptr(), o01.data_ptr() if want01 else None,
+          onm.data_ptr() if want_norm else None, ctypes.cast(m, ctypes.c_void_p), ctypes.cast(s, ctypes.c_void_p), B, h, w, H, W)
+    return o01, onm
+
+
+def disp_to_u16(pred, ori_h, ori_w):
+    """[B,H,W] fp32 disparity -> [B,ori_h,ori_w] uint16 (x256, clamped, cropped bottom/right) as demo.py:191-197."""
+    _chk("pred", pred)
+    B, H, W = pred.shape
+    out = torch.empty((B, int(ori_h), int(ori_w)), dtype=torch.uint16, device=pred.device)
+    _call("decnet_disp_to_u16", pred, pred.data_ptr(), out.data_ptr(), B, H, W, int(ori_h), int(ori_w))
+    return out
+
+
+def epe_3px(pred, gt, max_disp):
+    """(epe, 3-px error %) of modules/loss.py:427-437 as device tensors."""
+    _chk("pred", pred)
+    _chk("gt", gt, pred, pred.shape)
+    sums = torch.empty(3, dtype=torch.float64, device=pred.device)
+    _call("decnet_epe_3px", pred, pred.data_ptr(), gt.data_ptr(), float(max_disp), sums.data_ptr(), pred.numel())
+    return (sums[0] / sums[2]).float(), (100.0 - 100.0 * sums[1] / sums[2]).float()
+
+
 def detail_detection(img, iters=3, thold=0.3):
     """Image-space lost-detail masks (reference: utils.detailDetection, demo.py:161-162) for images already padded
     to a multiple of 3**iters: img [B,3,H,W] in [0,1] -> [mask_full, mask_1/3, ...] fp32 {0,1} [B,H/3^i,W/3^i]."""

@@ -262,6 +262,19 @@ long long decnet_detail_level_scratch_floats(int B, int H, int W);
 int decnet_detail_level(const float *data, float *down, float *mask, float *scratch, float thold,
                         int B, int H, int W, void *stream);
 
+/* the data formats either side of the path.
+ *   decnet_image_prepare_u8: uint8 RGB [B,h,w,3] -> top/left zero pad to HxW (demo.py:75-81), out01 = v/255 fp32
+ *     [B,3,H,W] (input of detailDetection, demo.py:158-162) and out_norm = (v/255 - mean)/std (demo.py:82-88); either
+ *     output may be NULL; mean3 / std3 are HOST pointers.
+ *   decnet_disp_to_u16: clamp(pred*256, 0, 65535) truncated to uint16 and cropped to the last ori_h rows / ori_w
+ *     columns (demo.py:191-197; the PNG container is written on the host).
+ *   decnet_epe_3px: sums3 (device, 3 doubles) = {sum |pred-gt|, #(|err|<3 or <5% gt), #valid} over 0 < gt < max_disp
+ *     (modules/loss.py:427-437: epe = sums[0]/sums[2], loss_3 = 100 - 100*sums[1]/sums[2]). */
+int decnet_image_prepare_u8(const unsigned char *img_hwc, float *out01, float *out_norm, const float *mean3_host,
+                            const float *std3_host, int B, int h, int w, int H, int W, void *stream);
+int decnet_disp_to_u16(const float *pred, unsigned short *out, int B, int H, int W, int ori_h, int ori_w, void *stream);
+int decnet_epe_3px(const float *pred, const float *gt, float max_disp, double *sums3, long long n, void *stream);
+
 /* SoftAttention conv input cat(left_fea, dense, sparse, left_mask, -var) -> [B,C+4,H,W]
  * (modules/SparseDenseNetRefinementMask.py:197).  C = 0 (left_fea may be NULL) packs only the four
  * single-channel maps -> [B,4,H,W], the second source of decnet_conv2d_tf32_nchw_cat. */
