@@ -110,46 +110,50 @@ costvol_kernel(const float *__restrict__ L, const float *__restrict__ R, void *_
     }
 }
 
-// LAYOUT 1 at full parallelism: one thread = one voxel x 8 channels (one 16-byte store; the octets of a voxel are
-// consecutive threads, so the channels-last rows are written coalesced).  The per-voxel thread of costvol_kernel<1>
-// walks 224 channels serially with only B*D*H*W = 46 080 threads at SceneFlow size: latency-bound, 10x off.
+// LAYOUT 1, block-cooperative: one CTA = one (b, d, h) row of the volume.  The NCHW features are read with w fastest
+// (coalesced), the products go through a shared-memory tile [w][Cpad] and leave as whole channels-last rows
+// (coalesced 16-byte stores).  The per-voxel thread of costvol_kernel<1> walks 224 channels serially with only
+// B*D*H*W = 46 080 threads at SceneFlow size (111 us); a thread per (voxel, 8 channels) reads 8 planes apart (144 us).
+constexpr int kCvTileW = 64;
 __global__ void __launch_bounds__(kBlock)
-costvol_bf16_kernel(const float *__restrict__ L, const float *__restrict__ R, __nv_bfloat16 *__restrict__ out,
-                    int B, int C, int H, int W, int D, int Cpad, int row0, int nrows)
+costvol_bf16_rows_kernel(const float *__restrict__ L, const float *__restrict__ R, __nv_bfloat16 *__restrict__ out,
+                         int C, int H, int W, int D, int Cpad, int row0, int nrows)
 {
-    const int octs = Cpad >> 3;
-    const long long n = (long long)B * D * nrows * W * octs;
-    const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (tid >= n) return;
-    const int oct = (int)(tid % octs);
-    const long long idx = tid / octs;
-    const int w = (int)(idx % W);
-    const int hl = (int)((idx / W) % nrows);
-    const int d = (int)((idx / ((long long)W * nrows)) % D);
-    const int b = (int)(idx / ((long long)W * nrows * D));
+    extern __shared__ __align__(16) unsigned char cv_smem[];
+    __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(cv_smem);             // [kCvTileW][Cpad + 2]: odd word stride, conflict-free
+    const int ts = Cpad + 2;
+    __shared__ Taps taps[kCvTileW];
+    const int hl = blockIdx.x % nrows, d = (blockIdx.x / nrows) % D, b = blockIdx.x / (nrows * D);
     const int h = row0 + hl;
     const bool in_img = h >= 0 && h < H;
     const int hc = min(max(h, 0), H - 1);
-    const float ix = sample_coord((float)w - (float)d, (float)W);
-    const float iy = sample_coord((float)hc, (float)H);
-    const Taps t = make_taps(ix, iy, H, W);
-    const bool left_on = (w >= d) && in_img;
     const size_t plane = (size_t)H * W;
-    const float *Lb = L + (size_t)b * C * plane + (size_t)hc * W + w;
+    const float *Lb = L + (size_t)b * C * plane + (size_t)hc * W;
     const float *Rb = R + (size_t)b * C * plane;
-    __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = oct * 8 + k;
-        float val = 0.f;
-        if (c < C) {
-            const float r = sample_plane(Rb + (size_t)c * plane, t, H, W);
-            const float l = left_on ? __ldg(Lb + (size_t)c * plane) : 0.f;
-            val = l * r;
+    const float iy = sample_coord((float)hc, (float)H);
+    for (int w0 = 0; w0 < W; w0 += kCvTileW) {
+        const int wt = min(kCvTileW, W - w0);
+        __syncthreads();                                                        // previous tile fully written out
+        if (threadIdx.x < wt) taps[threadIdx.x] = make_taps(sample_coord((float)(w0 + threadIdx.x) - (float)d, (float)W), iy, H, W);
+        // channel padding of the tile
+        for (int i = threadIdx.x; i < wt * (Cpad - C); i += kBlock) tile[(i / (Cpad - C)) * ts + C + i % (Cpad - C)] = __float2bfloat16(0.f);
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * wt; i += kBlock) {
+            const int c = i / wt, wl = i - c * wt, w = w0 + wl;
+            float val = 0.f;
+            if (in_img && w >= d) val = __ldg(Lb + (size_t)c * plane + w) * sample_plane(Rb + (size_t)c * plane, taps[wl], H, W);
+            else if (in_img) val = 0.f * sample_plane(Rb + (size_t)c * plane, taps[wl], H, W);   // keeps NaN/Inf of R like l * r with l = 0
+            tile[wl * ts + c] = __float2bfloat16(val);
         }
-        v[k] = __float2bfloat16(val);
+        __syncthreads();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((((size_t)b * D + d) * nrows + hl) * W + w0) * Cpad);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tile);
+        const int cw = Cpad >> 1, tw2 = ts >> 1;                                   // words per row: output / tile
+        for (int i = threadIdx.x; i < wt * cw; i += kBlock) {
+            const int wl = i / cw, k = i - wl * cw;
+            dst[i] = src[wl * tw2 + k];
+        }
     }
-    *reinterpret_cast<uint4 *>(out + (size_t)idx * Cpad + oct * 8) = *reinterpret_cast<const uint4 *>(v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -655,11 +659,15 @@ int decnet_costvol_bf16_ndhwc_rows(const float *L, const float *R, void *vol, in
     DECNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0 && nrows > 0, "non-positive size");
     DECNET_REQUIRE(Cpad >= C && Cpad % 8 == 0, "Cpad=%d must be >= C=%d and a multiple of 8", Cpad, C);
     DECNET_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15u) == 0, "volume must be 16-byte aligned");
-    const long long n = (long long)B * D * nrows * W * (Cpad / 8);
-    DECNET_REQUIRE((n + kBlock - 1) / kBlock < (1ll << 31), "volume too large for one launch");
-    costvol_bf16_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
-        L, R, static_cast<__nv_bfloat16 *>(vol), B, C, H, W, D, Cpad, row0, nrows);
-    return after_launch("costvol_bf16_kernel");
+    const long long blocks = (long long)B * D * nrows;
+    DECNET_REQUIRE(blocks < (1ll << 31), "volume too large for one launch");
+    const size_t smem = (size_t)kCvTileW * (Cpad + 2) * sizeof(__nv_bfloat16);
+    DECNET_REQUIRE(smem <= 200 * 1024, "Cpad too large");
+    if (smem > 48 * 1024)
+        DECNET_CUDA(cudaFuncSetAttribute(costvol_bf16_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    costvol_bf16_rows_kernel<<<(unsigned)blocks, kBlock, smem, (cudaStream_t)stream>>>(
+        L, R, static_cast<__nv_bfloat16 *>(vol), C, H, W, D, Cpad, row0, nrows);
+    return after_launch("costvol_bf16_rows_kernel");
 }
 
 int decnet_costvol_bf16_ndhwc(const float *L, const float *R, void *vol, int B, int C, int Cpad, int H, int W, int D,
