@@ -436,12 +436,11 @@ def run_ours(args):
         e2e_steps = max(4, args.steps)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall = time.perf_counter()
         e0.record()
         run_e2e(e2e_steps)
         e1.record()
         barrier()
-        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t_wall) * 1e3 * 0)   # device clock
+        ms_e2e = e0.elapsed_time(e1)                                                  # device clock
         if world > 1:
             t = torch.tensor([ms_e2e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

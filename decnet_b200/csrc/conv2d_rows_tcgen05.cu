@@ -55,14 +55,6 @@ struct Params {
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
 // the three column taps of one input row: one election, three MMAs (the third always accumulates)
 __device__ __forceinline__ void umma_tf32_x3_elect(uint32_t d2, uint32_t d1, uint32_t d0, uint64_t a2, uint64_t a1, uint64_t a0,
                                                    uint64_t db, uint32_t idesc, uint32_t accumulate) {
