@@ -36,7 +36,7 @@ SIGNATURES = {
     "decnet_conv2d_tf32_supported": (_i, [_i] * 5),
     "decnet_conv2d_tf32_packed_floats": (_i, [_i] * 2),
     "decnet_conv2d_tf32_nchw": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),
-    "decnet_conv2d_tf32_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
+    "decnet_conv2d_tf32_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 7 + [C.c_void_p]),
     "decnet_conv2d_tf32_rows_supported": (_i, [_i] * 5),
     "decnet_conv2d_tf32_rows_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv3d_debug_timing": (None, [C.c_void_p]),

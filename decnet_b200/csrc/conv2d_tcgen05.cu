@@ -49,6 +49,7 @@ struct Params {
     const float *bias;                     // [CP]
     float *out;                            // [B][Cout][H][W]
     int B, Cout, H, W;
+    int w_valid;                           // columns >= w_valid (<= W) are written as zeros: row-pitch padding of a W % 4 != 0 image
     int dil;                               // dilation = padding
     int nck;                               // channel chunks of 8
     int ck1, ck2;                          // chunks [0,ck1) come from source 0, [ck1,ck2) from source 1, [ck2,nck) from source 2
@@ -137,6 +138,7 @@ __device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, u
         const int col = tx * p.vw - p.pad + lane;
         const int h0 = ty * (4 * p.G);
         const bool col_ok = lane_ok && col >= 0 && col < p.W;
+        const bool keep = col < p.w_valid;                       // pitch-padding columns stay exactly zero
         const int slot = j & 1;
         const long long tq0 = clock64();
         mbar_wait_relaxed(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
@@ -162,7 +164,7 @@ __device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, u
                 for (int i = 0; i < 4; ++i) {
                     const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[0][i4 + i]), d);
                     const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v[2][i4 + i]), d);
-                    x[i4 + i] = fmaxf((left + __uint_as_float(v[1][i4 + i])) + (right + bb[i]), floor_);
+                    x[i4 + i] = keep ? fmaxf((left + __uint_as_float(v[1][i4 + i])) + (right + bb[i]), floor_) : 0.f;
                 }
             }
             if (col_ok && 4 * g < rows_left) {
@@ -406,8 +408,9 @@ int decnet_conv2d_tf32_packed_floats(int Cin, int Cout)
 
 int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
                                 const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
-                                int relu, void *stream)
+                                int relu, int w_valid, void *stream)
 {
+    DECNET_REQUIRE(w_valid >= 0 && w_valid <= W, "w_valid=%d outside [0, W=%d]", w_valid, W);
     DECNET_REQUIRE(srcs && src_channels && w_packed && bias_padded && out, "null pointer");
     DECNET_REQUIRE(nsrc >= 1 && nsrc <= 3, "1..3 concatenated sources, got %d", nsrc);
     DECNET_REQUIRE(B > 0 && H > 0 && W > 0, "non-positive size");
@@ -427,6 +430,7 @@ int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channel
     p.ck1 = cks[0]; p.ck2 = cks[0] + cks[1];
     p.dbg = g_conv2dtc_dbg; p.prof = g_conv2dtc_prof;
     p.bias = bias_padded; p.out = out; p.B = B; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu;
+    p.w_valid = w_valid > 0 ? w_valid : W;
     CUtensorMap tmX[3], tmW;
     for (int i = 0; i < 3; ++i) {
         if (i >= nsrc) { tmX[i] = tmX[0]; continue; }
@@ -466,7 +470,7 @@ int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channel
 int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *bias_padded, float *out,
                             int B, int Cin, int Cout, int H, int W, int dilation, int relu, void *stream)
 {
-    return decnet_conv2d_tf32_nchw_cat(&x, &Cin, 1, w_packed, bias_padded, out, B, Cout, H, W, dilation, relu, stream);
+    return decnet_conv2d_tf32_nchw_cat(&x, &Cin, 1, w_packed, bias_padded, out, B, Cout, H, W, dilation, relu, 0, stream);
 }
 
 }  // extern "C"

@@ -93,9 +93,11 @@ class Conv2dUnit(nn.Module):
             self._tc = (self._folded,) + ops.pack_conv2d_tf32_nchw_weights(w, b)
         return self._tc
 
-    def forward_cat(self, srcs):
+    def forward_cat(self, srcs, w_valid=None):
         """forward(torch.cat(srcs, 1)) with single-channel maps given as [B,H,W]; on the tensor-core path the
-        concatenation is never materialised (the kernel reads each source through its own tensor map)."""
+        concatenation is never materialised (the kernel reads each source through its own tensor map).
+        w_valid: the tensors are right-padded to a 16-byte row pitch (see pad_pitch); columns >= w_valid of the
+        result are zeros."""
         x0 = srcs[0]
         chans = tuple(1 if t.dim() == 3 else t.shape[1] for t in srcs)
         c = self.conv
@@ -105,20 +107,25 @@ class Conv2dUnit(nn.Module):
               and c.dilation == (d, d) and c.padding == (d, d) and c.groups == 1 and sum(chans) == c.in_channels
               and ops.conv2d_tf32_supported(ops.padded_cat_channels(chans), c.out_channels, x0.shape[-2], x0.shape[-1], d))
         if not ok:
-            return self.forward(torch.cat([t.unsqueeze(1) if t.dim() == 3 else t for t in srcs], 1))
+            return self.forward(torch.cat([t.unsqueeze(1) if t.dim() == 3 else t for t in srcs], 1), w_valid=w_valid)
         cache = getattr(self, "_tc_cat", None)
         if cache is None or cache[0] is not self._folded or cache[1] != chans:
             w, b = self.folded()
             self._tc_cat = (self._folded, chans) + ops.pack_conv2d_tf32_nchw_weights(w, b, chans)
         return ops.conv2d_tf32_nchw_cat([t.contiguous() for t in srcs], self._tc_cat[2], self._tc_cat[3],
-                                        c.out_channels, d, self.relu)
+                                        c.out_channels, d, self.relu, w_valid or 0)
 
-    def forward(self, x, addend=None):
+    def forward(self, x, addend=None, w_valid=None):
         fast = x.is_cuda and x.dtype == torch.float32 and USE_NATIVE_CONV2D
         tc = self.tensor_core(x) if (fast and addend is None) else None
         if tc is not None:
             c = self.conv
-            return ops.conv2d_tf32_nchw(x.contiguous(), tc[1], tc[2], c.out_channels, c.dilation[0], self.relu)
+            return ops.conv2d_tf32_nchw_cat([x.contiguous()], tc[1], tc[2], c.out_channels, c.dilation[0], self.relu,
+                                            w_valid or 0)
+        if w_valid:
+            out = self.forward(x, addend)
+            out[..., w_valid:] = 0                       # keep the pitch padding at zero behind a non-tensor-core layer
+            return out
         nat = self.native() if fast else None
         if nat is not None:
             c = self.conv
@@ -179,6 +186,20 @@ class Conv3dUnit(nn.Module):
     def scale_bias(self):
         scale = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + BN_EPS)
         return scale, self.bn.bias.detach() - self.bn.running_mean * scale
+
+
+def pad_pitch(t):
+    """(tensor right-padded with zero columns to a width that is a multiple of 4, original width or None).
+    The tensor-core Conv2d reads images through TMA, which needs 16-byte row strides: a KITTI-sized level
+    (W = 1269, 423, 141) runs its conv stacks on such padded copies and crops the result (unpad_pitch)."""
+    W = t.shape[-1]
+    if W % 4 == 0 or not (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32 and t.is_cuda):
+        return t, None
+    return F.pad(t, (0, 4 - W % 4)), W
+
+
+def unpad_pitch(t, w_valid):
+    return t if w_valid is None else t[..., :w_valid].contiguous()
 
 
 def _reset_folded(module):
@@ -315,15 +336,21 @@ class GenerateSparseMask(nn.Module):
         """Left and right masks `sigmoid(forward(.)) > thold` with the tail fused: one kernel for both
         squared differences, and one for 1x1 conv + BN + sigmoid + threshold of both views (the comparison
         runs on the logit against the exact float where torch.sigmoid crosses `thold`)."""
-        pl, pr = self.deconv(pre_l), self.deconv(pre_r)
-        cl, cr = self.conv_sub(cur_l), self.conv_sub(cur_r)
+        # widths that are not a multiple of 4 (KITTI) run on right-padded copies, the padding kept at zero (pad_pitch)
+        cur_l, wv = pad_pitch(cur_l)
+        cur_r, _ = pad_pitch(cur_r)
+        pl = self.deconv[1](pad_pitch(self.deconv[0](pre_l))[0], w_valid=wv)
+        pr = self.deconv[1](pad_pitch(self.deconv[0](pre_r))[0], w_valid=wv)
+        cl = self.conv_sub[1](self.conv_sub[0](cur_l, w_valid=wv), w_valid=wv)
+        cr = self.conv_sub[1](self.conv_sub[0](cur_r, w_valid=wv), w_valid=wv)
         rl, rr = ops.sqdiff_pair(cl, pl, cr, pr)
-        xl, xr = self.conv[0](rl), self.conv[0](rr)
+        xl, xr = self.conv[0](rl, w_valid=wv), self.conv[0](rr, w_valid=wv)
         if getattr(self, "_head", None) is None or self._head[0] is not self.conv[1]._folded:
             w, b = self.conv[1].folded()                    # [1,3,1,1], [1]
             self._head = (self.conv[1]._folded, [float(v) for v in w.flatten().cpu()], float(b.cpu()))
-        return ops.detail_head(xl.contiguous(), xr.contiguous(), self._head[1], self._head[2],
-                               ops.sigmoid_logit_threshold(thold, xl.device))
+        ml, mr = ops.detail_head(xl.contiguous(), xr.contiguous(), self._head[1], self._head[2],
+                                 ops.sigmoid_logit_threshold(thold, xl.device))
+        return unpad_pitch(ml, wv), unpad_pitch(mr, wv)
 
 
 # --------------------------------------------------------------------------------------
@@ -389,8 +416,10 @@ class SoftAttention(nn.Module):
 
     def logits_cat(self, left_fea, aux):
         """logits(cat(left_fea, aux)) with aux = [dense, sparse, left_mask, -var] as one [B,4,H,W] tensor."""
-        x = self.conv[0].forward_cat([left_fea, aux])
-        return self.conv[2](self.conv[1](x))
+        left_fea, wv = pad_pitch(left_fea)
+        aux, _ = pad_pitch(aux)
+        x = self.conv[0].forward_cat([left_fea, aux], w_valid=wv)
+        return unpad_pitch(self.conv[2](self.conv[1](x, w_valid=wv), w_valid=wv), wv)
 
     def forward(self, x):
         return torch.sigmoid(self.conv(x))
@@ -419,17 +448,20 @@ class Refinement(nn.Module):
         units = list(self.conv)
         c0 = units[0].conv
         C = left_fea.shape[1]
+        Wp = (left_fea.shape[3] + 3) // 4 * 4
+        wv = None
         if (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32
                 and ops.conv2d_tf32_supported(ops.padded_cat_channels((C, C, 1)), c0.out_channels, left_fea.shape[2],
-                                              left_fea.shape[3], c0.dilation[0])):
+                                              Wp, c0.dilation[0])):
             # first conv reads (left, warped right, disparity) as three sources: only the warp is materialised
             warped = ops.warp_bilinear(right_fea.contiguous(), disp_map)
-            x = units[0].forward_cat([left_fea.contiguous(), warped, disp_map])
+            lp, wv = pad_pitch(left_fea.contiguous())
+            x = units[0].forward_cat([lp, pad_pitch(warped)[0], pad_pitch(disp_map)[0]], w_valid=wv)
         else:
             x = units[0](ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map))
         for unit in units[1:-1]:
-            x = unit(x)
-        residual = self.conv[-1](x).squeeze(1)
+            x = unit(x, w_valid=wv)
+        residual = unpad_pitch(self.conv[-1](x, w_valid=wv), wv).squeeze(1)
         return disp_map + residual, residual
 
 

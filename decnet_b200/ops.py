@@ -519,7 +519,7 @@ def conv2d_tf32_nchw(x, w_packed, bias_padded, cout, dilation=1, relu=False):
     return out
 
 
-def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=False):
+def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=False, w_valid=0):
     """Conv over torch.cat(srcs, 1) without building it; srcs: 1..3 tensors [B,Ci,H,W] or [B,H,W] (one channel)."""
     import ctypes
     x0 = srcs[0]
@@ -537,7 +537,8 @@ def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=Fal
     cs = (ctypes.c_int * n)(*chans)
     out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x0.device)
     _call("decnet_conv2d_tf32_nchw_cat", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
-          w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(), B, int(cout), H, W, int(dilation), 1 if relu else 0)
+          w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(), B, int(cout), H, W, int(dilation), 1 if relu else 0,
+          int(w_valid))
     return out
 
 

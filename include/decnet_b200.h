@@ -185,10 +185,13 @@ int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *
  * cat (torch.cat((left, dense, sparse, mask, -var)) before SoftAttention, SparseDenseNetRefinementMask.py:197;
  * cat((left, warped_right, disp)) in Refinement, modules/submodule.py:758-759).  Source i has src_channels[i]
  * channels and occupies ceil(src_channels[i]/8) whole chunks of the packed weights: pack as if the input had
- * sum(8*ceil(C_i/8)) channels with zero weights in each source's padding. */
+ * sum(8*ceil(C_i/8)) channels with zero weights in each source's padding.
+ * w_valid (0 = W): output columns >= w_valid are written as zeros.  Images whose width is not a multiple of 4
+ * (KITTI: 1269) run through this kernel as tensors padded on the right to a 16-byte row pitch; the padding is kept
+ * at zero layer after layer, and zeros right of the image are exactly the convolution's own padding. */
 int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
                                 const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
-                                int relu, void *stream);
+                                int relu, int w_valid, void *stream);
 
 /* Second formulation of the same convolution for C_out <= 8, dilation <= 4 (conv2d_rows_tcgen05.cu): pixels on the
  * GEMM N dimension, block-Toeplitz weights on M, column taps as accumulator column offsets -- the epilogue needs no

@@ -147,3 +147,32 @@ def test_conv2d_tf32_rows_formulation(chans, Cout, H, W, dil):
     want = F.conv2d(torch.cat(srcs, 1).double(), w.double(), b.double(), padding=dil, dilation=dil).float()
     assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
     assert not ops.conv2d_tf32_rows_supported(24, 8, 60, 108, 4)          # band matrices + two stages exceed shared memory
+
+
+def test_widths_not_multiple_of_4_run_on_pitch_padded_copies():
+    """KITTI-style widths (1269, 423, 141): the unit pads the row pitch to 16 bytes, keeps the padding at zero through
+    a stack (w_valid) and crops; result = the fp32 route on the unpadded tensor, at TF32 tolerance."""
+    from decnet_b200 import model as dm, ops
+    torch.manual_seed(4)
+    B, C, H, W = 2, 8, 42, 141
+    L, R = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    disp = torch.rand(B, H, W, device="cuda") * 20
+    ref = dm.Refinement(C, stage_id=3).cuda().eval()
+    att = dm.SoftAttention(C + 4, C).cuda().eval()
+    xp, wv = dm.pad_pitch(L)
+    assert wv == W and xp.shape[-1] == 144 and float(xp[..., W:].abs().max()) == 0
+    with torch.no_grad():
+        y = ref.conv[1](ref.conv[1](xp, w_valid=wv), w_valid=wv)            # two layers deep: padding must stay zero
+        assert float(y[..., W:].abs().max()) == 0 and float(y[..., :W].abs().max()) > 0
+        p1, r1 = ref(L, R, disp)
+        a1 = att.logits_cat(L, ops.attn_pack(None, disp, disp, (disp > 10).float(), disp))
+        old = dm.USE_TF32_TCGEN05
+        try:
+            dm.USE_TF32_TCGEN05 = False                                     # fp32 direct kernels on the unpadded tensors
+            p0, r0 = ref(L, R, disp)
+            a0 = att.logits(ops.attn_pack(L, disp, disp, (disp > 10).float(), disp))
+        finally:
+            dm.USE_TF32_TCGEN05 = old
+    assert r1.shape == r0.shape == (B, H, W) and a1.shape == a0.shape
+    assert (r1 - r0).abs().max().item() <= 4e-3 * max(1.0, r0.abs().max().item())
+    assert (a1 - a0).abs().max().item() <= 4e-3 * max(1.0, a0.abs().max().item())
