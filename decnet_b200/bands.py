@@ -101,10 +101,17 @@ class DistTransport:
         dist = self.dist
         mine = bands[self.rank]
         B, rows, W = mine.shape
-        sizes = torch.tensor([rows], device=mine.device, dtype=torch.int64)
-        all_sizes = [torch.zeros_like(sizes) for _ in range(self.world)]
-        dist.all_gather(all_sizes, sizes, group=self.group)
-        all_sizes = [int(s.item()) for s in all_sizes]
+        if getattr(self, "h_coarse", None):
+            # every band is the balanced split of the 1/27 rows scaled to the level: sizes are known without talking
+            # (and without a host synchronisation, so the whole step can be captured in a CUDA graph)
+            cb = shard.coarse_bands(self.h_coarse, self.world)
+            f = rows // (cb[self.rank][1] - cb[self.rank][0])
+            all_sizes = [(b - a) * f for a, b in cb]
+        else:
+            sizes = torch.tensor([rows], device=mine.device, dtype=torch.int64)
+            all_sizes = [torch.zeros_like(sizes) for _ in range(self.world)]
+            dist.all_gather(all_sizes, sizes, group=self.group)
+            all_sizes = [int(s.item()) for s in all_sizes]
         mx = max(all_sizes)
         pad = torch.zeros((B, mx, W), dtype=mine.dtype, device=mine.device)
         pad[:, :rows] = mine
@@ -181,6 +188,7 @@ def forward_bands(model, left_feats, right_feats, transport, left_mask_list=None
     Returns {rank: full final disparity [B, H, W]} (all-gathered after the last stage)."""
     tr = transport
     H0 = left_feats["stage0"].shape[2]
+    tr.h_coarse = H0
     pred = _dense_stage_bands(model, left_feats["stage0"].contiguous(), right_feats["stage0"].contiguous(),
                               model.max_disp // 27, tr)
     full = tr.all_gather_rows(pred)
