@@ -154,6 +154,7 @@ def test_widths_not_multiple_of_4_run_on_pitch_padded_copies():
     a stack (w_valid) and crops; result = the fp32 route on the unpadded tensor, at TF32 tolerance."""
     from decnet_b200 import model as dm, ops
     torch.manual_seed(4)
+    torch.backends.cudnn.allow_tf32 = True              # the route under test (PyTorch's default; other tests switch it off)
     B, C, H, W = 2, 8, 42, 141
     L, R = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
     disp = torch.rand(B, H, W, device="cuda") * 20
