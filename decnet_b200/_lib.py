@@ -39,14 +39,15 @@ SIGNATURES = {
     "decnet_conv2d_tf32_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 7 + [C.c_void_p]),
     "decnet_conv2d_tf32_rows_supported": (_i, [_i] * 5),
     "decnet_conv2d_tf32_rows_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
+    "decnet_conv2d_tf32_nhwc_halo": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),
     "decnet_conv3d_debug_timing": (None, [C.c_void_p]),
     "decnet_conv3d_set_variant": (None, [_i]),
     "decnet_softargmin": (_i, [_f32p] * 2 + [_i] * 4 + [C.c_void_p]),
     "decnet_mask_threshold": (_i, [_f32p] * 2 + [C.c_float] + [_f32p] * 4 + [_i] * 3 + [C.c_void_p]),
     "decnet_dynup_pack": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
     "decnet_dynup_glue": (_i, [_f32p] * 3 + [_i] * 3 + [C.c_void_p]),
-    "decnet_dynup_pack_nhwc": (_i, [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
-    "decnet_dynup_glue_nhwc": (_i, [_f32p] * 3 + [_i] * 4 + [C.c_void_p]),
+    "decnet_dynup_pack_nhwc": (_i, [_f32p] * 3 + [_i] * 7 + [C.c_void_p]),
+    "decnet_dynup_glue_nhwc": (_i, [_f32p] * 3 + [_i] * 5 + [C.c_void_p]),
     "decnet_sqdiff_pair": (_i, [_f32p] * 6 + [C.c_longlong, C.c_void_p]),
     "decnet_detail_head": (_i, [_f32p] * 3 + [C.c_float, C.c_float] + [_f32p] * 2 + [_i] * 3 + [C.c_void_p]),
     "decnet_detail_level_scratch_floats": (C.c_longlong, [_i] * 3),

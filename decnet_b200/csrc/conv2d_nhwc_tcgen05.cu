@@ -1,0 +1,307 @@
+// decnet_b200/csrc/conv2d_nhwc_tcgen05.cu -- the GEMM-sized 3x3 Conv2d layers of DynamicUpsampling.weight_learning
+// (modules/submodule.py:571-575: 9C+1 -> 81 -> 81 -> 81 channels at the coarse resolution of each level) as a TF32
+// implicit GEMM on channels-last tensors that carry their own zero border.
+//
+// conv3d_tcgen05.cu's Conv2d mode loads one A tile per tap: nine TMA fills of the same pixels per channel chunk, and its
+// main loop waits for operands.  Here the activations live in a PADDED channels-last layout
+// [B, h+2, w+2, C] (one zero pixel all around each image, written by the producing kernel), so that in the flattened
+// pixel index p a tap (kh, kw) is the constant offset (kh-1)*(w+2) + (kw-1).  A tile is 128 consecutive padded pixels:
+//   * per (row tap kh, 32-channel chunk) ONE TMA box of 130 pixels x 128 B lands in shared memory (SWIZZLE_128B);
+//   * the three column taps read it at +0 / +1 / +2 pixel rows: the UMMA descriptor's start address simply moves by
+//     128 B -- the MMA swizzles on absolute shared-memory address bits, so a start that is not 1 KB aligned is fine
+//     (scripts/micro/umma_rowshift.cu);
+//   * the weights of the three column taps arrive as one box {32 ch, NP, 3 taps}.
+// One stage = 12 MMAs (3 taps x 4 K-steps of 8) behind one barrier round trip instead of 4, and 1.6x fewer bytes
+// from L2 per tile.  Border pixels of the output are written as zeros, so the next layer needs no padding pass; image
+// boundaries inside the flattened index are covered by the borders, the ends of the tensor by TMA's zero fill.
+//
+// Warp roles as in conv3d_tcgen05.cu: 0 TMA producer, 1 MMA issuer, 2-5 epilogue; persistent CTAs, two TMEM slots.
+#include "common.cuh"
+#include "tma_utils.cuh"
+#include <mutex>
+
+namespace decnet {
+namespace conv2dnhwc {
+
+constexpr int kMaxStages = 6;
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kARows = 130;                        // 128 pixels + one halo pixel on each side
+constexpr int kABytes = 17 * 1024;                 // 130 rows x 128 B rounded up to the 1 KB swizzle period
+
+struct Params {
+    const float *bias;                             // [NP]
+    float *out;                                    // padded channels-last [B, h+2, w+2, NP]
+    int B, h, w;                                   // interior size
+    int cp, np;
+    int nchunks, last_ksteps;
+    long long P;                                   // B * (h+2) * (w+2) padded pixels
+    int relu, round_tf32, tmem_cols, num_tiles, stages;
+};
+
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// KSTEPS K-steps of 8 tf32 (32 bytes: +2 in the descriptor's 16-byte address field) of one column tap: one election
+#define DN_NEXT(OFF)                                                               \
+        "add.u64 a, %1, " #OFF ";\n\t"                                              \
+        "add.u64 b, %2, " #OFF ";\n\t"                                              \
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %3, t;\n\t"
+#define DN_HEAD                                                                    \
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b;\n\t"                            \
+        "elect.sync _|e, 0xffffffff;\n\t"                                           \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                 \
+        "setp.eq.b32 t, 0, 0;\n\t"                                                  \
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+template <int KSTEPS>
+__device__ __forceinline__ void umma_tap(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate_first) {
+    if constexpr (KSTEPS == 4)
+        asm volatile(DN_HEAD DN_NEXT(2) DN_NEXT(4) DN_NEXT(6) "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+    else if constexpr (KSTEPS == 3)
+        asm volatile(DN_HEAD DN_NEXT(2) DN_NEXT(4) "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+    else if constexpr (KSTEPS == 2)
+        asm volatile(DN_HEAD DN_NEXT(2) "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+    else
+        asm volatile(DN_HEAD "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+__device__ __forceinline__ void umma_taps3(int ksteps, uint32_t acc, uint64_t da, uint64_t db, uint32_t db_tap_step,
+                                           uint32_t idesc, uint32_t first) {
+    // three column taps: A moves one pixel row (128 B = 8 sixteen-byte units), B one tap block
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+        const uint64_t a = da + (uint64_t)(8 * kw), b = db + (uint64_t)(kw * db_tap_step);
+        const uint32_t acc_first = (kw == 0) ? first : 1u;
+        switch (ksteps) {
+            case 4: umma_tap<4>(acc, a, b, idesc, acc_first); break;
+            case 3: umma_tap<3>(acc, a, b, idesc, acc_first); break;
+            case 2: umma_tap<2>(acc, a, b, idesc, acc_first); break;
+            default: umma_tap<1>(acc, a, b, idesc, acc_first); break;
+        }
+    }
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_tap_bytes = p.np * 128;                       // one column tap of the weights: NP rows x 128 B
+    const int stage_bytes = kABytes + 3 * b_tap_bytes;
+    const int tx_bytes = kARows * 128 + 3 * b_tap_bytes;      // bytes TMA actually delivers per stage
+    const int kStages = p.stages;
+    const int acc_stride = p.tmem_cols >> 1;
+    const int pitch = p.w + 2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int p0 = tile * kTileM;
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int ck = 0; ck < p.nchunks; ++ck) {
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        unsigned char *sa = base + (size_t)s * stage_bytes;
+                        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)tx_bytes);
+                        tma_load_2d(sa, &tmA, ck * 32, p0 + (kh - 1) * pitch - 1, &full_bar[s]);
+                        tma_load_3d(sa + kABytes, &tmB, ck * 32, 0, kh * 3, &full_bar[s]);
+                        if (++s == kStages) { s = 0; ph ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // c_format F32, a/b TF32, both K-major, N = np, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.np >> 3) << 17) | (8u << 24);
+        const uint32_t smem_base = smem_u32(base);
+        const uint32_t empty_base = smem_u32(&empty_bar[0]);
+        const uint32_t db_tap_step = (uint32_t)(b_tap_bytes >> 4);
+        int s = 0; uint32_t ph = 0; int j = 0;
+        bool ready = false;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+            const int slot = j & 1;
+            mbar_wait(&tmem_empty_bar[slot], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
+            uint32_t first = 0u;                              // 0: overwrite the accumulator
+            for (int kh = 0; kh < 3; ++kh)
+                for (int ck = 0; ck < p.nchunks; ++ck) {
+                    if (!ready) mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
+                    const uint64_t da = make_desc_sw128(sa);
+                    const uint64_t db = make_desc_sw128(sa + kABytes);
+                    int sn = s + 1; uint32_t phn = ph;
+                    if (sn == kStages) { sn = 0; phn ^= 1u; }
+                    ready = mbar_test_wait(&full_bar[sn], phn);
+                    umma_taps3(ck == p.nchunks - 1 ? p.last_ksteps : 4, acc, da, db, db_tap_step, idesc, first);
+                    umma_commit_elect(empty_base + (uint32_t)(s * 8));
+                    first = 1u;
+                    s = sn; ph = phn;
+                }
+            umma_commit_elect(smem_u32(&tmem_full_bar[slot]));
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const long long per_img = (long long)(p.h + 2) * pitch;
+        int j = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+            const long long pix = (long long)tile * kTileM + r;
+            const bool inside = pix < p.P;
+            const long long rem = pix % per_img;
+            const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
+            const bool interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;   // border pixels are stored as zeros
+            const int slot = j & 1;
+            mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * acc_stride);
+            for (int c0 = 0; c0 < p.np; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                if (inside) {
+                    const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
+                    float4 *op = reinterpret_cast<float4 *>(p.out + pix * p.np + c0);
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (interior) {
+                            const float4 bv = __ldg(bp + i4);
+                            o = make_float4(v[4 * i4] + bv.x, v[4 * i4 + 1] + bv.y, v[4 * i4 + 2] + bv.z, v[4 * i4 + 3] + bv.w);
+                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            if (p.round_tf32) {
+                                o.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
+                                o.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
+                                o.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u);
+                                o.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
+                            }
+                        }
+                        op[i4] = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace conv2dnhwc
+}  // namespace decnet
+
+using namespace decnet;
+using namespace decnet::conv2dnhwc;
+
+extern "C" {
+
+int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                                 int B, int h, int w, int cp, int np, int relu, int round_out_tf32, void *stream)
+{
+    DECNET_REQUIRE(x_pad && w_packed && bias && out_pad, "null pointer");
+    DECNET_REQUIRE(B > 0 && h > 0 && w > 0, "non-positive size");
+    DECNET_REQUIRE(cp % 8 == 0 && cp >= 8 && cp <= 4096, "cp=%d must be a multiple of 8", cp);
+    DECNET_REQUIRE(np % 16 == 0 && np >= 16 && np <= 256, "np=%d must be a multiple of 16 in [16,256]", np);
+    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x_pad) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out_pad) & 15u) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0,
+                   "pointers must be 16-byte aligned");
+    Params p{};
+    p.bias = bias; p.out = out_pad; p.B = B; p.h = h; p.w = w; p.cp = cp; p.np = np;
+    p.nchunks = (cp + 31) / 32;
+    p.last_ksteps = (cp - (p.nchunks - 1) * 32) / 8;
+    p.P = (long long)B * (h + 2) * (w + 2);
+    DECNET_REQUIRE(p.P + 2ll * (w + 3) < (1ll << 31), "tensor too large for 32-bit TMA coordinates");
+    p.relu = relu; p.round_tf32 = round_out_tf32;
+    p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;
+    p.num_tiles = (int)((p.P + kTileM - 1) / kTileM);
+    const size_t stage_bytes = (size_t)kABytes + (size_t)3 * np * 128;
+    p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    DECNET_REQUIRE(p.stages >= 2, "stage too large (np=%d)", np);
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[2] = {(uint64_t)cp, (uint64_t)p.P};
+        const uint64_t strides[1] = {(uint64_t)cp * 4};
+        const uint32_t box[2] = {32u, (uint32_t)kARows};
+        int rc = encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x_pad, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, 9u};
+        const uint64_t strides[2] = {(uint64_t)cp * 4, (uint64_t)np * cp * 4};
+        const uint32_t box[3] = {32u, (uint32_t)np, 3u};
+        int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, w_packed, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    {
+        static std::mutex mu;
+        static size_t set_for[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || set_for[dev] < smem) {
+            DECNET_CUDA(cudaFuncSetAttribute(conv2d_nhwc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) set_for[dev] = smem;
+        }
+    }
+    const int sms = sm_count_cached();
+    const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
+    conv2d_nhwc_halo_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+    return after_launch("conv2d_nhwc_halo_kernel");
+}
+
+}  // extern "C"

@@ -344,13 +344,32 @@ dynup_glue_kernel(const float *__restrict__ logits, const float *__restrict__ di
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 dynup_pack_nhwc_kernel(const float *__restrict__ disp, const float *__restrict__ Lf, float *__restrict__ out,
-                       int C, int h, int w, int CP, int TX, int round_tf32)
+                       int C, int h, int w, int CP, int TX, int round_tf32, int pad)
 {
+    // pad = 1: the output is [B, h+2, w+2, CP] with a zero border (decnet_conv2d_tf32_nhwc_halo's layout); blockIdx.y
+    // then runs over h+2 rows: the two border rows are zero-filled, interior rows get a zero pixel at both ends
+    if (pad) {
+        const int yp = blockIdx.y, bb = blockIdx.z, wp = w + 2;
+        float4 *row = reinterpret_cast<float4 *>(out + ((size_t)bb * (h + 2) + yp) * wp * CP);
+        const int cp4 = CP >> 2;
+        if (yp == 0 || yp == h + 1) {
+            // every tile zeroes its own span of the border row; tile 0 also the two end pixels
+            const int x0 = blockIdx.x * TX;
+            for (int i = threadIdx.x; i < min(TX, w - x0) * cp4; i += kBlock) row[(size_t)(x0 + 1) * cp4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (blockIdx.x == 0)
+                for (int i = threadIdx.x; i < 2 * cp4; i += kBlock)
+                    row[(i < cp4 ? 0 : (size_t)(wp - 1) * cp4) + (i % cp4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+        if (blockIdx.x == 0)
+            for (int i = threadIdx.x; i < 2 * cp4; i += kBlock)
+                row[(i < cp4 ? 0 : (size_t)(wp - 1) * cp4) + (i % cp4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // Block = TX coarse pixels of one row.  Phase 1: the 3C fine-row segments land in shared memory, one warp
     // per segment (coalesced).  Phase 2: channels-last float4 stores; the channel -> (segment, kx) mapping is a
     // per-block table, and the (pixel, channel) cursor advances by add/compare (no divisions per element).
     extern __shared__ float rows[];            // [C*3][3*TX] then int lut[CP]
-    const int x0 = blockIdx.x * TX, y = blockIdx.y, b = blockIdx.z;
+    const int x0 = blockIdx.x * TX, y = blockIdx.y - pad, b = blockIdx.z;
     const int nx = min(TX, w - x0);
     const int W3 = 3 * w, seg = 3 * TX;
     int *lut = reinterpret_cast<int *>(rows + (size_t)C * 3 * seg);
@@ -370,7 +389,7 @@ dynup_pack_nhwc_kernel(const float *__restrict__ disp, const float *__restrict__
         lut[ch] = v;
     }
     __syncthreads();
-    float4 *ob = reinterpret_cast<float4 *>(out + (((size_t)b * h + y) * w + x0) * CP);
+    float4 *ob = reinterpret_cast<float4 *>(out + (((size_t)b * (h + 2 * pad) + y + pad) * (w + 2 * pad) + x0 + pad) * CP);
     const float *db = disp + ((size_t)b * h + y) * w + x0;
     const int cp4 = CP >> 2, total4 = nx * cp4;
     int xl = threadIdx.x / cp4, c4 = threadIdx.x - xl * cp4;          // one division per thread
@@ -397,14 +416,14 @@ dynup_pack_nhwc_kernel(const float *__restrict__ disp, const float *__restrict__
 constexpr int kGluePx = 32;
 __global__ void __launch_bounds__(9 * kGluePx)
 dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict__ disp, float *__restrict__ out,
-                       int B, int h, int w, int NP)
+                       int B, int h, int w, int NP, int pad)
 {
     extern __shared__ __align__(16) float lg_s[];          // [32][NP + 1] (odd stride: conflict-free 9-float reads)
     const int x0 = blockIdx.x * kGluePx, y = blockIdx.y, b = blockIdx.z;
     const int nx = min(kGluePx, w - x0);
     const int stride = NP + 1;
     const size_t plane = (size_t)h * w;
-    const float *src = logits + (((size_t)b * h + y) * w + x0) * NP;
+    const float *src = logits + (((size_t)b * (h + 2 * pad) + y + pad) * (w + 2 * pad) + x0 + pad) * NP;   // pad: zero-bordered layout
     if ((NP & 3) == 0) {
         const float4 *s4 = reinterpret_cast<const float4 *>(src);
         const int np4 = NP >> 2;
@@ -812,7 +831,8 @@ int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, voi
 }
 
 int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out, int B, int C, int h, int w, int CP,
-                           int round_tf32, void *stream) {
+                           int round_tf32, int pad, void *stream) {
+    DECNET_REQUIRE(pad == 0 || pad == 1, "pad must be 0 or 1");
     DECNET_REQUIRE(disp && left_fea && out, "null pointer");
     DECNET_REQUIRE(B > 0 && B <= 65535 && C > 0 && h > 0 && h <= 65535 && w > 0, "bad size");
     DECNET_REQUIRE(CP >= 9 * C + 1, "CP=%d must hold 9*C+1=%d channels", CP, 9 * C + 1);
@@ -824,17 +844,20 @@ int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
     DECNET_REQUIRE(smem <= 200 * 1024, "C too large");
     if (smem > 48 * 1024)
         DECNET_CUDA(cudaFuncSetAttribute(dynup_pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dynup_pack_nhwc_kernel<<<dim3((w + TX - 1) / TX, h, B), kBlock, smem, (cudaStream_t)stream>>>(disp, left_fea, out, C, h, w, CP, TX, round_tf32);
+    DECNET_REQUIRE(h + 2 <= 65535, "too many rows");
+    dynup_pack_nhwc_kernel<<<dim3((w + TX - 1) / TX, h + 2 * pad, B), kBlock, smem, (cudaStream_t)stream>>>(disp, left_fea, out, C, h, w, CP, TX,
+                                                                                                        round_tf32, pad);
     return after_launch("dynup_pack_nhwc_kernel");
 }
 
-int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out, int B, int h, int w, int NP, void *stream) {
+int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out, int B, int h, int w, int NP, int pad, void *stream) {
+    DECNET_REQUIRE(pad == 0 || pad == 1, "pad must be 0 or 1");
     DECNET_REQUIRE(logits && disp && out, "null pointer");
     DECNET_REQUIRE(B > 0 && h > 0 && w > 0 && NP >= 81, "bad size");
     DECNET_REQUIRE(h <= 65535 && B <= 65535, "grid limit");
     const size_t smem = (size_t)kGluePx * (NP + 1) * sizeof(float);
     DECNET_REQUIRE(smem <= 48 * 1024, "NP too large");
-    dynup_glue_nhwc_kernel<<<dim3((w + kGluePx - 1) / kGluePx, h, B), 9 * kGluePx, smem, (cudaStream_t)stream>>>(logits, disp, out, B, h, w, NP);
+    dynup_glue_nhwc_kernel<<<dim3((w + kGluePx - 1) / kGluePx, h, B), 9 * kGluePx, smem, (cudaStream_t)stream>>>(logits, disp, out, B, h, w, NP, pad);
     return after_launch("dynup_glue_nhwc_kernel");
 }
 

@@ -389,10 +389,11 @@ class DynamicUpsampling(nn.Module):
             # TF32 allowed (PyTorch's default for convolutions): the three 81-channel convs run as tcgen05
             # implicit GEMMs on channels-last fp32, between channels-last pack / glue kernels
             cp0, packed = self._tf32_pack()
-            x = ops.dynup_pack_nhwc(disp_map, left_fea.contiguous(), cp0)
+            # the tensors carry a one-pixel zero border, so one TMA fill per row tap serves the three column taps
+            x = ops.dynup_pack_nhwc(disp_map, left_fea.contiguous(), cp0, pad=True)
             for i, (wp, bp, relu) in enumerate(packed):
-                x = ops.conv2d_tf32_nhwc(x, wp, bp, relu, round_out=i + 1 < len(packed))
-            return ops.dynup_glue_nhwc(x, disp_map)
+                x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=i + 1 < len(packed))
+            return ops.dynup_glue_nhwc(x, disp_map, pad=True)
         x = ops.dynup_pack(disp_map, left_fea.contiguous())
         logits = self.weight_learning(x)
         return ops.dynup_glue(logits.contiguous(), disp_map)

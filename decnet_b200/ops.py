@@ -588,24 +588,41 @@ def conv2d_tf32_rows_nchw_cat(srcs, w_compact, bias8, cout, dilation=1, relu=Fal
     return out
 
 
-def dynup_pack_nhwc(disp, left_fea, cp, round_tf32=True):
+def conv2d_tf32_nhwc_halo(x_pad, w_packed, bias, relu, round_out=False):
+    """x fp32 [B,h+2,w+2,cp] channels-last with a zero border -> fp32 [B,h+2,w+2,NP] (border zeros)."""
+    _chk("x_pad", x_pad)
+    B, hp, wp, cp = x_pad.shape
+    np_ = w_packed.shape[1]
+    out = torch.empty((B, hp, wp, np_), dtype=torch.float32, device=x_pad.device)
+    _call("decnet_conv2d_tf32_nhwc_halo", x_pad, x_pad.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(),
+          B, hp - 2, wp - 2, cp, np_, 1 if relu else 0, 1 if round_out else 0)
+    return out
+
+
+def dynup_pack_nhwc(disp, left_fea, cp, round_tf32=True, pad=False):
+    """pad=True: [B,h+2,w+2,cp] with a zero border (the layout conv2d_tf32_nhwc_halo chains on)."""
     _chk("disp", disp)
     B, h, w = disp.shape
     _chk("left_fea", left_fea, disp)
     Cc = left_fea.shape[1]
     if tuple(left_fea.shape) != (B, Cc, 3 * h, 3 * w):
         raise ValueError(f"left_fea {tuple(left_fea.shape)} is not 3x the disparity map {tuple(disp.shape)}")
-    out = torch.empty((B, h, w, int(cp)), dtype=torch.float32, device=disp.device)
+    k = 2 if pad else 0
+    out = torch.empty((B, h + k, w + k, int(cp)), dtype=torch.float32, device=disp.device)
     _call("decnet_dynup_pack_nhwc", disp, disp.data_ptr(), left_fea.data_ptr(), out.data_ptr(), B, Cc, h, w, int(cp),
-          1 if round_tf32 else 0)
+          1 if round_tf32 else 0, 1 if pad else 0)
     return out
 
 
-def dynup_glue_nhwc(logits_nhwc, disp):
+def dynup_glue_nhwc(logits_nhwc, disp, pad=False):
     _chk("disp", disp)
     B, h, w = disp.shape
     _chk("logits", logits_nhwc, disp)
+    k = 2 if pad else 0
+    if tuple(logits_nhwc.shape[:3]) != (B, h + k, w + k):
+        raise ValueError(f"logits {tuple(logits_nhwc.shape)} do not match disp {tuple(disp.shape)} (pad={pad})")
     NP = logits_nhwc.shape[-1]
     out = torch.empty((B, 3 * h, 3 * w), dtype=torch.float32, device=disp.device)
-    _call("decnet_dynup_glue_nhwc", disp, logits_nhwc.data_ptr(), disp.data_ptr(), out.data_ptr(), B, h, w, NP)
+    _call("decnet_dynup_glue_nhwc", disp, logits_nhwc.data_ptr(), disp.data_ptr(), out.data_ptr(), B, h, w, NP,
+          1 if pad else 0)
     return out

@@ -204,6 +204,13 @@ int decnet_conv2d_tf32_rows_nchw_cat(const float *const *srcs, const int *src_ch
                                      const float *bias8, float *out, int B, int Cout, int H, int W, int dilation,
                                      int relu, void *stream);
 
+/* The same TF32 convolution on channels-last tensors that carry a one-pixel ZERO border: x_pad fp32 [B,h+2,w+2,cp],
+ * out_pad fp32 [B,h+2,w+2,np] (border written as zeros, so layers chain without a padding pass).  One TMA fill per
+ * (row tap, 32-channel chunk) serves the three column taps through row-shifted UMMA descriptors
+ * (conv2d_nhwc_tcgen05.cu); weights / bias as for decnet_conv2d_tf32_nhwc. */
+int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                                 int B, int h, int w, int cp, int np, int relu, int round_out_tf32, void *stream);
+
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */
@@ -240,11 +247,12 @@ int decnet_dynup_glue(const float *logits, const float *disp, float *out,
                       int B, int h, int w, void *stream);
 
 /* Channels-last variants around decnet_conv2d_tf32_nhwc: pack writes [B,h,w,CP] (CP >= 9C+1, padding
- * channels zero), glue reads logits [B,h,w,NP] (NP >= 81, channel = sub*9+k). */
+ * channels zero), glue reads logits [B,h,w,NP] (NP >= 81, channel = sub*9+k).  pad = 1: both tensors are
+ * [B,h+2,w+2,.] with a one-pixel zero border (decnet_conv2d_tf32_nhwc_halo's layout; the pack writes the border). */
 int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
-                           int B, int C, int h, int w, int CP, int round_tf32, void *stream);
+                           int B, int C, int h, int w, int CP, int round_tf32, int pad, void *stream);
 int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out,
-                           int B, int h, int w, int NP, void *stream);
+                           int B, int h, int w, int NP, int pad, void *stream);
 
 /* Tail of GenerateSparseMask (modules/submodule.py:363-369) for BOTH views in one launch each:
  *   decnet_sqdiff_pair : out_i = (a_i - b_i)^2, i = 0 (left), 1 (right); n elements each

@@ -303,3 +303,30 @@ def test_fused_detail_tail_is_bit_exact_with_sigmoid_threshold():
     a, b = torch.randn(4, 3, 20, 24, device=dev), torch.randn(4, 3, 20, 24, device=dev)
     o0, o1 = ops.sqdiff_pair(a, b, b, a)
     assert torch.equal(o0, (a - b) ** 2) and torch.equal(o1, (b - a) ** 2)
+
+
+def test_dynup_padded_layout_and_halo_conv_match_the_unpadded_route():
+    """pad=True pack / glue (zero-bordered channels-last) and decnet_conv2d_tf32_nhwc_halo against the unpadded
+    kernels: the pack must equal F.pad of the unpadded pack bit for bit, the conv chain and the glue the same values."""
+    import torch.nn.functional as F
+    from decnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, C, h, w = 2, 8, 13, 37
+    disp = torch.rand(B, h, w, device="cuda", generator=g) * 30
+    Lf = torch.randn(B, C, 3 * h, 3 * w, device="cuda", generator=g)
+    cp = (9 * C + 1 + 7) // 8 * 8
+    a = ops.dynup_pack_nhwc(disp, Lf, cp)
+    b = ops.dynup_pack_nhwc(disp, Lf, cp, pad=True)
+    assert torch.equal(b, F.pad(a, (0, 0, 1, 1, 1, 1)))
+    wt = torch.randn(81, 9 * C + 1, 3, 3, device="cuda", generator=g) * 0.05
+    wp, bp, np_ = ops.pack_conv2d_tf32_weights(wt, torch.randn(81, device="cuda", generator=g) * 0.1, cp)
+    ya = ops.conv2d_tf32_nhwc(a, wp, bp, True)
+    yb = ops.conv2d_tf32_nhwc_halo(b, wp, bp, True)
+    assert float(yb[:, 0].abs().max()) == 0 and float(yb[:, :, -1].abs().max()) == 0
+    # same TF32 operands, fp32 accumulation in a different tap order
+    assert (yb[:, 1:-1, 1:-1] - ya).abs().max().item() <= 1e-5 * max(1.0, ya.abs().max().item())
+    yr = ops.conv2d_tf32_nhwc_halo(b, wp, bp, True, round_out=True)          # stored activations rounded to TF32 (nearest)
+    assert torch.equal(yr, ((yb.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32))
+    oa = ops.dynup_glue_nhwc(ya, disp)
+    ob = ops.dynup_glue_nhwc(F.pad(ya, (0, 0, 1, 1, 1, 1)).contiguous(), disp, pad=True)
+    assert torch.equal(oa, ob)
