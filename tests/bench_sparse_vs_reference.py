@@ -1,6 +1,7 @@
-"""Microbench of the sparse ops (BASELINE.json config 5): ours vs the reference kernels
+"""TEST INFRASTRUCTURE (lives under tests/ because it links the checker: oracle/_ref).
+Microbench of the sparse ops (BASELINE.json config 5): ours vs the reference kernels
 recompiled for sm_100a (oracle/_ref), per level / density.  CUDA-event timing, L2 flushed
-between iterations.  Usage: python scripts/bench_sparse.py [--B 8] [--iters 20]"""
+between iterations.  Usage: python tests/bench_sparse_vs_reference.py [--B 8] [--iters 20]"""
 import argparse
 import json
 import sys
