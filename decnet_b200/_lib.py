@@ -40,6 +40,8 @@ SIGNATURES = {
     "decnet_conv2d_tf32_rows_supported": (_i, [_i] * 5),
     "decnet_conv2d_tf32_rows_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv2d_tf32_nhwc_halo": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),
+    "decnet_nchw_cat_to_nhwc_pad": (_i, [C.c_void_p, C.c_void_p, _i, _f32p] + [_i] * 4 + [C.c_void_p]),
+    "decnet_nhwc_pad_to_nchw": (_i, [_f32p] * 2 + [_i] * 5 + [C.c_void_p]),
     "decnet_conv3d_debug_timing": (None, [C.c_void_p]),
     "decnet_conv3d_set_variant": (None, [_i]),
     "decnet_softargmin": (_i, [_f32p] * 2 + [_i] * 4 + [C.c_void_p]),

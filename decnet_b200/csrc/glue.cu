@@ -463,6 +463,49 @@ dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Layout bridges for the wide (72-channel) refinement layers of the 1/9 level, which run on the zero-bordered
+// channels-last TF32 kernel (conv2d_nhwc_tcgen05.cu):
+//   nchw_cat_to_nhwc_pad : cat of up to three NCHW sources -> [B, h+2, w+2, CP] (border and channel padding zero,
+//                          values rounded to TF32 like every operand of that kernel)
+//   nhwc_pad_to_nchw     : interior of [B, h+2, w+2, NP], first C channels -> NCHW [B, C, h, w]
+// The tensors are small (52 k pixels at SceneFlow size); one thread per output element.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+nchw_cat_to_nhwc_pad_kernel(const float *__restrict__ s0, const float *__restrict__ s1, const float *__restrict__ s2,
+                            int c0, int c1, int c2, float *__restrict__ out, int h, int w, int CP, long long n)
+{
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;      // over B*(h+2)*(w+2)*CP
+    if (i >= n) return;
+    const int c = (int)(i % CP);
+    long long p = i / CP;
+    const int xp = (int)(p % (w + 2)); p /= (w + 2);
+    const int yp = (int)(p % (h + 2));
+    const long long b = p / (h + 2);
+    float v = 0.f;
+    if (xp >= 1 && xp <= w && yp >= 1 && yp <= h && c < c0 + c1 + c2) {
+        const long long pix = (long long)(yp - 1) * w + (xp - 1), plane = (long long)h * w;
+        if (c < c0) v = __ldg(s0 + (b * c0 + c) * plane + pix);
+        else if (c < c0 + c1) v = __ldg(s1 + (b * c1 + (c - c0)) * plane + pix);
+        else v = __ldg(s2 + (b * c2 + (c - c0 - c1)) * plane + pix);
+        v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    }
+    out[i] = v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+nhwc_pad_to_nchw_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int NP, int h, int w, long long n)
+{
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;      // over B*C*h*w
+    if (i >= n) return;
+    const int x = (int)(i % w);
+    long long p = i / w;
+    const int y = (int)(p % h); p /= h;
+    const int c = (int)(p % C);
+    const long long b = p / C;
+    out[i] = __ldg(in + (((b * (h + 2) + y + 1) * (long long)(w + 2)) + x + 1) * NP + c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // a13 (input side): cat(Lf, dense, sparse, lmask, -var) -> [B, C+4, H, W]
 // (SparseDenseNetRefinementMask.py:197).  Flat copy, float4 where aligned.
 // ---------------------------------------------------------------------------------------------
@@ -757,6 +800,29 @@ int decnet_dynup_glue(const float *logits, const float *disp, float *out, int B,
     const long long n = (long long)B * h * w;
     dynup_glue_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(logits, disp, out, B, h, w);
     return after_launch("dynup_glue_kernel");
+}
+
+int decnet_nchw_cat_to_nhwc_pad(const float *const *srcs, const int *src_channels, int nsrc, float *out,
+                                int B, int h, int w, int CP, void *stream) {
+    DECNET_REQUIRE(srcs && src_channels && out, "null pointer");
+    DECNET_REQUIRE(nsrc >= 1 && nsrc <= 3 && B > 0 && h > 0 && w > 0, "bad size");
+    int c[3] = {0, 0, 0};
+    const float *s[3] = {nullptr, nullptr, nullptr};
+    int sum = 0;
+    for (int i = 0; i < nsrc; ++i) { DECNET_REQUIRE(srcs[i] && src_channels[i] > 0, "source %d", i); c[i] = src_channels[i]; s[i] = srcs[i]; sum += c[i]; }
+    DECNET_REQUIRE(CP >= sum, "CP=%d < %d channels", CP, sum);
+    const long long n = (long long)B * (h + 2) * (w + 2) * CP;
+    nchw_cat_to_nhwc_pad_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(s[0], s[1], s[2], c[0], c[1], c[2],
+                                                                                                     out, h, w, CP, n);
+    return after_launch("nchw_cat_to_nhwc_pad_kernel");
+}
+
+int decnet_nhwc_pad_to_nchw(const float *in_pad, float *out, int B, int C, int NP, int h, int w, void *stream) {
+    DECNET_REQUIRE(in_pad && out, "null pointer");
+    DECNET_REQUIRE(B > 0 && C > 0 && C <= NP && h > 0 && w > 0, "bad size");
+    const long long n = (long long)B * C * h * w;
+    nhwc_pad_to_nchw_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(in_pad, out, C, NP, h, w, n);
+    return after_launch("nhwc_pad_to_nchw_kernel");
 }
 
 int decnet_attn_pack(const float *left_fea, const float *dense, const float *sparse, const float *left_mask,

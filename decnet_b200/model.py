@@ -444,11 +444,39 @@ class Refinement(nn.Module):
         layers.append(Conv2dUnit(c // 2, 1, 3, padding=1, relu=False, bn=False))
         self.conv = nn.Sequential(*layers)
 
+    def _wide_pack(self, n_wide):
+        """Weights of the first `n_wide` layers for the zero-bordered channels-last TF32 kernel (cached)."""
+        if getattr(self, "_packed", None) is None:
+            units = list(self.conv)
+            cp = (units[0].conv.in_channels + 7) // 8 * 8
+            packed = []
+            for u in units[:n_wide]:
+                w, b = u.folded()
+                wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp)
+                packed.append((wp, bp, u.relu))
+                cp = np_
+            self._packed = ((units[0].conv.in_channels + 7) // 8 * 8, packed)
+        return self._packed
+
     def forward(self, left_fea, right_fea, disp_map):
         disp_map = disp_map.contiguous()
         units = list(self.conv)
         c0 = units[0].conv
         C = left_fea.shape[1]
+        if (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32 and C >= 48
+                and all(u.conv.dilation == (1, 1) for u in units[:4])):
+            # wide level (1/9: 145 -> 72 -> 72 -> 72 -> 36 channels): GEMM-sized layers, too wide for the resident-weight NCHW
+            # kernel -> zero-bordered channels-last TF32 kernel between two layout bridges, then back to NCHW for the rest
+            cp0, packed = self._wide_pack(4)
+            warped = ops.warp_bilinear(right_fea.contiguous(), disp_map)
+            x = ops.nchw_cat_to_nhwc_pad([left_fea.contiguous(), warped, disp_map], cp0)
+            for i, (wp, bp, relu) in enumerate(packed):
+                x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=i + 1 < len(packed))
+            x = ops.nhwc_pad_to_nchw(x, units[3].conv.out_channels)
+            for unit in units[4:-1]:
+                x = unit(x)
+            residual = self.conv[-1](x).squeeze(1)
+            return disp_map + residual, residual
         Wp = (left_fea.shape[3] + 3) // 4 * 4
         wv = None
         if (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32

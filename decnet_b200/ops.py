@@ -599,6 +599,35 @@ def conv2d_tf32_nhwc_halo(x_pad, w_packed, bias, relu, round_out=False):
     return out
 
 
+def nchw_cat_to_nhwc_pad(srcs, cp):
+    """cat(srcs, 1) (NCHW, single-channel maps as [B,H,W]) -> zero-bordered channels-last [B,H+2,W+2,cp], TF32-rounded."""
+    import ctypes
+    x0 = srcs[0]
+    _chk("srcs[0]", x0)
+    B, H, W = x0.shape[0], x0.shape[-2], x0.shape[-1]
+    chans = []
+    for i, t in enumerate(srcs):
+        _chk(f"srcs[{i}]", t, x0)
+        if (t.shape[0], t.shape[-2], t.shape[-1]) != (B, H, W):
+            raise ValueError(f"srcs[{i}] {tuple(t.shape)} does not match srcs[0] {tuple(x0.shape)}")
+        chans.append(1 if t.dim() == 3 else int(t.shape[1]))
+    n = len(srcs)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    cs = (ctypes.c_int * n)(*chans)
+    out = torch.empty((B, H + 2, W + 2, int(cp)), dtype=torch.float32, device=x0.device)
+    _call("decnet_nchw_cat_to_nhwc_pad", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
+          out.data_ptr(), B, H, W, int(cp))
+    return out
+
+
+def nhwc_pad_to_nchw(x_pad, channels):
+    _chk("x_pad", x_pad)
+    B, hp, wp, np_ = x_pad.shape
+    out = torch.empty((B, int(channels), hp - 2, wp - 2), dtype=torch.float32, device=x_pad.device)
+    _call("decnet_nhwc_pad_to_nchw", x_pad, x_pad.data_ptr(), out.data_ptr(), B, int(channels), np_, hp - 2, wp - 2)
+    return out
+
+
 def dynup_pack_nhwc(disp, left_fea, cp, round_tf32=True, pad=False):
     """pad=True: [B,h+2,w+2,cp] with a zero border (the layout conv2d_tf32_nhwc_halo chains on)."""
     _chk("disp", disp)

@@ -211,6 +211,13 @@ int decnet_conv2d_tf32_rows_nchw_cat(const float *const *srcs, const int *src_ch
 int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                  int B, int h, int w, int cp, int np, int relu, int round_out_tf32, void *stream);
 
+/* Layout bridges around decnet_conv2d_tf32_nhwc_halo for layers whose neighbours are NCHW (the 72-channel refinement
+ * layers of the 1/9 level): concatenation of up to three NCHW fp32 sources -> zero-bordered channels-last
+ * [B,h+2,w+2,CP] (TF32-rounded, channel padding zero), and back: interior / first C channels -> NCHW [B,C,h,w]. */
+int decnet_nchw_cat_to_nhwc_pad(const float *const *srcs, const int *src_channels, int nsrc, float *out,
+                                int B, int h, int w, int CP, void *stream);
+int decnet_nhwc_pad_to_nchw(const float *in_pad, float *out, int B, int C, int NP, int h, int w, void *stream);
+
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */

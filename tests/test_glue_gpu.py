@@ -330,3 +330,33 @@ def test_dynup_padded_layout_and_halo_conv_match_the_unpadded_route():
     oa = ops.dynup_glue_nhwc(ya, disp)
     ob = ops.dynup_glue_nhwc(F.pad(ya, (0, 0, 1, 1, 1, 1)).contiguous(), disp, pad=True)
     assert torch.equal(oa, ob)
+
+
+def test_layout_bridges_and_wide_refinement_route():
+    """nchw_cat_to_nhwc_pad / nhwc_pad_to_nchw are exact re-layouts (TF32 rounding on the way in), and the wide-level
+    refinement (72 channels: zero-bordered channels-last TF32 kernel for the first four layers) matches the fp32 route."""
+    import torch.nn.functional as F
+    from decnet_b200 import model as dm, ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, C, H, W = 2, 72, 20, 36
+    L = torch.randn(B, C, H, W, device="cuda", generator=g)
+    R = torch.randn(B, C, H, W, device="cuda", generator=g)
+    disp = torch.rand(B, H, W, device="cuda", generator=g) * 8
+    x = ops.nchw_cat_to_nhwc_pad([L, R, disp], 152)
+    cat = torch.cat([L, R, disp.unsqueeze(1)], 1)
+    want = F.pad(cat.permute(0, 2, 3, 1), (0, 152 - 145, 1, 1, 1, 1))
+    want = ((want.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(x, want)
+    back = ops.nhwc_pad_to_nchw(x, 145)
+    assert torch.equal(back, want[:, 1:-1, 1:-1, :145].permute(0, 3, 1, 2))
+    torch.manual_seed(3)
+    ref = dm.Refinement(C, stage_id=1).cuda().eval()
+    with torch.no_grad():
+        p1, r1 = ref(L, R, disp)
+        old = dm.USE_TF32_TCGEN05
+        try:
+            dm.USE_TF32_TCGEN05 = False
+            p0, r0 = ref(L, R, disp)
+        finally:
+            dm.USE_TF32_TCGEN05 = old
+    assert (r1 - r0).abs().max().item() <= 4e-3 * max(1.0, r0.abs().max().item())
