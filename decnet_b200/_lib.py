@@ -68,6 +68,8 @@ SIGNATURES = {
     "decnet_deconv3x3s3": (_i, [_f32p] * 4 + [_i] * 6 + [C.c_void_p]),
     "decnet_last_sparse_path": (_i, []),
     "decnet_set_sparse_path": (None, [_i]),
+    "decnet_last_sparse_variant": (_i, []),
+    "decnet_set_sparse_variant": (None, [_i]),
 }
 
 

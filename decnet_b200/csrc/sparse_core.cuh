@@ -77,24 +77,32 @@ __device__ __forceinline__ int pick_group_log2(int nL, int nR, int W, int D, int
     return best;
 }
 
-// (see compact_row_masks doc above)
+// Barrier of the threads that work on one row: the whole CTA (N == 0) or a named barrier `id` of N threads.
+template <int N> __device__ __forceinline__ void role_sync(int id) {
+    if (N == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
+}
+
+// (see compact_row_masks doc above)  SMEM_SRC: the mask rows were staged in shared memory (plain loads);
+// BAR_N / bar_id: the barrier of the `nthreads` threads running it (0 = __syncthreads); PRE: mask chunks per
+// thread loaded up front.
+template <bool SMEM_SRC = false, int BAR_N = 0, int PRE = 4>
 __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ lmask_row,
                                          const float *__restrict__ rmask_row,
                                          int W, int tid, int nthreads,
                                          int tile_bw = 0, int chunk_stride = 0, uint32_t bw_magic = 0,
-                                         int D = 0, int C = 0)
+                                         int D = 0, int C = 0, int bar_id = 0)
 {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int nch = (W + 31) >> 5;
     // all mask loads of this thread are issued before the first ballot (one memory round trip)
-    constexpr int PRE = 4;
     float lm[PRE], rm[PRE];
 #pragma unroll
     for (int it = 0; it < PRE; ++it) {
         const int w = ((warp + it * nwarps) << 5) + lane;
         const bool in = w < W;
-        lm[it] = in ? __ldg(lmask_row + w) : 0.f;
-        rm[it] = in ? __ldg(rmask_row + w) : 0.f;
+        lm[it] = in ? (SMEM_SRC ? lmask_row[w] : __ldg(lmask_row + w)) : 0.f;
+        rm[it] = in ? (SMEM_SRC ? rmask_row[w] : __ldg(rmask_row + w)) : 0.f;
     }
 #pragma unroll
     for (int it = 0; it < PRE; ++it) {
@@ -107,14 +115,14 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ l
     }
     for (int k = warp + PRE * nwarps; k < nch; k += nwarps) {
         const int w = (k << 5) + lane;
-        const bool lv = (w < W) && (__ldg(lmask_row + w) != 0.f);
-        const bool rv = (w < W) && (__ldg(rmask_row + w) != 0.f);
+        const bool lv = (w < W) && ((SMEM_SRC ? lmask_row[w] : __ldg(lmask_row + w)) != 0.f);
+        const bool rv = (w < W) && ((SMEM_SRC ? rmask_row[w] : __ldg(rmask_row + w)) != 0.f);
         const uint32_t lb = __ballot_sync(0xffffffffu, lv);
         const uint32_t rb = __ballot_sync(0xffffffffu, rv);
         if (lane == 0) { s.lbits[k] = lb; s.rbits[k] = rb; }
     }
     if (tid == 0) { s.lbits[nch] = 0u; s.rbits[nch] = 0u; }
-    __syncthreads();
+    role_sync<BAR_N>(bar_id);
     if (warp == 0) {
         int carryL = 0, carryR = 0;
         for (int base = 0; base < nch; base += 32) {
@@ -137,7 +145,7 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ l
             s.counts[2] = pick_group_log2(carryL, carryR, W, D, C, nthreads);
         }
     }
-    __syncthreads();
+    role_sync<BAR_N>(bar_id);
     for (int k = warp; k < nch; k += nwarps) {
         const int w = (k << 5) + lane;
         const uint32_t lb = s.lbits[k], rb = s.rbits[k];
@@ -151,7 +159,7 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ l
         if ((lb >> lane) & 1u) s.llist[s.loff[k] + __popc(lb & below)] = packed;
         if ((rb >> lane) & 1u) s.rlist[s.roff[k] + __popc(rb & below)] = packed;
     }
-    __syncthreads();
+    role_sync<BAR_N>(bar_id);
 }
 
 template <int G> __device__ __forceinline__ float gmax(float v) {

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "sparse_core.cuh"
 #include "tma_utils.cuh"
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -32,61 +33,56 @@ namespace decnet {
 namespace sparse {
 
 // -------------------------------------------------------------------------------------
-// Forward row kernel.  grid = B*H rows, block = kThreads, 3 CTAs/SM at the SceneFlow
-// shapes (62 KB of slabs + 8 KB of lists per CTA) so that while one CTA evaluates its row
-// two more have their slabs in flight.
+// Forward row kernel: a CTA walks rows  blockIdx.x, blockIdx.x + gridDim.x, ...
+//   <NT = 256, NB = 3>, grid = B*H : one row per CTA, 3 CTAs/SM (62 KB of slabs + 8 KB of lists per
+//                    CTA at the SceneFlow shapes), so that while one CTA evaluates its row two more
+//                    have their slabs in flight.
+//   <NT = 384, NB = 2>, grid = 2 * #SM : PERSISTENT.  Half an SM's shared memory per CTA leaves room
+//                    to compact BOTH operands of every realistic row, so the raw slabs are dead as
+//                    soon as the two gathers are done: the next row's slabs (and its two mask rows,
+//                    cp.async into a small staging buffer) are put in flight right there, BEFORE the
+//                    cost / softmax phase, which then runs entirely under the next row's load.
 //   USE_TMA = true : each operand's [C, W] slab arrives as ceil(W/256) TMA boxes
 //                    {bw, 1, C} of the 3-D view (W, H, B*C); one elected thread issues them
 //                    and the CTA waits on a single mbarrier (complete_tx::bytes).
 //   USE_TMA = false: cp.async (16 B when W % 4 == 0 and pointers are 16-B aligned, else
 //                    4 B) for shapes TMA cannot describe (e.g. KITTI's odd widths).
 // -------------------------------------------------------------------------------------
-template <int MODE, bool USE_TMA>
-__global__ void __launch_bounds__(kThreads, 3)
-sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
-                  const float *__restrict__ L, const float *__restrict__ R,
-                  const float *__restrict__ lmask, const float *__restrict__ rmask,
-                  const float *__restrict__ disp_in,
-                  float *__restrict__ out_a,   // MAT: out   VAR: var   FUSED: out
-                  float *__restrict__ out_b,   // FUSED: var, else unused
-                  float *__restrict__ sum_sim, float *__restrict__ max_cost,
-                  int C, int H, int W, int D, int vec_ok, int bw, int nchunks, int chunk_stride,
-                  uint32_t bw_magic, int rc_cap)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
-    const int tid = threadIdx.x;
-    const int h = blockIdx.x, b = blockIdx.y;
-    const int row = b * H + h;
-    const int Wp = (W + 3) & ~3;
-    const int Cp = (C + 3) & ~3;
-    unsigned char *base = reinterpret_cast<unsigned char *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    const int tile_floats = USE_TMA ? nchunks * chunk_stride : C * Wp;
-    float *Ls = reinterpret_cast<float *>(base);
-    float *Rs = Ls + tile_floats;
-    RowSmem s;
-    float *Rc = reinterpret_cast<float *>(carve_lists(s, reinterpret_cast<unsigned char *>(Rs + tile_floats), W));
+struct RowArgs {
+    const float *L, *R, *lmask, *rmask, *disp_in;
+    float *out_a;      // MAT: out   VAR: var   FUSED: out
+    float *out_b;      // FUSED: var, else unused
+    float *sum_sim, *max_cost;
+    int C, H, W, D, nrows;
+    int vec_ok, mvec_ok;              // 128-bit access allowed on features+outputs / on the mask rows
+    int bw, nchunks, chunk_stride;    // TMA box geometry
+    uint32_t bw_magic;
+    int rc_cap;                       // floats available for the compacted operands
+    int stage_masks;                  // masks go through the shared staging buffer (persistent mode)
+};
 
-    // 1. put the whole [C,W] slabs of both views in flight
+template <bool USE_TMA, int NT>
+__device__ __forceinline__ void issue_slabs(const CUtensorMap &tmL, const CUtensorMap &tmR, const RowArgs &a,
+                                            float *Ls, float *Rs, uint64_t *mbar, int row, int tid)
+{
+    const int b = row / a.H, h = row - b * a.H;
     if (USE_TMA) {
-        if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
-        __syncthreads();
         if (tid == 0) {
-            mbar_arrive_expect_tx(&mbar, (uint32_t)(2 * nchunks * C * bw * 4));
-            for (int ch = 0; ch < nchunks; ++ch) {
-                tma_load_3d(Ls + ch * chunk_stride, &tmL, ch * bw, h, b * C, &mbar);
-                tma_load_3d(Rs + ch * chunk_stride, &tmR, ch * bw, h, b * C, &mbar);
+            mbar_arrive_expect_tx(mbar, (uint32_t)(2 * a.nchunks * a.C * a.bw * 4));
+            for (int ch = 0; ch < a.nchunks; ++ch) {
+                tma_load_3d(Ls + ch * a.chunk_stride, &tmL, ch * a.bw, h, b * a.C, mbar);
+                tma_load_3d(Rs + ch * a.chunk_stride, &tmR, ch * a.bw, h, b * a.C, mbar);
             }
         }
     } else {
         const int lane = tid & 31, warp = tid >> 5;
-        const size_t plane = (size_t)H * W;
-        const float *Lrow = L + (size_t)b * C * plane + (size_t)h * W;
-        const float *Rrow = R + (size_t)b * C * plane + (size_t)h * W;
-        if (vec_ok) {
+        const int W = a.W, Wp = (W + 3) & ~3;
+        const size_t plane = (size_t)a.H * W;
+        const float *Lrow = a.L + (size_t)b * a.C * plane + (size_t)h * W;
+        const float *Rrow = a.R + (size_t)b * a.C * plane + (size_t)h * W;
+        if (a.vec_ok) {
             const int w4n = W >> 2;
-            for (int c = warp; c < C; c += kThreads / 32) {
+            for (int c = warp; c < a.C; c += NT / 32) {
                 const float *ls = Lrow + (size_t)c * plane, *rs = Rrow + (size_t)c * plane;
                 float *ld = Ls + c * Wp, *rd = Rs + c * Wp;
                 for (int w4 = lane; w4 < w4n; w4 += 32) {
@@ -95,47 +91,188 @@ sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
                 }
             }
         } else {
-            for (int c = warp; c < C; c += kThreads / 32) {
+            for (int c = warp; c < a.C; c += NT / 32) {
                 const float *ls = Lrow + (size_t)c * plane, *rs = Rrow + (size_t)c * plane;
                 float *ld = Ls + c * Wp, *rd = Rs + c * Wp;
                 for (int w = lane; w < W; w += 32) { cp_async_4(ld + w, ls + w); cp_async_4(rd + w, rs + w); }
             }
         }
-        cp_async_commit();
     }
+}
 
-    // 2. while they fly: compact both masks (mask loads first), zero the output rows
+// both mask rows of `row` -> Ms[0..Wp) (left), Ms[Wp..2Wp) (right)
+template <int NT>
+__device__ __forceinline__ void issue_masks(const RowArgs &a, float *Ms, int row, int tid)
+{
+    const int W = a.W, Wp = (W + 3) & ~3;
+    const float *lm = a.lmask + (size_t)row * W, *rm = a.rmask + (size_t)row * W;
+    if (a.mvec_ok) {
+        for (int w4 = tid; w4 < (W >> 2); w4 += NT) {
+            cp_async_16(Ms + 4 * w4, lm + 4 * w4);
+            cp_async_16(Ms + Wp + 4 * w4, rm + 4 * w4);
+        }
+    } else {
+        for (int w = tid; w < W; w += NT) { cp_async_4(Ms + w, lm + w); cp_async_4(Ms + Wp + w, rm + w); }
+    }
+}
+
+template <int MODE, bool USE_TMA, int NT, int NB>
+__global__ void __launch_bounds__(NT, NB)
+sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+                  const __grid_constant__ RowArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    const int tid = threadIdx.x;
+    const int C = a.C, W = a.W, D = a.D;
+    const int Wp = (W + 3) & ~3;
+    const int Cp = (C + 3) & ~3;
+    unsigned char *base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int tile_floats = USE_TMA ? a.nchunks * a.chunk_stride : C * Wp;
+    float *Ls = reinterpret_cast<float *>(base);
+    float *Rs = Ls + tile_floats;
+    RowSmem s;
+    float *Ms = reinterpret_cast<float *>(carve_lists(s, reinterpret_cast<unsigned char *>(Rs + tile_floats), W));
+    float *Rc = a.stage_masks ? Ms + 2 * Wp : Ms;
+    const int cs = USE_TMA ? a.bw : Wp;
+
+    if (USE_TMA) {
+        if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+        __syncthreads();
+    }
+    uint32_t parity = 0;
+    bool inflight = false;            // this row's slabs (and staged masks) were issued during the previous row
+
+    for (int row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+        const size_t m0 = (size_t)row * W;
+        // 1. put the whole [C,W] slabs of both views in flight (masks first: they are needed first)
+        if (!inflight) {
+            if (a.stage_masks) { issue_masks<NT>(a, Ms, row, tid); cp_async_commit(); }
+            issue_slabs<USE_TMA, NT>(tmL, tmR, a, Ls, Rs, &mbar, row, tid);
+            if (!USE_TMA) cp_async_commit();
+        }
+        // 2. while they fly: compact both masks, zero the output rows
+        if (a.stage_masks) {
+            if (USE_TMA) cp_async_wait_all();
+            else asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            __syncthreads();
+            compact_row_masks<true>(s, Ms, Ms + Wp, W, tid, NT, USE_TMA ? a.bw : 0, a.chunk_stride, a.bw_magic, D, C);
+        } else {
+            compact_row_masks<false>(s, a.lmask + m0, a.rmask + m0, W, tid, NT, USE_TMA ? a.bw : 0, a.chunk_stride,
+                                     a.bw_magic, D, C);
+        }
+        zero_rows(a.out_a + m0, a.sum_sim + m0, a.max_cost + m0, MODE == MODE_FUSED ? a.out_b + m0 : nullptr,
+                  W, a.vec_ok, tid, NT);
+        // The slabs must have landed before this CTA may retire or reuse the buffers, even when the
+        // row has no masked pixel and the zeros are already the answer.
+        if (USE_TMA) { if (tid == 0) mbar_wait(&mbar, parity); parity ^= 1u; }
+        else cp_async_wait_all();
+        __syncthreads();   // slabs visible to all; also orders the zero fill before the result stores
+        inflight = false;
+        const int nL = s.counts[0], nR = s.counts[1];
+        const int next = row + (int)gridDim.x;
+        if (nL != 0) {
+            // 3. costs / softmax regression / variance for every masked pixel, stored straight to global
+            const float *disp_row = MODE == MODE_VAR ? a.disp_in + m0 : nullptr;
+            if ((nR + nL) * Cp <= a.rc_cap) {
+                // both operands compacted: Rc[j][Cp] for the valid right columns, Lc[i][Cp] for the masked left pixels
+                float *Lc = Rc + nR * Cp;
+                gather_columns(s.rlist, nR, Rs, cs, C, Cp, Rc, tid, NT);
+                gather_columns(s.llist, nL, Ls, cs, C, Cp, Lc, tid, NT);
+                __syncthreads();
+                if (a.stage_masks && next < a.nrows) {
+                    // slabs and mask staging are dead: the next row loads under this row's arithmetic
+                    issue_masks<NT>(a, Ms, next, tid); cp_async_commit();
+                    if (USE_TMA && tid == 0) fence_proxy_async_smem();   // generic reads above -> async-proxy writes
+                    issue_slabs<USE_TMA, NT>(tmL, tmR, a, Ls, Rs, &mbar, next, tid);
+                    if (!USE_TMA) cp_async_commit();
+                    inflight = true;
+                }
+                process_row<MODE, 2>(s, Lc, Rc, cs, C, Cp, D, disp_row,
+                                     a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
+            } else if (nR * Cp <= a.rc_cap) {
+                gather_columns(s.rlist, nR, Rs, cs, C, Cp, Rc, tid, NT);
+                __syncthreads();
+                process_row<MODE, 1>(s, Ls, Rc, cs, C, Cp, D, disp_row,
+                                     a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
+            } else {
+                process_row<MODE, 0>(s, Ls, Rs, cs, C, Cp, D, disp_row,
+                                     a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
+            }
+        }
+        if (next < a.nrows) __syncthreads();   // lists / compacted operands / slabs are free for the next row
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// Sector-gather row kernel (variants 3 / 4): no slabs at all.
+// The row kernel above stages the whole [C,W] rows of both views although only the masked left pixels and
+// the valid right columns are ever read, and its 62 KB of slabs limit an SM to three rows in flight while a
+// row is a chain of short latency-bound phases.  Here the compacted operands Rc[j][Cp] / Lc[i][Cp] are
+// gathered STRAIGHT from global memory through the sorted column lists (neighbouring list entries share
+// 32-byte sectors; the read-only path coalesces them), so
+//   * DRAM traffic drops with the mask density (a sector is fetched only if one of its 8 columns is listed),
+//   * a CTA needs only its lists and the operand buffer: 5-8 rows per SM are in flight, which is what
+//     hides the per-row latency chain.
+// Rows whose operands do not fit the buffer (density above ~50 %) are evaluated from global memory directly.
+// -------------------------------------------------------------------------------------
+__device__ inline void gather_columns_global(const uint32_t *__restrict__ list, int n, const float *__restrict__ row,
+                                             size_t plane, int C, int Cp, float *__restrict__ dst, int tid, int nthreads)
+{
+    const int q4 = Cp >> 2;
+    const uint32_t magic = 0xffffffffu / (uint32_t)q4 + 1u;      // idx / q4, exact for idx < 2^16 * q4
+    const int total = n * q4;
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const int j = (q4 == 1) ? idx : (int)__umulhi((uint32_t)idx, magic);
+        const int q = idx - j * q4;
+        const int c = 4 * q;
+        const float *src = row + (size_t)c * plane + (list[j] & 0xffffu);
+        float4 v;
+        v.x = __ldg(src);
+        v.y = (c + 1 < C) ? __ldg(src + plane) : 0.f;
+        v.z = (c + 2 < C) ? __ldg(src + 2 * plane) : 0.f;
+        v.w = (c + 3 < C) ? __ldg(src + 3 * plane) : 0.f;
+        *reinterpret_cast<float4 *>(dst + j * Cp + c) = v;
+    }
+}
+
+template <int MODE, int NT, int NB>
+__global__ void __launch_bounds__(NT, NB)
+sparse_row_gather_kernel(const __grid_constant__ RowArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int C = a.C, W = a.W, D = a.D;
+    const int Cp = (C + 3) & ~3;
+    const int row = blockIdx.x;
+    const int b = row / a.H, h = row - b * a.H;
+    const size_t plane = (size_t)a.H * W;
     const size_t m0 = (size_t)row * W;
-    compact_row_masks(s, lmask + m0, rmask + m0, W, tid, kThreads, USE_TMA ? bw : 0, chunk_stride, bw_magic, D, C);
-    zero_rows(out_a + m0, sum_sim + m0, max_cost + m0, MODE == MODE_FUSED ? out_b + m0 : nullptr,
-              W, vec_ok, tid, kThreads);
-    // The slabs must have landed before this CTA may retire (its shared memory is recycled),
-    // even when the row has no masked pixel and the zeros are already the answer.
-    if (USE_TMA) { if (tid == 0) mbar_wait(&mbar, 0); }
-    else cp_async_wait_all();
-    __syncthreads();   // slabs visible to all; also orders the zero fill before the result stores
+    const float *Lrow = a.L + (size_t)b * C * plane + (size_t)h * W;
+    const float *Rrow = a.R + (size_t)b * C * plane + (size_t)h * W;
+    RowSmem s;
+    float *Rc = reinterpret_cast<float *>(carve_lists(s, smem_raw, W));
+
+    compact_row_masks<false, 0, (NT <= 128 ? 8 : 4)>(s, a.lmask + m0, a.rmask + m0, W, tid, NT, 0, 0, 0, D, C);
+    zero_rows(a.out_a + m0, a.sum_sim + m0, a.max_cost + m0, MODE == MODE_FUSED ? a.out_b + m0 : nullptr,
+              W, a.vec_ok, tid, NT);
     const int nL = s.counts[0], nR = s.counts[1];
     if (nL == 0) return;
-
-    // 3. costs / softmax regression / variance for every masked pixel, stored straight to global
-    const int cs = USE_TMA ? bw : Wp;
-    const float *disp_row = MODE == MODE_VAR ? disp_in + m0 : nullptr;
-    if ((nR + nL) * Cp <= rc_cap) {
-        // both operands compacted: Rc[j][Cp] for the valid right columns, Lc[i][Cp] for the masked left pixels
+    const float *disp_row = MODE == MODE_VAR ? a.disp_in + m0 : nullptr;
+    if ((nR + nL) * Cp <= a.rc_cap) {
         float *Lc = Rc + nR * Cp;
-        gather_columns(s.rlist, nR, Rs, cs, C, Cp, Rc, tid, kThreads);
-        gather_columns(s.llist, nL, Ls, cs, C, Cp, Lc, tid, kThreads);
-        __syncthreads();
-        process_row<MODE, 2>(s, Lc, Rc, cs, C, Cp, D, disp_row,
-                             out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
-    } else if (nR * Cp <= rc_cap) {
-        gather_columns(s.rlist, nR, Rs, cs, C, Cp, Rc, tid, kThreads);
-        __syncthreads();
-        process_row<MODE, 1>(s, Ls, Rc, cs, C, Cp, D, disp_row,
-                             out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+        gather_columns_global(s.rlist, nR, Rrow, plane, C, Cp, Rc, tid, NT);
+        gather_columns_global(s.llist, nL, Lrow, plane, C, Cp, Lc, tid, NT);
+        __syncthreads();   // operands complete; also orders the zero fill before the result stores
+        process_row<MODE, 2>(s, Lc, Rc, 0, C, Cp, D, disp_row,
+                             a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
     } else {
-        process_row<MODE, 0>(s, Ls, Rs, cs, C, Cp, D, disp_row,
-                             out_a + m0, out_b + m0, sum_sim + m0, max_cost + m0, tid, kThreads);
+        __syncthreads();
+        // list entries carry the column in both halves (tile_bw = 0), so the slab addressing of mode 0
+        // reads global memory with the plane as the channel stride
+        process_row<MODE, 0>(s, Lrow, Rrow, (int)plane, C, Cp, D, disp_row,
+                             a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
     }
 }
 
@@ -317,6 +454,8 @@ sparse_row_backward_kernel(const float *__restrict__ L, const float *__restrict_
 // -------------------------------------------------------------------------------------
 static thread_local int g_last_path = 0;
 static thread_local int g_forced_path = 0;
+static thread_local int g_last_variant = 0;
+static thread_local int g_forced_variant = 0;
 
 static int validate_common(const void *L, const void *R, const void *ml, const void *mr,
                            int B, int C, int H, int W)
@@ -330,12 +469,13 @@ static int validate_common(const void *L, const void *R, const void *ml, const v
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-struct TileGeom { int use_tma, bw, nchunks, chunk_stride, rc_cap; uint32_t bw_magic; size_t smem; };
+struct TileGeom { int use_tma, bw, nchunks, chunk_stride, rc_cap, persistent; uint32_t bw_magic; size_t smem; };
 
 // TMA needs 16-B aligned rows (W % 4 == 0, aligned bases), box dims <= 256 and tile offsets
 // that fit the 16-bit field of the packed column lists.  The leftover shared memory of the
-// chosen occupancy tier (3, 2 or 1 CTAs per SM) becomes the compacted right-column buffer.
-static TileGeom plan_tiles(const float *L, const float *R, int C, int W, bool allow_tma)
+// chosen occupancy tier becomes the buffer of the compacted operands: 3, 2 or 1 CTAs per SM for
+// the one-row-per-CTA launch, half an SM for the persistent one (which also stages the mask rows).
+static TileGeom plan_tiles(const float *L, const float *R, int C, int W, bool allow_tma, bool persistent)
 {
     TileGeom g{};
     const size_t Wp = (size_t)((W + 3) & ~3);
@@ -356,11 +496,18 @@ static TileGeom plan_tiles(const float *L, const float *R, int C, int W, bool al
         g.use_tma = 0; g.bw = 0; g.nchunks = 0; g.chunk_stride = 0; g.bw_magic = 0;
         fixed = 2 * (size_t)C * Wp * 4 + list_smem_bytes(W) + 128;
     }
-    const size_t want = Wp * Cp * 4;                      // every right column valid
+    const size_t want = 2 * Wp * Cp * 4;                  // every column of both views listed
     size_t budget = kMaxSmem;
-    for (int n = 3; n >= 1; --n) {
-        const size_t b = (size_t)(228 * 1024) / n - 1024 - 64;   // per-CTA share minus the reserved KB
-        if (fixed + 2048 <= b || n == 1) { budget = b < kMaxSmem ? b : kMaxSmem; break; }
+    const size_t half = (size_t)(228 * 1024) / 2 - 1024 - 64;
+    if (persistent && fixed + 2 * Wp * 4 + 2048 <= half) {
+        g.persistent = 1;
+        fixed += 2 * Wp * 4;                              // mask staging rows
+        budget = half;
+    } else {
+        for (int n = 3; n >= 1; --n) {
+            const size_t b = (size_t)(228 * 1024) / n - 1024 - 64;   // per-CTA share minus the reserved KB
+            if (fixed + 2048 <= b || n == 1) { budget = b < kMaxSmem ? b : kMaxSmem; break; }
+        }
     }
     size_t rc = budget > fixed ? budget - fixed : 0;
     if (rc > want) rc = want;
@@ -370,7 +517,47 @@ static TileGeom plan_tiles(const float *L, const float *R, int C, int W, bool al
     return g;
 }
 
-template <int MODE, bool USE_TMA>
+// Operand buffer of the sector-gather kernel: room for half of the row's columns of both views (32 KB at most).
+static size_t gather_smem(int C, int W, int &rc_cap)
+{
+    const size_t Wp = (size_t)((W + 3) & ~3);
+    const size_t Cp = (size_t)((C + 3) & ~3);
+    size_t cap = Wp * Cp * 4;
+    if (cap > 32 * 1024) cap = 32 * 1024;
+    cap &= ~(size_t)15;
+    rc_cap = (int)(cap / 4);
+    return list_smem_bytes(W) + cap;
+}
+
+template <int MODE, int NT, int NB>
+static int launch_gather(const float *L, const float *R, const float *ml, const float *mr,
+                         const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
+                         int B, int C, int H, int W, int D, cudaStream_t st)
+{
+    RowArgs a{};
+    const size_t smem = gather_smem(C, W, a.rc_cap);
+    auto kern = sparse_row_gather_kernel<MODE, NT, NB>;
+    {
+        static std::mutex mu;
+        static size_t set_for[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || set_for[dev] < smem) {
+            DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) set_for[dev] = smem;
+        }
+    }
+    a.L = L; a.R = R; a.lmask = ml; a.rmask = mr; a.disp_in = disp;
+    a.out_a = out_a; a.out_b = out_b; a.sum_sim = ssim; a.max_cost = mx;
+    a.C = C; a.H = H; a.W = W; a.D = D; a.nrows = B * H;
+    a.vec_ok = (W % 4 == 0) && aligned16(out_a) && aligned16(ssim) && aligned16(mx) &&
+               (MODE != MODE_FUSED || aligned16(out_b));
+    kern<<<a.nrows, NT, smem, st>>>(a);
+    return after_launch("sparse_row_gather_kernel");
+}
+
+template <int MODE, bool USE_TMA, int NT, int NB>
 static int launch_forward(const TileGeom &g, const float *L, const float *R, const float *ml, const float *mr,
                           const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
                           int B, int C, int H, int W, int D, cudaStream_t st)
@@ -388,7 +575,7 @@ static int launch_forward(const TileGeom &g, const float *L, const float *R, con
                                CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     }
-    auto kern = sparse_row_kernel<MODE, USE_TMA>;
+    auto kern = sparse_row_kernel<MODE, USE_TMA, NT, NB>;
     {   // once per (instantiation, device, size): the attribute call costs host time on every launch
         static std::mutex mu;
         static size_t set_for[64] = {0};
@@ -400,10 +587,18 @@ static int launch_forward(const TileGeom &g, const float *L, const float *R, con
             if (dev >= 0 && dev < 64) set_for[dev] = g.smem;
         }
     }
-    const int vec_ok = (W % 4 == 0) && aligned16(L) && aligned16(R) && aligned16(out_a) && aligned16(ssim) &&
-                       aligned16(mx) && (MODE != MODE_FUSED || aligned16(out_b));
-    kern<<<dim3(H, B), kThreads, g.smem, st>>>(tmL, tmR, L, R, ml, mr, disp, out_a, out_b, ssim, mx, C, H, W, D,
-                                               vec_ok, g.bw, g.nchunks, g.chunk_stride, g.bw_magic, g.rc_cap);
+    RowArgs a{};
+    a.L = L; a.R = R; a.lmask = ml; a.rmask = mr; a.disp_in = disp;
+    a.out_a = out_a; a.out_b = out_b; a.sum_sim = ssim; a.max_cost = mx;
+    a.C = C; a.H = H; a.W = W; a.D = D; a.nrows = B * H;
+    a.vec_ok = (W % 4 == 0) && aligned16(L) && aligned16(R) && aligned16(out_a) && aligned16(ssim) &&
+               aligned16(mx) && (MODE != MODE_FUSED || aligned16(out_b));
+    a.mvec_ok = (W % 4 == 0) && aligned16(ml) && aligned16(mr);
+    a.bw = g.bw; a.nchunks = g.nchunks; a.chunk_stride = g.chunk_stride; a.bw_magic = g.bw_magic;
+    a.rc_cap = g.rc_cap;
+    a.stage_masks = g.persistent;
+    const int grid = g.persistent ? std::min(a.nrows, NB * sm_count_cached()) : a.nrows;
+    kern<<<grid, NT, g.smem, st>>>(tmL, tmR, a);
     return after_launch("sparse_row_kernel");
 }
 
@@ -418,7 +613,21 @@ static int forward_dispatch(int mode, const float *L, const float *R, const floa
     DECNET_REQUIRE(mode != MODE_FUSED || out_b, "null variance output pointer");
     if (D < 0) D = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TileGeom g = plan_tiles(L, R, C, W, g_forced_path != 1);
+    // sector-gather kernel: any W / alignment; int indexing of the direct-from-global fallback needs C*H*W < 2^31
+    if ((g_forced_variant == 3 || g_forced_variant == 4) && g_forced_path == 0 && (long long)C * H * W < (1ll << 31)) {
+        g_last_path = 3; g_last_variant = g_forced_variant;
+#define DECNET_GATHER(M)                                                                                       \
+    (g_forced_variant == 3 ? launch_gather<M, 128, 6>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st) \
+                           : launch_gather<M, 256, 3>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st))
+        switch (mode) {
+            case MODE_MAT: return DECNET_GATHER(MODE_MAT);
+            case MODE_VAR: return DECNET_GATHER(MODE_VAR);
+            default:       return DECNET_GATHER(MODE_FUSED);
+        }
+#undef DECNET_GATHER
+    }
+    const bool persistent = g_forced_variant == 2;
+    TileGeom g = plan_tiles(L, R, C, W, g_forced_path != 1, persistent);
     if (g_forced_path == 2 && !g.use_tma) {
         set_error("TMA path forced but shape/alignment not eligible (W=%d)", W);
         return DECNET_ERR_UNSUPPORTED;
@@ -428,14 +637,17 @@ static int forward_dispatch(int mode, const float *L, const float *R, const floa
         return DECNET_ERR_UNSUPPORTED;
     }
     g_last_path = g.use_tma ? 2 : 1;
-#define DECNET_FWD(M)                                                                                         \
-    (g.use_tma ? launch_forward<M, true>(g, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st)     \
-               : launch_forward<M, false>(g, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st))
+    g_last_variant = g.persistent ? 2 : 1;
+#define DECNET_FWD2(M, T)                                                                                          \
+    (g.persistent ? launch_forward<M, T, 384, 2>(g, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st)  \
+                  : launch_forward<M, T, 256, 3>(g, L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st))
+#define DECNET_FWD(M) (g.use_tma ? DECNET_FWD2(M, true) : DECNET_FWD2(M, false))
     switch (mode) {
         case MODE_MAT: return DECNET_FWD(MODE_MAT);
         case MODE_VAR: return DECNET_FWD(MODE_VAR);
         default:       return DECNET_FWD(MODE_FUSED);
     }
+#undef DECNET_FWD2
 #undef DECNET_FWD
 }
 
@@ -512,5 +724,7 @@ int decnet_candidate_signature(const float *ml, const float *mr, int32_t *count,
 
 int decnet_last_sparse_path(void) { return g_last_path; }
 void decnet_set_sparse_path(int path) { g_forced_path = path; }
+int decnet_last_sparse_variant(void) { return g_last_variant; }
+void decnet_set_sparse_variant(int variant) { g_forced_variant = variant; }
 
 }  // extern "C"

@@ -108,11 +108,21 @@ int decnet_candidate_signature(const float *ref_mask, const float *tar_mask,
                                int32_t *count, uint64_t *hash,
                                int B, int H, int W, int max_disp, void *stream);
 
-/* Which row kernel the last spamat/spavar forward on this thread used:
- * 0 = none, 1 = cp.async row kernel (any W / alignment), 2 = TMA persistent kernel. */
+/* Which load path the last spamat/spavar forward on this thread used:
+ * 0 = none, 1 = rows staged by cp.async (any W / alignment), 2 = rows staged by TMA,
+ * 3 = no staging (sector-gather kernel). */
 int decnet_last_sparse_path(void);
-/* Force a path for the forward ops on this thread: 0 = auto, 1 = cp.async, 2 = TMA. */
+/* Force a staged path for the forward ops on this thread: 0 = auto, 1 = cp.async, 2 = TMA. */
 void decnet_set_sparse_path(int path);
+/* Launch shape of the forward row kernel:
+ *   1 = one row per CTA, [C,W] rows of both views staged in shared memory (3 CTAs/SM);
+ *   2 = the same with persistent CTAs (2 per SM) that put the next row's rows and masks in flight before
+ *       evaluating the current row;
+ *   3 / 4 = sector-gather kernel, 128 / 256 threads: only the listed columns are read, straight from global
+ *       memory into the compacted operand buffers (needs path 0).
+ * set: 0 = auto, else force; last: what the last forward used. */
+int decnet_last_sparse_variant(void);
+void decnet_set_sparse_variant(int variant);
 
 /* ------------------------------------------------------------------------- *
  * Coarse dense stage.

@@ -40,7 +40,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--rhos", type=float, nargs="+", default=[0.01, 0.03, 0.1, 0.3])
     ap.add_argument("--ref", type=int, default=1)
-    ap.add_argument("--paths", type=int, nargs="+", default=[1, 2])
+    ap.add_argument("--combos", type=lambda t: tuple(int(x) for x in t.split(",")), nargs="+",
+                    default=[(2, 1), (0, 3), (0, 4)], help="path,variant pairs")
     ap.add_argument("--levels", nargs="+", default=["s1", "s2", "s3"])
     args = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
@@ -59,17 +60,21 @@ def main():
             abytes = 4 * args.B * H * W * (2 * C + 2 + 4)
             rec = {"level": name, "C": C, "H": H, "W": W, "D": D, "B": args.B, "rho": rho,
                    "alg_MB_fused": abytes / 1e6}
-            for path in args.paths:
+            # (path, variant): 1/2 = staged rows by cp.async / TMA, variant 1 one row per CTA, 2 persistent with
+            # next-row prefetch; path 0 + variant 3 / 4 = sector-gather kernel with 128 / 256 threads
+            for path, variant in args.combos:
+                key = f"fused_p{path}v{variant}"
                 _lib.lib().decnet_set_sparse_path(path)
+                _lib.lib().decnet_set_sparse_variant(variant)
                 try:
                     ms = time_fn(lambda: ops.spamat_spavar_forward(L, R, ml, mr, D), args.iters, flush)
-                    rec[f"fused_path{path}_us"] = ms * 1e3
-                    rec[f"fused_path{path}_GBs"] = abytes / (ms * 1e-3) / 1e9
-                    rec[f"fused_path{path}_frac"] = abytes / (ms * 1e-3) / 1e9 / peak
+                    rec[f"{key}_us"] = round(ms * 1e3, 2)
+                    rec[f"{key}_frac"] = round(abytes / (ms * 1e-3) / 1e9 / peak, 4)
                 except _lib.DecnetError as e:
-                    rec[f"fused_path{path}_us"] = None
+                    rec[f"{key}_us"] = None
                 finally:
                     _lib.lib().decnet_set_sparse_path(0)
+                    _lib.lib().decnet_set_sparse_variant(0)
             if have_ref:
                 def ref_both():
                     o, _, _ = ref_cuda.spamat_forward(L, R, ml, mr, D, sync=False)

@@ -58,6 +58,24 @@ def test_sparse_properties_full_size(name, B, C, H, W, D):
         finally:
             _lib.lib().decnet_set_sparse_path(0)
         assert torch.equal(o1, out) and torch.equal(v1, var) and torch.equal(s1, ssim) and torch.equal(m1, mx)
+    # 8. the other launch shapes (persistent staged rows on both load paths, sector-gather kernel with 128 / 256
+    #    threads) agree: max_cost bit for bit (same FMA chain), the sums to rounding (lanes per pixel differ)
+    from decnet_b200 import _lib
+    combos = [(1, 2), (0, 3), (0, 4)] + ([(2, 2)] if W % 4 == 0 else [])
+    for path, variant in combos:
+        _lib.lib().decnet_set_sparse_path(path)
+        _lib.lib().decnet_set_sparse_variant(variant)
+        try:
+            o3, v3, s3, m3 = _fused(L, R, ml, mr, D)
+            # a shape whose staged rows leave no room for the mask staging falls back to one row per CTA
+            assert _lib.lib().decnet_last_sparse_variant() in (variant, 1 if variant == 2 else variant)
+        finally:
+            _lib.lib().decnet_set_sparse_path(0)
+            _lib.lib().decnet_set_sparse_variant(0)
+        assert torch.equal(m3, mx)
+        assert torch.allclose(o3, out, rtol=1e-6, atol=1e-5) and torch.allclose(s3, ssim, rtol=1e-6, atol=1e-7)
+        assert torch.allclose(v3, var, rtol=1e-5, atol=1e-4)
+        assert torch.equal(o3 == 0, out == 0)
 
 
 def test_sparse_translation_property():

@@ -17,15 +17,23 @@ def _cmp_forward(got, want, what):
             f"{what}: {k} max abs diff {(got[k].cpu() - want[k].cpu()).abs().max().item()}"
 
 
+# variants: 1 one row per CTA, 2 persistent with next-row prefetch (both staged: cp.async or TMA path),
+#           3 / 4 sector-gather kernel with 128 / 256 threads (no staging: path 3)
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("name,B,C,H,W,D", LEVEL_SHAPES)
 @pytest.mark.parametrize("rho", [0.03, 0.3, 1.0])
-def test_forward_vs_cpu_oracle(name, B, C, H, W, D, rho, path):
+def test_forward_vs_cpu_oracle(name, B, C, H, W, D, rho, path, variant):
     from decnet_b200 import ops, _lib
     from oracle import sparse as osp
     L, R = make_feats(B, C, H, W, device="cuda")
     ml, mr = make_masks(B, H, W, rho, rho, device="cuda")
+    if variant >= 3:
+        if path == 1:
+            pytest.skip("the sector-gather kernel has one load path")
+        path = 0
     _lib.lib().decnet_set_sparse_path(path)
+    _lib.lib().decnet_set_sparse_variant(variant)
     try:
         try:
             out, ssim, mx = ops.spamat_forward(L, R, ml, mr, D)
@@ -35,9 +43,11 @@ def test_forward_vs_cpu_oracle(name, B, C, H, W, D, rho, path):
             raise
         var, ssim_v, mx_v = ops.spavar_forward(L, R, ml, mr, out, D)
         f_out, f_var, f_ssim, f_mx = ops.spamat_spavar_forward(L, R, ml, mr, D)
-        assert _lib.lib().decnet_last_sparse_path() == path
+        assert _lib.lib().decnet_last_sparse_path() == (path if variant < 3 else 3)
+        assert _lib.lib().decnet_last_sparse_variant() == variant
     finally:
         _lib.lib().decnet_set_sparse_path(0)
+        _lib.lib().decnet_set_sparse_variant(0)
     o_out, o_ssim, o_mx = osp.spamat_forward(L, R, ml, mr, D)
     o_var, _, _ = osp.spavar_forward(L, R, ml, mr, o_out, D)
     want = {"out": o_out, "sum_sim": o_ssim, "max_cost": o_mx}
