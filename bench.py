@@ -482,14 +482,14 @@ def run_ours(args):
         t_k = e0.elapsed_time(e1) * 1e-3 / iters
         alg = 4.0 * Bc * Hc * Wc * (2 * Cc + 2 + 4)
         ach = alg / t_k / 1e9
-        roof = {"bound": "hbm", "kernel": "sparse_row_kernel<FUSED,TMA> (SpaMat+SpaVar, finest level)",
+        roof = {"bound": "hbm", "kernel": "sparse_row_gather_kernel<FUSED> (SpaMat+SpaVar, finest level)",
                 "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "traffic": None, "peak_source": pk["source"] + " (burst copy)", "algorithmic_bytes": alg,
                 "us_per_launch": t_k * 1e6, "mask_density": args.rho}
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists():
             try:
-                roof["traffic"] = json.loads(tr.read_text()).get("sparse_row_kernel_bytes_per_launch")
+                roof["traffic"] = json.loads(tr.read_text()).get("sparse_row_gather_kernel_bytes_per_launch")
             except Exception:
                 pass
         # the thin 3x3 Conv2d layers (conv2d_tcgen05_kernel, 31 % of the step): the 8->8 layer at the finest level,

@@ -206,15 +206,16 @@ sparse_row_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
 }
 
 // -------------------------------------------------------------------------------------
-// Sector-gather row kernel (variants 3 / 4): no slabs at all.
+// Sector-gather row kernel (variant 3, the default): no slabs at all.
 // The row kernel above stages the whole [C,W] rows of both views although only the masked left pixels and
 // the valid right columns are ever read, and its 62 KB of slabs limit an SM to three rows in flight while a
 // row is a chain of short latency-bound phases.  Here the compacted operands Rc[j][Cp] / Lc[i][Cp] are
 // gathered STRAIGHT from global memory through the sorted column lists (neighbouring list entries share
 // 32-byte sectors; the read-only path coalesces them), so
 //   * DRAM traffic drops with the mask density (a sector is fetched only if one of its 8 columns is listed),
-//   * a CTA needs only its lists and the operand buffer: 5-8 rows per SM are in flight, which is what
-//     hides the per-row latency chain.
+//   * a CTA needs only its lists and the operand buffer: four CTAs of 256 threads per SM (64 registers) instead
+//     of three, which is what hides the per-row latency chain (measured: 128-thread CTAs, 6 or 8 per SM, lose
+//     more in the cost phase -- one lane per pixel -- than they gain).
 // Rows whose operands do not fit the buffer (density above ~50 %) are evaluated from global memory directly.
 // -------------------------------------------------------------------------------------
 __device__ inline void gather_columns_global(const uint32_t *__restrict__ list, int n, const float *__restrict__ row,
@@ -273,6 +274,108 @@ sparse_row_gather_kernel(const __grid_constant__ RowArgs a)
         // reads global memory with the plane as the channel stride
         process_row<MODE, 0>(s, Lrow, Rrow, (int)plane, C, Cp, D, disp_row,
                              a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// Software-pipelined sector-gather kernel (variant 4, opt-in: measured slower than one row per CTA).
+// Same operands as sparse_row_gather_kernel, but a persistent CTA walks its rows with every global read one
+// row ahead of its use, all of them cp.async so no thread ever waits for the data it has just asked for:
+//   iteration k:  wait(gathers of row k, masks of row k+1)            <- issued one cost phase ago
+//                 compact row k+1 from the staged masks, zero its output rows,
+//                 cp.async-gather its operands into the OTHER list/operand buffer,
+//                 cp.async the masks of row k+2,
+//                 costs / softmax regression / variance of row k       <- runs under all of the above loads
+// Rows whose operands do not fit a buffer are evaluated from global memory directly (mode 0).
+// -------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 256;
+
+// 4-byte cp.async gather of the listed columns: warp = channel, lane = list entry (sorted columns: neighbouring
+// lanes share sectors)
+__device__ __forceinline__ void gather_columns_async(const uint32_t *__restrict__ list, int n,
+                                                     const float *__restrict__ row, size_t plane, int C, int Cp,
+                                                     float *__restrict__ dst, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int j = lane; j < n; j += 32) {
+        const float *src = row + (list[j] & 0xffffu);
+        float *d = dst + j * Cp;
+        for (int c = warp; c < C; c += kStreamThreads / 32) cp_async_4(d + c, src + (size_t)c * plane);
+    }
+}
+
+template <int MODE, int NB>
+__global__ void __launch_bounds__(kStreamThreads, NB)
+sparse_row_stream_kernel(const __grid_constant__ RowArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = kStreamThreads;
+    const int tid = threadIdx.x;
+    const int C = a.C, W = a.W, D = a.D, H = a.H;
+    const int Wp = (W + 3) & ~3;
+    const int Cp = (C + 3) & ~3;
+    const size_t plane = (size_t)H * W;
+    const size_t list_bytes = list_smem_bytes(W);
+    float *Ms = reinterpret_cast<float *>(smem_raw);                      // staged mask rows [2][Wp]
+    unsigned char *lists0 = reinterpret_cast<unsigned char *>(Ms + 2 * Wp);
+    float *ob0 = reinterpret_cast<float *>(lists0 + 2 * list_bytes);      // operand buffers [2][rc_cap]
+    const int nmine = (a.nrows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int stride = (int)gridDim.x;
+
+    // compaction + zero fill + operand gather of the CTA's k-th row into buffer k & 1 (masks already staged)
+    auto front = [&](int k) {
+        const int row = (int)blockIdx.x + k * stride;
+        const int b = row / H, h = row - b * H;
+        const size_t m0 = (size_t)row * W;
+        RowSmem s;
+        carve_lists(s, lists0 + (k & 1) * list_bytes, W);
+        float *Rc = ob0 + (size_t)(k & 1) * a.rc_cap;
+        compact_row_masks<true>(s, Ms, Ms + Wp, W, tid, NT, 0, 0, 0, D, C);
+        zero_rows(a.out_a + m0, a.sum_sim + m0, a.max_cost + m0, MODE == MODE_FUSED ? a.out_b + m0 : nullptr,
+                  W, a.vec_ok, tid, NT);
+        const int nL = s.counts[0], nR = s.counts[1];
+        if (nL != 0 && (nR + nL) * Cp <= a.rc_cap) {
+            const float *Lrow = a.L + (size_t)b * C * plane + (size_t)h * W;
+            const float *Rrow = a.R + (size_t)b * C * plane + (size_t)h * W;
+            gather_columns_async(s.rlist, nR, Rrow, plane, C, Cp, Rc, tid);
+            gather_columns_async(s.llist, nL, Lrow, plane, C, Cp, Rc + nR * Cp, tid);
+        }
+        cp_async_commit();
+    };
+
+    if (nmine <= 0) return;
+    issue_masks<NT>(a, Ms, (int)blockIdx.x, tid);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    front(0);
+    if (nmine > 1) { issue_masks<NT>(a, Ms, (int)blockIdx.x + stride, tid); cp_async_commit(); }
+
+    for (int k = 0; k < nmine; ++k) {
+        cp_async_wait_all();
+        __syncthreads();          // operands of row k and masks of row k+1 landed; everyone is done with row k-1
+        if (k + 1 < nmine) {
+            front(k + 1);         // its barriers also order the reads of the mask staging before the refill below
+            if (k + 2 < nmine) { issue_masks<NT>(a, Ms, (int)blockIdx.x + (k + 2) * stride, tid); cp_async_commit(); }
+        }
+        const int row = (int)blockIdx.x + k * stride;
+        const size_t m0 = (size_t)row * W;
+        RowSmem s;
+        carve_lists(s, lists0 + (k & 1) * list_bytes, W);
+        const int nL = s.counts[0], nR = s.counts[1];
+        if (nL == 0) continue;
+        const float *disp_row = MODE == MODE_VAR ? a.disp_in + m0 : nullptr;
+        if ((nR + nL) * Cp <= a.rc_cap) {
+            const float *Rc = ob0 + (size_t)(k & 1) * a.rc_cap;
+            process_row<MODE, 2>(s, Rc + nR * Cp, Rc, 0, C, Cp, D, disp_row,
+                                 a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
+        } else {
+            const int b = row / H, h = row - b * H;
+            const float *Lrow = a.L + (size_t)b * C * plane + (size_t)h * W;
+            const float *Rrow = a.R + (size_t)b * C * plane + (size_t)h * W;
+            process_row<MODE, 0>(s, Lrow, Rrow, (int)plane, C, Cp, D, disp_row,
+                                 a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
+        }
     }
 }
 
@@ -517,16 +620,20 @@ static TileGeom plan_tiles(const float *L, const float *R, int C, int W, bool al
     return g;
 }
 
-// Operand buffer of the sector-gather kernel: room for half of the row's columns of both views (32 KB at most).
-static size_t gather_smem(int C, int W, int &rc_cap)
+// Operand buffer of the sector-gather kernel: what the CTA's share of the SM leaves after the lists, at most
+// half of the row's columns of both views and 32 KB.
+static size_t gather_smem(int C, int W, int nb, int &rc_cap)
 {
     const size_t Wp = (size_t)((W + 3) & ~3);
     const size_t Cp = (size_t)((C + 3) & ~3);
+    const size_t lists = list_smem_bytes(W);
     size_t cap = Wp * Cp * 4;
     if (cap > 32 * 1024) cap = 32 * 1024;
+    const size_t share = (size_t)(228 * 1024) / nb - 1280;
+    if (lists + cap > share) cap = share > lists + 4096 ? share - lists : 4096;
     cap &= ~(size_t)15;
     rc_cap = (int)(cap / 4);
-    return list_smem_bytes(W) + cap;
+    return lists + cap;
 }
 
 template <int MODE, int NT, int NB>
@@ -535,7 +642,7 @@ static int launch_gather(const float *L, const float *R, const float *ml, const 
                          int B, int C, int H, int W, int D, cudaStream_t st)
 {
     RowArgs a{};
-    const size_t smem = gather_smem(C, W, a.rc_cap);
+    const size_t smem = gather_smem(C, W, NB, a.rc_cap);
     auto kern = sparse_row_gather_kernel<MODE, NT, NB>;
     {
         static std::mutex mu;
@@ -555,6 +662,50 @@ static int launch_gather(const float *L, const float *R, const float *ml, const 
                (MODE != MODE_FUSED || aligned16(out_b));
     kern<<<a.nrows, NT, smem, st>>>(a);
     return after_launch("sparse_row_gather_kernel");
+}
+
+// Shared memory of the pipelined kernel: mask staging + two list sets + two operand buffers in a 1/NB share of the SM.
+static size_t stream_smem(int C, int W, int nb, int &rc_cap)
+{
+    const size_t Wp = (size_t)((W + 3) & ~3);
+    const size_t Cp = (size_t)((C + 3) & ~3);
+    const size_t fixed = 2 * Wp * 4 + 2 * list_smem_bytes(W);
+    const size_t share = (size_t)(228 * 1024) / nb - 1280;
+    size_t cap = Wp * Cp * 4;                              // half of the row's columns of both views
+    if (fixed + 2 * cap > share) cap = share > fixed + 2 * 2048 ? (share - fixed) / 2 : 2048;
+    cap &= ~(size_t)15;
+    rc_cap = (int)(cap / 4);
+    return fixed + 2 * cap;
+}
+
+template <int MODE, int NB>
+static int launch_stream(const float *L, const float *R, const float *ml, const float *mr,
+                         const float *disp, float *out_a, float *out_b, float *ssim, float *mx,
+                         int B, int C, int H, int W, int D, cudaStream_t st)
+{
+    RowArgs a{};
+    const size_t smem = stream_smem(C, W, NB, a.rc_cap);
+    auto kern = sparse_row_stream_kernel<MODE, NB>;
+    {
+        static std::mutex mu;
+        static size_t set_for[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || set_for[dev] < smem) {
+            DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) set_for[dev] = smem;
+        }
+    }
+    a.L = L; a.R = R; a.lmask = ml; a.rmask = mr; a.disp_in = disp;
+    a.out_a = out_a; a.out_b = out_b; a.sum_sim = ssim; a.max_cost = mx;
+    a.C = C; a.H = H; a.W = W; a.D = D; a.nrows = B * H;
+    a.vec_ok = (W % 4 == 0) && aligned16(out_a) && aligned16(ssim) && aligned16(mx) &&
+               (MODE != MODE_FUSED || aligned16(out_b));
+    a.mvec_ok = (W % 4 == 0) && aligned16(ml) && aligned16(mr);
+    const int grid = std::min(a.nrows, NB * sm_count_cached());
+    kern<<<grid, kStreamThreads, smem, st>>>(a);
+    return after_launch("sparse_row_stream_kernel");
 }
 
 template <int MODE, bool USE_TMA, int NT, int NB>
@@ -613,12 +764,16 @@ static int forward_dispatch(int mode, const float *L, const float *R, const floa
     DECNET_REQUIRE(mode != MODE_FUSED || out_b, "null variance output pointer");
     if (D < 0) D = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // sector-gather kernel: any W / alignment; int indexing of the direct-from-global fallback needs C*H*W < 2^31
-    if ((g_forced_variant == 3 || g_forced_variant == 4) && g_forced_path == 0 && (long long)C * H * W < (1ll << 31)) {
-        g_last_path = 3; g_last_variant = g_forced_variant;
-#define DECNET_GATHER(M)                                                                                       \
-    (g_forced_variant == 3 ? launch_gather<M, 128, 6>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st) \
-                           : launch_gather<M, 256, 3>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st))
+    // Default: the sector-gather kernel (any W / alignment; the int indexing of its direct-from-global fallback
+    // needs C*H*W < 2^31).  Variant 4 is its software-pipelined persistent form (measured slower, opt-in);
+    // forcing a staged load path or variant 1 / 2 selects the staged row kernel.
+    if ((g_forced_variant == 0 || g_forced_variant == 3 || g_forced_variant == 4) && g_forced_path == 0 &&
+        (long long)C * H * W < (1ll << 31)) {
+        const int v = g_forced_variant == 4 ? 4 : 3;
+        g_last_path = 3; g_last_variant = v;
+#define DECNET_GATHER(M)                                                                                    \
+    (v == 3 ? launch_gather<M, 256, 4>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st)       \
+            : launch_stream<M, 3>(L, R, ml, mr, disp, out_a, out_b, ssim, mx, B, C, H, W, D, st))
         switch (mode) {
             case MODE_MAT: return DECNET_GATHER(MODE_MAT);
             case MODE_VAR: return DECNET_GATHER(MODE_VAR);

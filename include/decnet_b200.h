@@ -114,13 +114,14 @@ int decnet_candidate_signature(const float *ref_mask, const float *tar_mask,
 int decnet_last_sparse_path(void);
 /* Force a staged path for the forward ops on this thread: 0 = auto, 1 = cp.async, 2 = TMA. */
 void decnet_set_sparse_path(int path);
-/* Launch shape of the forward row kernel:
- *   1 = one row per CTA, [C,W] rows of both views staged in shared memory (3 CTAs/SM);
+/* Forward row kernel:
+ *   3 = sector-gather kernel (default): only the listed columns are read, straight from global memory into the
+ *       compacted operand buffers; one row per CTA, 256 threads, 4 CTAs/SM; any W / alignment (needs path 0);
+ *   4 = its software-pipelined form: persistent CTAs, every read issued one row ahead with cp.async;
+ *   1 = one row per CTA with the [C,W] rows of both views staged in shared memory (3 CTAs/SM);
  *   2 = the same with persistent CTAs (2 per SM) that put the next row's rows and masks in flight before
- *       evaluating the current row;
- *   3 / 4 = sector-gather kernel, 128 / 256 threads: only the listed columns are read, straight from global
- *       memory into the compacted operand buffers (needs path 0).
- * set: 0 = auto, else force; last: what the last forward used. */
+ *       evaluating the current row.
+ * set: 0 = auto (3; 1 when a staged path is forced or C*H*W >= 2^31), else force; last: what the last forward used. */
 int decnet_last_sparse_variant(void);
 void decnet_set_sparse_variant(int variant);
 

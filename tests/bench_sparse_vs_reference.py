@@ -41,7 +41,7 @@ def main():
     ap.add_argument("--rhos", type=float, nargs="+", default=[0.01, 0.03, 0.1, 0.3])
     ap.add_argument("--ref", type=int, default=1)
     ap.add_argument("--combos", type=lambda t: tuple(int(x) for x in t.split(",")), nargs="+",
-                    default=[(2, 1), (0, 3), (0, 4)], help="path,variant pairs")
+                    default=[(2, 1), (2, 2), (0, 3), (0, 4)], help="path,variant pairs")
     ap.add_argument("--levels", nargs="+", default=["s1", "s2", "s3"])
     args = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
@@ -61,7 +61,7 @@ def main():
             rec = {"level": name, "C": C, "H": H, "W": W, "D": D, "B": args.B, "rho": rho,
                    "alg_MB_fused": abytes / 1e6}
             # (path, variant): 1/2 = staged rows by cp.async / TMA, variant 1 one row per CTA, 2 persistent with
-            # next-row prefetch; path 0 + variant 3 / 4 = sector-gather kernel with 128 / 256 threads
+            # next-row prefetch; path 0 + variant 3 = sector-gather kernel, 4 = its software-pipelined form
             for path, variant in args.combos:
                 key = f"fused_p{path}v{variant}"
                 _lib.lib().decnet_set_sparse_path(path)

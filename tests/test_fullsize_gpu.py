@@ -49,19 +49,22 @@ def test_sparse_properties_full_size(name, B, C, H, W, D):
     has = m & (cnt > 0)
     assert torch.allclose(mz[has], torch.full_like(mz[has], 1e-6))
     assert torch.allclose(sz[has], cnt[has].float() * torch.exp(torch.tensor(-1e-6)).item() + 1e-6, rtol=1e-5)
-    # 7. TMA path and cp.async path agree exactly where both apply
+    # 7. the two staged load paths (TMA, cp.async) agree exactly where both apply
     if W % 4 == 0:
         from decnet_b200 import _lib
-        _lib.lib().decnet_set_sparse_path(1)
-        try:
-            o1, v1, s1, m1 = _fused(L, R, ml, mr, D)
-        finally:
-            _lib.lib().decnet_set_sparse_path(0)
-        assert torch.equal(o1, out) and torch.equal(v1, var) and torch.equal(s1, ssim) and torch.equal(m1, mx)
-    # 8. the other launch shapes (persistent staged rows on both load paths, sector-gather kernel with 128 / 256
-    #    threads) agree: max_cost bit for bit (same FMA chain), the sums to rounding (lanes per pixel differ)
+        res = []
+        for path in (1, 2):
+            _lib.lib().decnet_set_sparse_path(path)
+            try:
+                res.append(_fused(L, R, ml, mr, D))
+            finally:
+                _lib.lib().decnet_set_sparse_path(0)
+        for x, y in zip(*res):
+            assert torch.equal(x, y)
+    # 8. every forward kernel (staged rows: one row per CTA / persistent, both load paths; sector-gather: one row
+    #    per CTA / software-pipelined) agrees with the default: max_cost bit for bit (same FMA chain), the sums to rounding (lanes per pixel differ)
     from decnet_b200 import _lib
-    combos = [(1, 2), (0, 3), (0, 4)] + ([(2, 2)] if W % 4 == 0 else [])
+    combos = [(1, 1), (1, 2), (0, 3), (0, 4)] + ([(2, 1), (2, 2)] if W % 4 == 0 else [])
     for path, variant in combos:
         _lib.lib().decnet_set_sparse_path(path)
         _lib.lib().decnet_set_sparse_variant(variant)

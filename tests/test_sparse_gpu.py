@@ -18,7 +18,7 @@ def _cmp_forward(got, want, what):
 
 
 # variants: 1 one row per CTA, 2 persistent with next-row prefetch (both staged: cp.async or TMA path),
-#           3 / 4 sector-gather kernel with 128 / 256 threads (no staging: path 3)
+#           3 sector-gather kernel (the default), 4 its software-pipelined persistent form (no staging: path 3)
 @pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("name,B,C,H,W,D", LEVEL_SHAPES)
