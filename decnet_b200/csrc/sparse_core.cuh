@@ -131,12 +131,17 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ l
     }
     if (tid == 0) { s.lbits[nch] = 0u; s.rbits[nch] = 0u; }
     role_sync<BAR_N>(bar_id);
-    if (warp == 0) {
+    // Every warp scans the chunk counts itself (32 chunks per step: five shuffles) and takes the offsets of ITS
+    // chunks from its own registers, so no barrier separates the scan from the list build and no warp waits
+    // for a scanning warp; warp 0 also publishes the offsets that row_prefix() reads later.
+    {
         int carryL = 0, carryR = 0;
+        const uint32_t below = (1u << lane) - 1u;
         for (int base = 0; base < nch; base += 32) {
-            const int k = base + lane;
-            const int cl = (k < nch) ? __popc(s.lbits[k]) : 0;
-            const int cr = (k < nch) ? __popc(s.rbits[k]) : 0;
+            const int kk = base + lane;
+            const uint32_t lbv = (kk < nch) ? s.lbits[kk] : 0u;
+            const uint32_t rbv = (kk < nch) ? s.rbits[kk] : 0u;
+            const int cl = __popc(lbv), cr = __popc(rbv);
             int il = cl, ir = cr;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -144,29 +149,33 @@ __device__ inline void compact_row_masks(RowSmem &s, const float *__restrict__ l
                 const int tr = __shfl_up_sync(0xffffffffu, ir, o);
                 if (lane >= o) { il += tl; ir += tr; }
             }
-            if (k < nch) { s.loff[k] = carryL + il - cl; s.roff[k] = carryR + ir - cr; }
+            const int exL = carryL + il - cl, exR = carryR + ir - cr;
+            if (warp == 0 && kk < nch) { s.loff[kk] = exL; s.roff[kk] = exR; }
+            const int kend = min(base + 32, nch);
+            for (int k = base + warp; k < kend; k += nwarps) {           // warp-uniform bounds
+                const int src = k - base;
+                const uint32_t lb = __shfl_sync(0xffffffffu, lbv, src), rb = __shfl_sync(0xffffffffu, rbv, src);
+                const int oL = __shfl_sync(0xffffffffu, exL, src), oR = __shfl_sync(0xffffffffu, exR, src);
+                const int w = (k << 5) + lane;
+                uint32_t off = (uint32_t)w;
+                if (tile_bw > 0) {
+                    const int ch = (int)__umulhi((uint32_t)w, bw_magic);     // w / tile_bw (exact for w < 2^16)
+                    off = (uint32_t)(ch * chunk_stride + (w - ch * tile_bw));
+                }
+                const uint32_t packed = (off << 16) | (uint32_t)w;
+                if ((lb >> lane) & 1u) s.llist[oL + __popc(lb & below)] = packed;
+                if ((rb >> lane) & 1u) s.rlist[oR + __popc(rb & below)] = packed;
+            }
             carryL += __shfl_sync(0xffffffffu, il, 31);
             carryR += __shfl_sync(0xffffffffu, ir, 31);
         }
-        const int lg = pick_group_log2(carryL, carryR, W, D, C, nthreads, lane);
-        if (lane == 0) {
-            s.loff[nch] = carryL; s.roff[nch] = carryR; s.counts[0] = carryL; s.counts[1] = carryR;
-            s.counts[2] = lg;
+        if (warp == 0) {
+            const int lg = pick_group_log2(carryL, carryR, W, D, C, nthreads, lane);
+            if (lane == 0) {
+                s.loff[nch] = carryL; s.roff[nch] = carryR; s.counts[0] = carryL; s.counts[1] = carryR;
+                s.counts[2] = lg;
+            }
         }
-    }
-    role_sync<BAR_N>(bar_id);
-    for (int k = warp; k < nch; k += nwarps) {
-        const int w = (k << 5) + lane;
-        const uint32_t lb = s.lbits[k], rb = s.rbits[k];
-        const uint32_t below = (1u << lane) - 1u;
-        uint32_t off = (uint32_t)w;
-        if (tile_bw > 0) {
-            const int ch = (int)__umulhi((uint32_t)w, bw_magic);     // w / tile_bw (exact for w < 2^16)
-            off = (uint32_t)(ch * chunk_stride + (w - ch * tile_bw));
-        }
-        const uint32_t packed = (off << 16) | (uint32_t)w;
-        if ((lb >> lane) & 1u) s.llist[s.loff[k] + __popc(lb & below)] = packed;
-        if ((rb >> lane) & 1u) s.rlist[s.roff[k] + __popc(rb & below)] = packed;
     }
     role_sync<BAR_N>(bar_id);
 }
