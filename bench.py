@@ -43,6 +43,8 @@ def parse():
                     help="pairs: shard by stereo pair (weak scaling); bands: ONE pair split into row bands "
                          "with halo exchange over NCCL (strong scaling, BASELINE.json configs[3])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="masks + sparse ops on the main stream instead of a forked second stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-from-images", action="store_true",
                     help="skip the extra leg that starts from images (feature extractor + hot path, SURVEY.md 8f rank 2)")
@@ -197,6 +199,7 @@ def run_from_images(args, info, dev, timed):
                            conv3d_impl=args.conv3d)
     model.load_state_dict(make_hotpath_state(17))
     model = model.to(dev)
+    model.overlap = not args.no_overlap
     g = torch.Generator(device=dev).manual_seed(99)
     sets = []
     for _ in range(2):
@@ -558,6 +561,7 @@ def run_ours(args):
                                                 f"D{info['max_disp'] * 3 ** i // 27}" for i, c in enumerate((216, 72, 24, 8))),
                            "left_mask_density": info["left_mask_density"], "conv3d_impl": args.conv3d,
                            "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches",
+                           "streams": "masks + sparse ops on a forked second stream (two graph branches)" if not args.no_overlap else "one stream",
                            "l2": "inputs (400 MB of feature pyramids per step) exceed the 126 MB L2; no flush",
                            "parallelism": (f"row bands of one batch over {world} rank(s): per-layer halo send/recv in the "
                                            "3-D aggregation, all-gather of the per-level disparity") if bands_mode

@@ -541,11 +541,46 @@ class DecompMatching(nn.Module):
         _reset_folded(self)
         return out
 
+    # Masks (a5/a6) and the sparse ops (a9/a10) of every level depend on the features only, not on the disparity
+    # coming up from the coarser level: they run on a second stream, forked at the start of forward() and joined
+    # where the soft attention first needs them, so that they fill the SMs the main chain leaves idle (the last,
+    # partial round of tiles of the persistent conv kernels, launch gaps).  Captured in a CUDA graph this becomes two
+    # parallel branches.  `overlap = False` restores the single-stream order.
+    overlap = True
+
     @torch.no_grad()
     def forward(self, left_feats, right_feats, left_mask_list=None, right_mask_list=None, is_check=False):
         taps = {k: [] for k in ("pred", "dense", "sparse", "var", "soft_mask", "fusion", "residual",
                                 "left_mask", "right_mask", "left_detail", "right_detail")} if is_check else None
         pred = None
+        branch = events = side = None
+        if self.overlap and not is_check:
+            dev = left_feats["stage0"].device
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_side", None) is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(dev)
+            side = self._side
+            side.wait_stream(main)                       # fork: the features are ready on the main stream
+            with torch.cuda.stream(side):
+                branch, events = [], []
+                pre = (left_feats["stage0"].contiguous(), right_feats["stage0"].contiguous())
+                for s in range(1, self.num_stage):
+                    if s >= self.skip_stage_id:
+                        branch.append(None); events.append(None)
+                        continue
+                    l = s - 1
+                    Lf, Rf = left_feats[f"stage{s}"].contiguous(), right_feats[f"stage{s}"].contiguous()
+                    D = self.max_disp // (self.down_scale ** (self.num_stage - s - 1))
+                    if self.use_detail:
+                        lm, rm = self.detail_detection[l].masks_pair(Lf, pre[0], Rf, pre[1], self.thold)
+                        pre = (Lf, Rf)
+                    else:
+                        lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
+                    sparse, var, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm, rm, D)
+                    branch.append((lm, rm, sparse, var))
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
         pre_l = pre_r = None
         for s in range(self.num_stage):
             Lf = left_feats[f"stage{s}"].contiguous()
@@ -561,18 +596,23 @@ class DecompMatching(nn.Module):
                 pred = F.interpolate(pred.unsqueeze(1) * self.down_scale, list(Lf.shape[-2:]), mode="bicubic").squeeze(1)
             else:
                 l = s - 1
-                if self.use_detail:
-                    lm, rm = self.detail_detection[l].masks_pair(Lf, pre_l, Rf, pre_r, self.thold)
-                    if is_check:
-                        ld, _, _ = self.detail_detection[l](Lf, pre_l)
-                        rd, _, _ = self.detail_detection[l](Rf, pre_r)
-                        taps["left_detail"].append(torch.sigmoid(ld).contiguous())
-                        taps["right_detail"].append(torch.sigmoid(rd).contiguous())
-                    pre_l, pre_r = Lf, Rf
+                if branch is not None:
+                    dense = self.dynamic_upsampling[l](pred, Lf)
+                    torch.cuda.current_stream(Lf.device).wait_event(events[l])      # join for this level
+                    lm, rm, sparse, var = branch[l]
                 else:
-                    lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
-                dense = self.dynamic_upsampling[l](pred, Lf)
-                sparse, var, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm, rm, D)     # SpaMat + SpaVar, one pass
+                    if self.use_detail:
+                        lm, rm = self.detail_detection[l].masks_pair(Lf, pre_l, Rf, pre_r, self.thold)
+                        if is_check:
+                            ld, _, _ = self.detail_detection[l](Lf, pre_l)
+                            rd, _, _ = self.detail_detection[l](Rf, pre_r)
+                            taps["left_detail"].append(torch.sigmoid(ld).contiguous())
+                            taps["right_detail"].append(torch.sigmoid(rd).contiguous())
+                        pre_l, pre_r = Lf, Rf
+                    else:
+                        lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
+                    dense = self.dynamic_upsampling[l](pred, Lf)
+                    sparse, var, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm, rm, D)     # SpaMat + SpaVar, one pass
                 aux = ops.attn_pack(None, dense, sparse, lm, var)                  # [dense, sparse, mask, -var]
                 logit = self.soft_attention[l].logits_cat(Lf, aux).squeeze(1).contiguous()
                 soft, fused = ops.blend(logit, dense, sparse, want_mask=is_check)
@@ -583,6 +623,11 @@ class DecompMatching(nn.Module):
                         taps[k].append(v)
             if is_check:
                 taps["pred"].append(pred)
+        if side is not None:
+            # join (a captured graph needs every forked stream back).  The side stream's tensors are consumed on the
+            # main stream; their memory returns to the side stream's pool and is reused only by the next forward's
+            # branch, which starts behind that forward's fork, i.e. behind everything enqueued here.
+            torch.cuda.current_stream(pred.device).wait_stream(side)
         return (pred, taps) if is_check else [pred]
 
     def dense_stage(self, Lf, Rf, D):
