@@ -290,6 +290,7 @@ def run_ours(args):
     bands_mode = args.mode == "bands"
     model, left, right, info = build_workload(args.workload, args.batch, seed=17 + (0 if bands_mode else rank),
                                               device=dev, rho=args.rho, conv3d_impl=args.conv3d)
+    model.overlap = not args.no_overlap
     B = args.batch
     if bands_mode:
         from decnet_b200 import bands as _bands
