@@ -211,8 +211,14 @@ def run_from_images(args, info, dev, timed):
 
     dens = calibrate_mask_density(model, feats(sets[0]["l"]), feats(sets[0]["r"]), args.rho)
 
+    from decnet_b200.features import extract_pair
+
     def step_eager(st):
-        return ops.disp_to_u16(model(feats(st["l"]), feats(st["r"]))[0], oh, ow)
+        if args.no_overlap:
+            fl, fr = feats(st["l"]), feats(st["r"])
+        else:                                            # right view on a forked second stream
+            fl, fr = extract_pair(fe, st["l"], st["r"], prepare=lambda u8: ops.image_prepare_u8(u8, want01=False)[1])
+        return ops.disp_to_u16(model(fl, fr)[0], oh, ow)
 
     for st in sets:
         step_eager(st)

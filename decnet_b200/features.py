@@ -114,3 +114,21 @@ class FeatExtNetChannelPlus(nn.Module):
         res, _ = self.deconv1(self.addition_trans0(conv0), res)
         out["stage3"] = res
         return out
+
+
+def extract_pair(fe, left, right, prepare=None):
+    """Features of both views, the right view on a forked second stream (the two extractions are independent;
+    demo.py:166-167 runs them back to back inside the model).  `prepare` is applied to each input first
+    (e.g. the uint8 -> padded / normalised image kernel).  Returns (left_feats, right_feats), joined on the
+    current stream; capturable in a CUDA graph (two branches)."""
+    main = torch.cuda.current_stream(left.device)
+    side = getattr(fe, "_side", None)
+    if side is None or side.device != left.device:
+        side = fe._side = torch.cuda.Stream(left.device)
+    side.wait_stream(main)                               # fork
+    with torch.cuda.stream(side):
+        fr = fe(prepare(right) if prepare is not None else right)
+    fl = fe(prepare(left) if prepare is not None else left)
+    # join; the right view's tensors live in the side stream's pool and are reused only behind the next fork
+    main.wait_stream(side)
+    return fl, fr

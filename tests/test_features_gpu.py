@@ -62,3 +62,30 @@ def test_features_full_size_tensor_core_route_vs_fp32_route():
                      ("stage3", (2, 8, 540, 972))):
         assert tuple(a[k].shape) == shape
         assert float((a[k] - b[k]).abs().max()) <= 1e-2 * max(1.0, float(b[k].abs().max())), k
+
+
+def test_extract_pair_two_streams_equals_two_calls():
+    """Both views with the right one on a forked stream: same bits as two calls on one stream, eagerly and
+    replayed from a captured graph (two branches)."""
+    from decnet_b200.features import extract_pair
+    m = _model(5)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xl = torch.randn(2, 3, 108, 216, device="cuda", generator=g)
+    xr = torch.randn(2, 3, 108, 216, device="cuda", generator=g)
+    wl, wr = m(xl), m(xr)
+    fl, fr = extract_pair(m, xl, xr)
+    torch.cuda.synchronize()
+    for k in wl:
+        assert torch.equal(fl[k], wl[k]) and torch.equal(fr[k], wr[k])
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        extract_pair(m, xl, xr)
+        with torch.cuda.graph(graph, stream=side):
+            gl, gr = extract_pair(m, xl, xr)
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    for k in wl:
+        assert torch.equal(gl[k], wl[k]) and torch.equal(gr[k], wr[k])

@@ -110,6 +110,32 @@ def test_pipeline_full_size_runs_and_is_deterministic(workload, batch):
     assert all(abs(d - 0.1) < 0.02 for d in dens), dens
 
 
+@pytest.mark.parametrize("workload,batch", [("sceneflow", 2), ("kitti", 2)])
+def test_two_stream_step_equals_single_stream(workload, batch):
+    """Masks + sparse ops on the forked second stream (DecompMatching.overlap, the default) change the order of
+    execution only: same bits as the single-stream order, eagerly and replayed from a captured graph."""
+    from decnet_b200.synthetic import build_workload
+    model, left, right, info = build_workload(workload, batch, rho=0.1)
+    model.overlap = False
+    want = model(left, right)[0].clone()
+    model.overlap = True
+    got = model(left, right)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        model(left, right)
+        with torch.cuda.graph(graph, stream=side):
+            out = model(left, right)[0]
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+
+
 def test_middlebury_bands_match_single_device():
     """BASELINE.json configs[3] at full size: 8 row bands (simulated in one process) vs one device."""
     from decnet_b200 import bands
