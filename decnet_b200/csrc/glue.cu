@@ -399,7 +399,7 @@ dynup_pack_nhwc_kernel(const float *__restrict__ disp, const float *__restrict__
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int l = lut[4 * c4 + e];
-            float v = l >= 0 ? rows[l + 3 * xl] : (l == -2 ? __ldg(db + xl) : 0.f);
+            float v = l >= 0 ? rows[l + 3 * xl] : ((l == -2 && disp) ? __ldg(db + xl) : 0.f);
             if (round_tf32) v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);   // == cvt.rna.tf32
             o[e] = v;
         }
@@ -407,6 +407,22 @@ dynup_pack_nhwc_kernel(const float *__restrict__ disp, const float *__restrict__
         xl += dxl; c4 += dc4;
         if (c4 >= cp4) { c4 -= cp4; ++xl; }
     }
+}
+
+// Channel 0 of a packed tensor (the only channel that depends on the disparity): lets the feature channels be
+// packed ahead of time, on another stream, with disp = NULL.
+__global__ void __launch_bounds__(kBlock)
+dynup_set_disp_nhwc_kernel(const float *__restrict__ disp, float *__restrict__ out, int h, int w, int CP,
+                           int round_tf32, int pad, long long n)
+{
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % w);
+    const long long t = i / w;
+    const int y = (int)(t % h), b = (int)(t / h);
+    float v = __ldg(disp + i);
+    if (round_tf32) v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    out[(((size_t)b * (h + 2 * pad) + y + pad) * (w + 2 * pad) + x + pad) * CP] = v;
 }
 
 // Block = 32 coarse pixels of one row x 9 sub-pixels (288 threads).  The 32 x NP logits are staged through
@@ -899,7 +915,7 @@ int decnet_haar_level(const float *x, float *ll, float *detail, float *mask, voi
 int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out, int B, int C, int h, int w, int CP,
                            int round_tf32, int pad, void *stream) {
     DECNET_REQUIRE(pad == 0 || pad == 1, "pad must be 0 or 1");
-    DECNET_REQUIRE(disp && left_fea && out, "null pointer");
+    DECNET_REQUIRE(left_fea && out, "null pointer");         // disp may be NULL: channel 0 is written as zero
     DECNET_REQUIRE(B > 0 && B <= 65535 && C > 0 && h > 0 && h <= 65535 && w > 0, "bad size");
     DECNET_REQUIRE(CP >= 9 * C + 1, "CP=%d must hold 9*C+1=%d channels", CP, 9 * C + 1);
     int TX = 1200 / C;                            // <= 43 KB of shared memory: 5 blocks per SM
@@ -914,6 +930,17 @@ int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
     dynup_pack_nhwc_kernel<<<dim3((w + TX - 1) / TX, h + 2 * pad, B), kBlock, smem, (cudaStream_t)stream>>>(disp, left_fea, out, C, h, w, CP, TX,
                                                                                                         round_tf32, pad);
     return after_launch("dynup_pack_nhwc_kernel");
+}
+
+int decnet_dynup_set_disp_nhwc(const float *disp, float *packed, int B, int h, int w, int CP, int round_tf32, int pad,
+                               void *stream) {
+    DECNET_REQUIRE(pad == 0 || pad == 1, "pad must be 0 or 1");
+    DECNET_REQUIRE(disp && packed, "null pointer");
+    DECNET_REQUIRE(B > 0 && h > 0 && w > 0 && CP > 0, "bad size");
+    const long long n = (long long)B * h * w;
+    dynup_set_disp_nhwc_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        disp, packed, h, w, CP, round_tf32, pad, n);
+    return after_launch("dynup_set_disp_nhwc_kernel");
 }
 
 int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out, int B, int h, int w, int NP, int pad, void *stream) {

@@ -383,16 +383,27 @@ class DynamicUpsampling(nn.Module):
             self._packed = ((cin0 + 7) // 8 * 8, packed)
         return self._packed
 
-    def forward(self, disp_map, left_fea):
+    def prepack(self, left_fea):
+        """The feature channels of the conv input (everything but the disparity channel), or None when the TF32
+        tensor-core route is off.  Independent of the disparity: the stage loop runs it ahead, on its second stream."""
+        if USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32:
+            cp0, _ = self._tf32_pack()
+            return ops.dynup_pack_nhwc(None, left_fea.contiguous(), cp0, pad=True)
+        return None
+
+    def forward(self, disp_map, left_fea, packed=None):
         disp_map = disp_map.contiguous()
         if USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32:
             # TF32 allowed (PyTorch's default for convolutions): the three 81-channel convs run as tcgen05
             # implicit GEMMs on channels-last fp32, between channels-last pack / glue kernels
-            cp0, packed = self._tf32_pack()
+            cp0, packed_w = self._tf32_pack()
             # the tensors carry a one-pixel zero border, so one TMA fill per row tap serves the three column taps
-            x = ops.dynup_pack_nhwc(disp_map, left_fea.contiguous(), cp0, pad=True)
-            for i, (wp, bp, relu) in enumerate(packed):
-                x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=i + 1 < len(packed))
+            if packed is not None:
+                x = ops.dynup_set_disp_nhwc(packed, disp_map, pad=True)        # feature channels packed ahead (prepack)
+            else:
+                x = ops.dynup_pack_nhwc(disp_map, left_fea.contiguous(), cp0, pad=True)
+            for i, (wp, bp, relu) in enumerate(packed_w):
+                x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=i + 1 < len(packed_w))
             return ops.dynup_glue_nhwc(x, disp_map, pad=True)
         x = ops.dynup_pack(disp_map, left_fea.contiguous())
         logits = self.weight_learning(x)
@@ -553,7 +564,7 @@ class DecompMatching(nn.Module):
         taps = {k: [] for k in ("pred", "dense", "sparse", "var", "soft_mask", "fusion", "residual",
                                 "left_mask", "right_mask", "left_detail", "right_detail")} if is_check else None
         pred = None
-        branch = events = side = None
+        branch = events = packs = pack_events = side = None
         if self.overlap and not is_check:
             dev = left_feats["stage0"].device
             main = torch.cuda.current_stream(dev)
@@ -562,7 +573,17 @@ class DecompMatching(nn.Module):
             side = self._side
             side.wait_stream(main)                       # fork: the features are ready on the main stream
             with torch.cuda.stream(side):
-                branch, events = [], []
+                branch, events, packs, pack_events = [], [], [], []
+                # first what the main chain needs first: the feature channels of every level's up-sampling input
+                for s in range(1, self.num_stage):
+                    pk = None
+                    if s < self.skip_stage_id:
+                        pk = self.dynamic_upsampling[s - 1].prepack(left_feats[f"stage{s}"])
+                    ev = None
+                    if pk is not None:
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    packs.append(pk); pack_events.append(ev)
                 pre = (left_feats["stage0"].contiguous(), right_feats["stage0"].contiguous())
                 for s in range(1, self.num_stage):
                     if s >= self.skip_stage_id:
@@ -597,7 +618,9 @@ class DecompMatching(nn.Module):
             else:
                 l = s - 1
                 if branch is not None:
-                    dense = self.dynamic_upsampling[l](pred, Lf)
+                    if pack_events[l] is not None:
+                        torch.cuda.current_stream(Lf.device).wait_event(pack_events[l])
+                    dense = self.dynamic_upsampling[l](pred, Lf, packed=packs[l])
                     torch.cuda.current_stream(Lf.device).wait_event(events[l])      # join for this level
                     lm, rm, sparse, var = branch[l]
                 else:

@@ -629,18 +629,35 @@ def nhwc_pad_to_nchw(x_pad, channels):
 
 
 def dynup_pack_nhwc(disp, left_fea, cp, round_tf32=True, pad=False):
-    """pad=True: [B,h+2,w+2,cp] with a zero border (the layout conv2d_tf32_nhwc_halo chains on)."""
+    """pad=True: [B,h+2,w+2,cp] with a zero border (the layout conv2d_tf32_nhwc_halo chains on).
+    disp=None: only the feature channels (channel 0 zero) -- dynup_set_disp_nhwc() completes it later."""
+    _chk("left_fea", left_fea)
+    B, Cc, H3, W3 = left_fea.shape
+    if H3 % 3 or W3 % 3:
+        raise ValueError(f"left_fea {tuple(left_fea.shape)} is not 3x a coarse grid")
+    h, w = H3 // 3, W3 // 3
+    if disp is not None:
+        _chk("disp", disp, left_fea)
+        if tuple(disp.shape) != (B, h, w):
+            raise ValueError(f"left_fea {tuple(left_fea.shape)} is not 3x the disparity map {tuple(disp.shape)}")
+    k = 2 if pad else 0
+    out = torch.empty((B, h + k, w + k, int(cp)), dtype=torch.float32, device=left_fea.device)
+    _call("decnet_dynup_pack_nhwc", left_fea, disp.data_ptr() if disp is not None else None, left_fea.data_ptr(),
+          out.data_ptr(), B, Cc, h, w, int(cp), 1 if round_tf32 else 0, 1 if pad else 0)
+    return out
+
+
+def dynup_set_disp_nhwc(packed, disp, round_tf32=True, pad=False):
+    """Writes channel 0 (the disparity) of a tensor packed with disp=None, in place; returns it."""
     _chk("disp", disp)
     B, h, w = disp.shape
-    _chk("left_fea", left_fea, disp)
-    Cc = left_fea.shape[1]
-    if tuple(left_fea.shape) != (B, Cc, 3 * h, 3 * w):
-        raise ValueError(f"left_fea {tuple(left_fea.shape)} is not 3x the disparity map {tuple(disp.shape)}")
+    _chk("packed", packed, disp)
     k = 2 if pad else 0
-    out = torch.empty((B, h + k, w + k, int(cp)), dtype=torch.float32, device=disp.device)
-    _call("decnet_dynup_pack_nhwc", disp, disp.data_ptr(), left_fea.data_ptr(), out.data_ptr(), B, Cc, h, w, int(cp),
+    if tuple(packed.shape[:3]) != (B, h + k, w + k):
+        raise ValueError(f"packed {tuple(packed.shape)} does not match disp {tuple(disp.shape)} (pad={pad})")
+    _call("decnet_dynup_set_disp_nhwc", disp, disp.data_ptr(), packed.data_ptr(), B, h, w, packed.shape[-1],
           1 if round_tf32 else 0, 1 if pad else 0)
-    return out
+    return packed
 
 
 def dynup_glue_nhwc(logits_nhwc, disp, pad=False):

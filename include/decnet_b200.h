@@ -271,6 +271,10 @@ int decnet_dynup_pack_nhwc(const float *disp, const float *left_fea, float *out,
                            int B, int C, int h, int w, int CP, int round_tf32, int pad, void *stream);
 int decnet_dynup_glue_nhwc(const float *logits, const float *disp, float *out,
                            int B, int h, int w, int NP, int pad, void *stream);
+/* The feature channels do not depend on the disparity: decnet_dynup_pack_nhwc with disp = NULL writes channel 0 as
+ * zero (it can run ahead of the disparity, on another stream) and this fills channel 0 of the interior pixels. */
+int decnet_dynup_set_disp_nhwc(const float *disp, float *packed,
+                               int B, int h, int w, int CP, int round_tf32, int pad, void *stream);
 
 /* Tail of GenerateSparseMask (modules/submodule.py:363-369) for BOTH views in one launch each:
  *   decnet_sqdiff_pair : out_i = (a_i - b_i)^2, i = 0 (left), 1 (right); n elements each

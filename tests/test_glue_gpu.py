@@ -318,6 +318,11 @@ def test_dynup_padded_layout_and_halo_conv_match_the_unpadded_route():
     a = ops.dynup_pack_nhwc(disp, Lf, cp)
     b = ops.dynup_pack_nhwc(disp, Lf, cp, pad=True)
     assert torch.equal(b, F.pad(a, (0, 0, 1, 1, 1, 1)))
+    # feature channels packed ahead of the disparity (disp=None), channel 0 filled later: same bits
+    for pad in (False, True):
+        early = ops.dynup_pack_nhwc(None, Lf, cp, pad=pad)
+        assert float(early[..., 0].abs().max()) == 0
+        assert torch.equal(ops.dynup_set_disp_nhwc(early, disp, pad=pad), b if pad else a)
     wt = torch.randn(81, 9 * C + 1, 3, 3, device="cuda", generator=g) * 0.05
     wp, bp, np_ = ops.pack_conv2d_tf32_weights(wt, torch.randn(81, device="cuda", generator=g) * 0.1, cp)
     ya = ops.conv2d_tf32_nhwc(a, wp, bp, True)
