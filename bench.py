@@ -502,6 +502,30 @@ def run_ours(args):
                 roof["traffic"] = json.loads(tr.read_text()).get("sparse_row_gather_kernel_bytes_per_launch")
             except Exception:
                 pass
+        # the same launch at other mask densities, and the staged (TMA) row kernel beside the default sector-gather
+        # kernel: us per launch, same timing method (back-to-back launches, inputs larger than L2)
+        def time_sparse(mlx, mrx, n=10):
+            for _ in range(2):
+                ops.spamat_spavar_forward(Lf, Rf, mlx, mrx, Dc)
+            e0.record()
+            for _ in range(n):
+                ops.spamat_spavar_forward(Lf, Rf, mlx, mrx, Dc)
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / n
+        sweep = {}
+        for rho_s in (0.01, 0.03, args.rho):
+            mls, mrs = ops.mask_threshold(pl, pr, 1.0 - rho_s)
+            rec = {"gather_us": round(time_sparse(mls, mrs), 2)}
+            lib.decnet_set_sparse_variant(1)
+            try:
+                rec["staged_us"] = round(time_sparse(mls, mrs), 2)
+            except Exception:
+                rec["staged_us"] = None
+            finally:
+                lib.decnet_set_sparse_variant(0)
+            rec["gather_frac"] = round(alg / (rec["gather_us"] * 1e-6) / 1e9 / pk["hbm_gbs"], 4)
+            sweep[str(rho_s)] = rec
+        roof["density_sweep"] = sweep
         # the thin 3x3 Conv2d layers (conv2d_tcgen05_kernel, 31 % of the step): the 8->8 layer at the finest level,
         # algorithmic bytes = input + output once
         try:
