@@ -5,23 +5,27 @@
 // recomputed by four separate kernels):
 //
 //   * Both ops are ROW-LOCAL: pixel (b,h,w) only touches row (b,h) of the two
-//     feature maps, and C*W is the same at every pyramid level.  One CTA owns one
-//     row: the [C,W] slabs of L and R are staged in shared memory once
-//     (cp.async 128-bit here, TMA in sparse_match_tma.cu) and every cost of the
-//     row is evaluated from shared memory.
+//     feature maps.  One CTA owns one row.
 //   * Mask compaction: per 32-column chunk one __ballot_sync gives the mask bits,
 //     __popc the chunk count, a warp scan over chunk counts the offsets; the
 //     sorted list of valid right columns makes the candidate set of pixel w the
 //     CONTIGUOUS list range [prefix(max(0,w-D+1)), prefix(w+1)) -- bit-exact with
 //     the reference's `tar_mask[w-d] != 0` scan, and work is proportional to
 //     density^2 instead of D.
+//   * The listed columns of both views are transposed into compact [j][C] operand
+//     buffers in shared memory.  Default (sparse_row_gather_kernel): gathered straight
+//     from global memory through the sorted lists -- only the sectors that hold a listed
+//     column are read, four CTAs per SM.  Alternative (sparse_row_kernel): the whole
+//     [C,W] rows staged first by TMA or cp.async.  DESIGN.md section 3.1 has the
+//     measurements of both and of the persistent / pipelined forms kept behind
+//     decnet_set_sparse_variant().
 //   * A group of G lanes (G picked per row from the candidate density) owns one
 //     masked pixel; lanes own candidates; the channel dot product is the same
-//     sequential FMA chain as the reference (bit-identical costs); max / sum
-//     reductions are warp shuffles; SpaVar reuses the exp() of SpaMat and is
-//     evaluated against the FINAL mean (two-phase, no moment expansion).
-//   * All outputs of a row are assembled in shared memory and written with
-//     coalesced 128-bit stores, zeros included.
+//     sequential FMA chain as the reference (bit-identical costs); softmax is one
+//     pass (online max) with fp64 moments, so SpaVar around the final mean costs no
+//     second pass; max / sum reductions are warp shuffles.
+//   * Outputs are written completely (the row is zero-filled with 128-bit stores,
+//     masked pixels stored on top), so callers need no memset.
 #include "common.cuh"
 #include "sparse_core.cuh"
 #include "tma_utils.cuh"
