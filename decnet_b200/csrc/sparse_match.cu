@@ -272,10 +272,16 @@ sparse_row_gather_kernel(const __grid_constant__ RowArgs a)
         __syncthreads();   // operands complete; also orders the zero fill before the result stores
         process_row<MODE, 2>(s, Lc, Rc, 0, C, Cp, D, disp_row,
                              a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
+    } else if (nR * Cp <= a.rc_cap) {
+        // only the right columns fit (wide C or a dense row): each masked left pixel reads its own channel vector
+        // from global memory (list entries carry the column in both halves, the plane is the channel stride)
+        gather_columns_global(s.rlist, nR, Rrow, plane, C, Cp, Rc, tid, NT);
+        __syncthreads();
+        process_row<MODE, 1>(s, Lrow, Rc, (int)plane, C, Cp, D, disp_row,
+                             a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
     } else {
         __syncthreads();
-        // list entries carry the column in both halves (tile_bw = 0), so the slab addressing of mode 0
-        // reads global memory with the plane as the channel stride
+        // nothing fits: the slab addressing of mode 0 on global memory
         process_row<MODE, 0>(s, Lrow, Rrow, (int)plane, C, Cp, D, disp_row,
                              a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
     }
@@ -632,7 +638,8 @@ static size_t gather_smem(int C, int W, int nb, int &rc_cap)
     const size_t Cp = (size_t)((C + 3) & ~3);
     const size_t lists = list_smem_bytes(W);
     size_t cap = Wp * Cp * 4;
-    if (cap > 32 * 1024) cap = 32 * 1024;
+    if (cap > 32 * 1024) cap = 32 * 1024;                 // more would push the SM to its largest carve-out: the gather's
+                                                          // read-only loads lose their L1 (measured: C = 32, 353 -> 475 us)
     const size_t share = (size_t)(228 * 1024) / nb - 1280;
     if (lists + cap > share) cap = share > lists + 4096 ? share - lists : 4096;
     cap &= ~(size_t)15;

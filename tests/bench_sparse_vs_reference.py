@@ -49,7 +49,10 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     from oracle import ref_cuda
     have_ref = args.ref and ref_cuda.available()
-    levels = [("s1", 72, 60, 108, 24), ("s2", 24, 180, 324, 72), ("s3", 8, 540, 972, 216)]
+    # the model's three levels, then BASELINE.json configs[4]'s other channel counts at 1/3 and full resolution
+    levels = [("s1", 72, 60, 108, 24), ("s2", 24, 180, 324, 72), ("s3", 8, 540, 972, 216),
+              ("c32_third", 32, 180, 324, 72), ("c64_third", 64, 180, 324, 72),
+              ("c32_full", 32, 540, 972, 216), ("c64_full", 64, 540, 972, 216)]
     rows = []
     for name, C, H, W, D in levels:
         if name not in args.levels:
