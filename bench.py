@@ -38,7 +38,9 @@ def parse():
     ap.add_argument("--workload", default="sceneflow")
     ap.add_argument("--batch", type=int, default=8, help="stereo pairs per GPU per step")
     ap.add_argument("--rho", type=float, default=0.10, help="calibrated lost-detail mask density")
-    ap.add_argument("--conv3d", default=os.environ.get("DECNET_CONV3D", "tcgen05"), choices=["tcgen05", "cudnn"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="arithmetic mode of the 2-D tensor-core convs: fp32 = error-compensated 3xTF32 (parity-gated default), "
+                         "tf32 = plain TF32 (what the reference gets from cuDNN on a GPU)")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "bands"],
                     help="pairs: shard by stereo pair (weak scaling); bands: ONE pair split into row bands "
                          "with halo exchange over NCCL (strong scaling, BASELINE.json configs[3])")
@@ -192,11 +194,11 @@ def run_from_images(args, info, dev, timed):
     from decnet_b200.synthetic import calibrate_mask_density
     B, H, W = args.batch, info["H"], info["W"]
     oh, ow = (540, 960) if args.workload == "sceneflow" else (H, W)          # unpadded image size (demo.py pads top/left)
-    fe = FeatExtNetChannelPlus(8)
+    fe = FeatExtNetChannelPlus(8, precision=args.precision)
     fe.load_state_dict(make_featext_state(17))
     fe = fe.to(dev)
     model = DecompMatching(max_disp=info["max_disp"], skip_stage_id=info["skip_stage_id"], use_detail=True, thold=0.9,
-                           conv3d_impl=args.conv3d)
+                           precision=args.precision)
     model.load_state_dict(make_hotpath_state(17))
     model = model.to(dev)
     model.overlap = not args.no_overlap
@@ -289,13 +291,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.benchmark = True
-    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True          # only the feature extractor's library layers (from_images leg) use cuDNN
     lib = _lib.lib()
 
     bands_mode = args.mode == "bands"
     model, left, right, info = build_workload(args.workload, args.batch, seed=17 + (0 if bands_mode else rank),
-                                              device=dev, rho=args.rho, conv3d_impl=args.conv3d)
+                                              device=dev, rho=args.rho, precision=args.precision)
     model.overlap = not args.no_overlap
     B = args.batch
     if bands_mode:
@@ -533,19 +534,20 @@ def run_ours(args):
             if ops.conv2d_tf32_supported(Cq, 8, Hq, Wq, 1):
                 gq = torch.Generator(device=dev).manual_seed(7)
                 wq = torch.randn(8, Cq, 3, 3, device=dev, generator=gq) * 0.1
-                wpk, bpk = ops.pack_conv2d_tf32_nchw_weights(wq, torch.zeros(8, device=dev))
+                split_q = args.precision == "fp32"
+                wpk, bpk = ops.pack_conv2d_tf32_nchw_weights(wq, torch.zeros(8, device=dev), split=split_q)
                 xq = left["stage3"]
                 for _ in range(3):
-                    ops.conv2d_tf32_nchw(xq, wpk, bpk, 8, 1, True)
+                    ops.conv2d_tf32_nchw_cat([xq], wpk, bpk, 8, 1, True, split=split_q)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(20):
-                    ops.conv2d_tf32_nchw(xq, wpk, bpk, 8, 1, True)
+                    ops.conv2d_tf32_nchw_cat([xq], wpk, bpk, 8, 1, True, split=split_q)
                 e1.record(); torch.cuda.synchronize()
                 t_c = e0.elapsed_time(e1) * 1e-3 / 20
                 alg_c = 4.0 * Bq * Hq * Wq * (Cq + 8)
-                roof_conv2d = {"bound": "hbm", "kernel": "conv2d_tcgen05_kernel (3x3, 8->8 channels, finest level, TF32)",
+                roof_conv2d = {"bound": "hbm", "kernel": "conv2d_tcgen05_kernel (3x3, 8->8 channels, finest level, " + ("3xTF32" if split_q else "TF32") + ")",
                                "achieved": alg_c / t_c / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                "frac": alg_c / t_c / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes": alg_c,
                                "us_per_launch": t_c * 1e6}
@@ -560,8 +562,8 @@ def run_ours(args):
         try:
             from decnet_b200 import conv3d as c3
             roof_tensor = c3.measure_roofline(model, left["stage0"], right["stage0"], info["max_disp"] // 27, pk)
-        except Exception as e:  # not built yet / cudnn bring-up path
-            roof_tensor = {"bound": "tensor", "note": f"conv3d impl '{args.conv3d}': {type(e).__name__}: {e}"}
+        except Exception as e:
+            roof_tensor = {"bound": "tensor", "note": f"{type(e).__name__}: {e}"}
 
     # ---- extra leg: the same step fed from IMAGES -- feature extractor on both
     # views + hot path in one CUDA graph; its end-to-end form uploads 2 x B images (a quarter of the bytes of
@@ -590,7 +592,7 @@ def run_ours(args):
                                        "full decomposition pyramid" + (" (BASELINE.json configs[1])" if args.workload == "sceneflow" and B == 8 else ""),
                            "levels": " | ".join(f"1/{27 // 3 ** i} C{c} {info['H'] * 3 ** i // 27}x{info['W'] * 3 ** i // 27} "
                                                 f"D{info['max_disp'] * 3 ** i // 27}" for i, c in enumerate((216, 72, 24, 8))),
-                           "left_mask_density": info["left_mask_density"], "conv3d_impl": args.conv3d,
+                           "left_mask_density": info["left_mask_density"], "precision": args.precision,
                            "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches",
                            "streams": "masks + sparse ops on a forked second stream (two graph branches)" if not args.no_overlap else "one stream",
                            "l2": "inputs (400 MB of feature pyramids per step) exceed the 126 MB L2; no flush",

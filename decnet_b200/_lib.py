@@ -11,6 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("DECNET_B200_LIB", _PKG / "libdecnet_b200.so"))
 
+ABI_VERSION = 2
 _f32p = C.c_void_p
 _i = C.c_int
 
@@ -37,10 +38,14 @@ SIGNATURES = {
     "decnet_conv2d_tf32_packed_floats": (_i, [_i] * 2),
     "decnet_conv2d_tf32_nchw": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),
     "decnet_conv2d_tf32_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 7 + [C.c_void_p]),
+    "decnet_conv2d_tc_supported": (_i, [_i] * 6),
+    "decnet_conv2d_tc_packed_floats": (_i, [_i] * 3),
+    "decnet_conv2d_tc_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 8 + [C.c_void_p]),
+    "decnet_conv2d_tc_nhwc_halo": (_i, [_f32p] * 4 + [_i] * 8 + [C.c_void_p]),
     "decnet_conv2d_tf32_rows_supported": (_i, [_i] * 5),
     "decnet_conv2d_tf32_rows_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv2d_tf32_nhwc_halo": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),
-    "decnet_nchw_cat_to_nhwc_pad": (_i, [C.c_void_p, C.c_void_p, _i, _f32p] + [_i] * 4 + [C.c_void_p]),
+    "decnet_nchw_cat_to_nhwc_pad": (_i, [C.c_void_p, C.c_void_p, _i, _f32p] + [_i] * 5 + [C.c_void_p]),
     "decnet_nhwc_pad_to_nchw": (_i, [_f32p] * 2 + [_i] * 5 + [C.c_void_p]),
     "decnet_conv3d_debug_timing": (None, [C.c_void_p]),
     "decnet_conv3d_set_variant": (None, [_i]),
@@ -94,7 +99,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.decnet_abi_version() != 1:
+        if handle.decnet_abi_version() != ABI_VERSION:
             raise DecnetError("libdecnet_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -27,12 +27,12 @@ def pack_unit(unit, cp: int):
 
 
 def packed_stack(reg):
-    """Cached per-module pack (invalidated by load_state_dict / .to(), see model._reset_folded)."""
-    if reg._packed is None:
+    """Per-module pack, cached on the identity of the module's parameters and BN statistics (model._Cached)."""
+    def build():
         cin = reg.conv0[0].conv.weight.shape[1]
         cp = _pad16(cin)
-        reg._packed = {"cp": cp, "units": [pack_unit(u, cp) + (u.relu,) for u in reg.units()]}
-    return reg._packed
+        return {"cp": cp, "units": [pack_unit(u, cp) + (u.relu,) for u in reg.units()]}
+    return reg._cached("packed", build)
 
 
 def conv3d_layer(x, w, bias, np_, relu, residual=None, out=None, out_f32=False):

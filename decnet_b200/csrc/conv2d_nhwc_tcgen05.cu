@@ -15,7 +15,13 @@
 // from L2 per tile.  Border pixels of the output are written as zeros, so the next layer needs no padding pass; image
 // boundaries inside the flattened index are covered by the borders, the ends of the tensor by TMA's zero fill.
 //
-// Warp roles as in conv3d_tcgen05.cu: 0 TMA producer, 1 MMA issuer, 2-5 epilogue; persistent CTAs, two TMEM slots.
+// split = 1 ("3xTF32", fp32-class results: the mode the parity gates run on): the activations arrive as plain fp32, four
+// converter warps write hi = rna_tf32(x) in place and lo = rna_tf32(x - hi) beside it, the weights arrive as hi and lo
+// parts ([18][NP][cp]: taps 0-8 hi, 9-17 lo), and every column tap issues lo*hi + hi*lo + hi*hi into the same accumulator
+// (36 MMAs per stage).  A stage is then 2 x 17 KB of A and 2 x 3 x NP x 128 B of B.
+//
+// Warp roles as in conv3d_tcgen05.cu: 0 TMA producer, 1 MMA issuer, 2-5 epilogue, 6-9 converters (split mode only);
+// persistent CTAs, two TMEM slots.
 #include "common.cuh"
 #include "tma_utils.cuh"
 #include <mutex>
@@ -24,7 +30,8 @@ namespace decnet {
 namespace conv2dnhwc {
 
 constexpr int kMaxStages = 6;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kConvWarps = 4;
 constexpr int kTileM = 128;
 constexpr int kARows = 130;                        // 128 pixels + one halo pixel on each side
 constexpr int kABytes = 17 * 1024;                 // 130 rows x 128 B rounded up to the 1 KB swizzle period
@@ -37,6 +44,7 @@ struct Params {
     int nchunks, last_ksteps;
     long long P;                                   // B * (h+2) * (w+2) padded pixels
     int relu, round_tf32, tmem_cols, num_tiles, stages;
+    int split;                                     // 1: 3xTF32 (hi/lo split of both operands)
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -107,6 +115,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t ready_bar[kMaxStages];   // split mode: hi/lo tiles written by the converters
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
@@ -115,15 +124,17 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     unsigned char *base = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_tap_bytes = p.np * 128;                       // one column tap of the weights: NP rows x 128 B
-    const int stage_bytes = kABytes + 3 * b_tap_bytes;
-    const int tx_bytes = kARows * 128 + 3 * b_tap_bytes;      // bytes TMA actually delivers per stage
+    const int nsplit = p.split ? 2 : 1;
+    const int b_off = nsplit * kABytes;                       // stage: [A hi][A lo][B hi (3 taps)][B lo (3 taps)]
+    const int stage_bytes = nsplit * (kABytes + 3 * b_tap_bytes);
+    const int tx_bytes = kARows * 128 + nsplit * 3 * b_tap_bytes;   // bytes TMA actually delivers per stage
     const int kStages = p.stages;
     const int acc_stride = p.tmem_cols >> 1;
     const int pitch = p.w + 2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_mbar_init();
     }
@@ -149,7 +160,8 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         unsigned char *sa = base + (size_t)s * stage_bytes;
                         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)tx_bytes);
                         tma_load_2d(sa, &tmA, ck * 32, p0 + (kh - 1) * pitch - 1, &full_bar[s]);
-                        tma_load_3d(sa + kABytes, &tmB, ck * 32, 0, kh * 3, &full_bar[s]);
+                        tma_load_3d(sa + b_off, &tmB, ck * 32, 0, kh * 3, &full_bar[s]);
+                        if (p.split) tma_load_3d(sa + b_off + 3 * b_tap_bytes, &tmB, ck * 32, 0, 9 + kh * 3, &full_bar[s]);
                         if (++s == kStages) { s = 0; ph ^= 1u; }
                     }
             }
@@ -161,6 +173,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const uint32_t smem_base = smem_u32(base);
         const uint32_t empty_base = smem_u32(&empty_bar[0]);
         const uint32_t db_tap_step = (uint32_t)(b_tap_bytes >> 4);
+        uint64_t *const go_bar = p.split ? ready_bar : full_bar;   // what the MMAs of a stage wait for
         int s = 0; uint32_t ph = 0; int j = 0;
         bool ready = false;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
@@ -171,20 +184,60 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             uint32_t first = 0u;                              // 0: overwrite the accumulator
             for (int kh = 0; kh < 3; ++kh)
                 for (int ck = 0; ck < p.nchunks; ++ck) {
-                    if (!ready) mbar_wait(&full_bar[s], ph);
+                    if (!ready) mbar_wait(&go_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
                     const uint64_t da = make_desc_sw128(sa);
-                    const uint64_t db = make_desc_sw128(sa + kABytes);
+                    const uint64_t db = make_desc_sw128(sa + (uint32_t)b_off);
                     int sn = s + 1; uint32_t phn = ph;
                     if (sn == kStages) { sn = 0; phn ^= 1u; }
-                    ready = mbar_test_wait(&full_bar[sn], phn);
-                    umma_taps3(ck == p.nchunks - 1 ? p.last_ksteps : 4, acc, da, db, db_tap_step, idesc, first);
+                    ready = mbar_test_wait(&go_bar[sn], phn);
+                    const int ks = ck == p.nchunks - 1 ? p.last_ksteps : 4;
+                    if (p.split) {
+                        // small terms first: lo(x)*hi(w) + hi(x)*lo(w), then hi(x)*hi(w)
+                        const uint64_t da_lo = make_desc_sw128(sa + (uint32_t)kABytes);
+                        const uint64_t db_lo = make_desc_sw128(sa + (uint32_t)(b_off + 3 * b_tap_bytes));
+                        umma_taps3(ks, acc, da_lo, db, db_tap_step, idesc, first);
+                        umma_taps3(ks, acc, da, db_lo, db_tap_step, idesc, 1u);
+                        umma_taps3(ks, acc, da, db, db_tap_step, idesc, 1u);
+                    } else {
+                        umma_taps3(ks, acc, da, db, db_tap_step, idesc, first);
+                    }
                     umma_commit_elect(empty_base + (uint32_t)(s * 8));
                     first = 1u;
                     s = sn; ph = phn;
                 }
             umma_commit_elect(smem_u32(&tmem_full_bar[slot]));
+        }
+    } else if (warp >= 6) {
+        // ===================== converters (warps 6..9, split mode): hi in place, lo beside it =====================
+        if (p.split) {
+            const int ctid = threadIdx.x - 6 * 32;
+            constexpr int n16 = kARows * 128 / 16;                // 16-byte words TMA delivered for A
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+                for (int it = 0; it < 3 * p.nchunks; ++it) {
+                    mbar_wait(&full_bar[s], ph);
+                    uint4 *st = reinterpret_cast<uint4 *>(base + (size_t)s * stage_bytes);
+                    uint4 *sl = reinterpret_cast<uint4 *>(base + (size_t)s * stage_bytes + kABytes);
+#pragma unroll 4
+                    for (int i = ctid; i < n16; i += kConvWarps * 32) {
+                        const uint4 v = st[i];
+                        uint4 h, l;
+                        h.x = (v.x + 0x1000u) & 0xFFFFE000u; h.y = (v.y + 0x1000u) & 0xFFFFE000u;
+                        h.z = (v.z + 0x1000u) & 0xFFFFE000u; h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+                        l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + 0x1000u) & 0xFFFFE000u;
+                        l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + 0x1000u) & 0xFFFFE000u;
+                        l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + 0x1000u) & 0xFFFFE000u;
+                        l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + 0x1000u) & 0xFFFFE000u;
+                        st[i] = h;
+                        sl[i] = l;
+                    }
+                    fence_proxy_async_smem();                     // generic-proxy writes -> visible to the MMA's async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready_bar[s]);
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
+                }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -246,8 +299,8 @@ using namespace decnet::conv2dnhwc;
 
 extern "C" {
 
-int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
-                                 int B, int h, int w, int cp, int np, int relu, int round_out_tf32, void *stream)
+int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                               int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream)
 {
     DECNET_REQUIRE(x_pad && w_packed && bias && out_pad, "null pointer");
     DECNET_REQUIRE(B > 0 && h > 0 && w > 0, "non-positive size");
@@ -262,10 +315,10 @@ int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, cons
     p.last_ksteps = (cp - (p.nchunks - 1) * 32) / 8;
     p.P = (long long)B * (h + 2) * (w + 2);
     DECNET_REQUIRE(p.P + 2ll * (w + 3) < (1ll << 31), "tensor too large for 32-bit TMA coordinates");
-    p.relu = relu; p.round_tf32 = round_out_tf32;
+    p.relu = relu; p.round_tf32 = round_out_tf32; p.split = split ? 1 : 0;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;
     p.num_tiles = (int)((p.P + kTileM - 1) / kTileM);
-    const size_t stage_bytes = (size_t)kABytes + (size_t)3 * np * 128;
+    const size_t stage_bytes = ((size_t)kABytes + (size_t)3 * np * 128) * (p.split ? 2 : 1);
     p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     DECNET_REQUIRE(p.stages >= 2, "stage too large (np=%d)", np);
@@ -280,7 +333,7 @@ int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, cons
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, 9u};
+        const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, p.split ? 18u : 9u};
         const uint64_t strides[2] = {(uint64_t)cp * 4, (uint64_t)np * cp * 4};
         const uint32_t box[3] = {32u, (uint32_t)np, 3u};
         int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, w_packed, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -302,6 +355,12 @@ int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, cons
     const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
     conv2d_nhwc_halo_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
     return after_launch("conv2d_nhwc_halo_kernel");
+}
+
+int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                                 int B, int h, int w, int cp, int np, int relu, int round_out_tf32, void *stream)
+{
+    return decnet_conv2d_tc_nhwc_halo(x_pad, w_packed, bias, out_pad, B, h, w, cp, np, relu, round_out_tf32, 0, stream);
 }
 
 }  // extern "C"

@@ -28,6 +28,12 @@
 //     (cvt.rna, what cuDNN's TF32 path does) in place before the MMA warp reads it.  Weights are
 //     rounded on the host.
 //
+//   * split = 1 ("3xTF32"): the converters write hi = rna_tf32(x) in place and lo = rna_tf32(x - hi) into the second
+//     half of the stage, the weights arrive as hi and lo parts, and every (row group, row tap) issues three MMAs into
+//     the same accumulator: lo*hi + hi*lo + hi*hi.  The dropped lo*lo term and the rounding of the lo parts are
+//     ~2^-22 relative, so the result is fp32-class (the parity gates of tests/test_glue_gpu.py run on this mode);
+//     the kernel is bound by its epilogue, so the extra MMAs on K = 8 are nearly free.
+//
 // Warp roles (704 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-5 = converters,
 // 6-21 = epilogue.  Persistent CTAs, smem ring of RH-KB stages, two TMEM accumulator slots, the
 // weights of the whole layer resident in smem.
@@ -58,6 +64,8 @@ struct Params {
     int tw, th, num_tiles, stages;
     int relu;
     int w_rows, w_bytes;                   // packed weight rows (of 128 B) and the smem reserved for them
+    int split;                             // 1: error-compensated 3xTF32 (hi/lo operand split, fp32-class result)
+    int lo_off, w_lo_off;                  // split: byte offset of the lo tile inside a stage / of the lo weights
     int tmem_cols;
     long long *prof;                       // tuning only: per-role cycle counters of CTA 0 (16 int64), or null
     int dbg;                               // tuning only: 1 skip rounding, 2 skip epilogue math/stores, 4 skip MMAs
@@ -214,7 +222,8 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     if (threadIdx.x < p.CP) bias_s[threadIdx.x] = p.bias[threadIdx.x];
     unsigned char *wsm = base;                                   // resident weights
     unsigned char *ring = base + p.w_bytes;                      // stages
-    const int stage_bytes = p.RH * kRowBlock;
+    const int tile_bytes = p.RH * kRowBlock;                     // what TMA delivers per stage
+    const int stage_bytes = p.split ? 2 * tile_bytes : tile_bytes;
     const int kStages = p.stages;
     const int acc_stride = p.G * p.N;                            // TMEM columns per accumulator slot
 
@@ -254,7 +263,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     const long long tq0 = clock64();
                     mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);
                     prof_acc[0] += clock64() - tq0;
-                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)tile_bytes);
                     // the input is the channel concatenation of up to three tensors (each padded to whole chunks)
                     const CUtensorMap *tm = ck < p.ck1 ? &tmX : (ck < p.ck2 ? &tmX1 : &tmX2);
                     const int cl = ck < p.ck1 ? ck : (ck < p.ck2 ? ck - p.ck1 : ck - p.ck2);
@@ -287,9 +296,19 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 for (int g = 0; g < ((p.dbg & 4) ? 0 : p.G); ++g) {
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
-                        const uint64_t da = make_desc_mn(sa + (uint32_t)((4 * g + kh * p.dil) * kRowBlock));
-                        const uint64_t db = make_desc_mn(w_base + (uint32_t)(((kh * p.nck + ck) * p.natoms) * kRowBlock));
-                        umma_tf32_elect(acc + (uint32_t)(g * p.N), da, db, idesc, (ck | kh) != 0 ? 1u : 0u);
+                        const uint32_t a_off = sa + (uint32_t)((4 * g + kh * p.dil) * kRowBlock);
+                        const uint32_t b_off = w_base + (uint32_t)(((kh * p.nck + ck) * p.natoms) * kRowBlock);
+                        const uint64_t da = make_desc_mn(a_off), db = make_desc_mn(b_off);
+                        const uint32_t d = acc + (uint32_t)(g * p.N);
+                        const uint32_t accum = (ck | kh) != 0 ? 1u : 0u;
+                        if (p.split) {
+                            // small terms first: lo(x)*hi(w) + hi(x)*lo(w) + hi(x)*hi(w)
+                            umma_tf32_elect(d, make_desc_mn(a_off + (uint32_t)p.lo_off), db, idesc, accum);
+                            umma_tf32_elect(d, da, make_desc_mn(b_off + (uint32_t)p.w_lo_off), idesc, 1u);
+                            umma_tf32_elect(d, da, db, idesc, 1u);
+                        } else {
+                            umma_tf32_elect(d, da, db, idesc, accum);
+                        }
                     }
                 }
                 umma_commit_elect(empty_base + (uint32_t)(s * 8));
@@ -300,7 +319,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     } else if (warp < 2 + kConvWarps) {
         // ===================== converters: round the landed tile to TF32 in place =====================
         const int ctid = threadIdx.x - 64;
-        const int n16 = stage_bytes >> 4;                         // 16-byte words in a stage (RH * 64)
+        const int n16 = tile_bytes >> 4;                          // 16-byte words in a tile (RH * 64)
         int s = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             for (int ck = 0; ck < p.nck; ++ck) {
@@ -308,11 +327,28 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 mbar_wait(&full_bar[s], ph);
                 prof_acc[0] += clock64() - tq0;
                 uint4 *st = reinterpret_cast<uint4 *>(ring + (size_t)s * stage_bytes);
+                if (p.split) {
+                    // hi in place, lo = rna(x - hi) (the difference is exact in fp32) at the same swizzled offset of the lo tile
+                    uint4 *sl = reinterpret_cast<uint4 *>(ring + (size_t)s * stage_bytes + p.lo_off);
 #pragma unroll 4
-                for (int i = ctid; i < ((p.dbg & 1) ? 0 : n16); i += kConvWarps * 32) {
-                    uint4 v = st[i];
-                    v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
-                    st[i] = v;
+                    for (int i = ctid; i < n16; i += kConvWarps * 32) {
+                        const uint4 v = st[i];
+                        uint4 h, l;
+                        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                        l.x = rna_tf32(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)));
+                        l.y = rna_tf32(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)));
+                        l.z = rna_tf32(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)));
+                        l.w = rna_tf32(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
+                        st[i] = h;
+                        sl[i] = l;
+                    }
+                } else {
+#pragma unroll 4
+                    for (int i = ctid; i < ((p.dbg & 1) ? 0 : n16); i += kConvWarps * 32) {
+                        uint4 v = st[i];
+                        v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
+                        st[i] = v;
+                    }
                 }
                 fence_proxy_async_smem();                         // generic-proxy writes -> visible to the MMA's async proxy
                 __syncwarp();
@@ -340,17 +376,19 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 }
 
 // Shape support and tile plan (host).  Returns false when the layer does not fit this kernel.
-static bool plan(int Cin, int Cout, int H, int W, int dil, int B, Params &p, size_t &smem)
+static bool plan(int Cin, int Cout, int H, int W, int dil, int B, int split, Params &p, size_t &smem)
 {
+    p.split = split ? 1 : 0;
     if (Cin < 1 || Cout < 1 || dil < 1 || dil > 12 || (W & 3) != 0) return false;   // TMA strides: multiples of 16 B
     p.nck = (Cin + 7) / 8;
     p.CP = Cout <= 4 ? 4 : (Cout + 7) / 8 * 8;
     p.N = (3 * p.CP + 31) / 32 * 32;
     if (p.N > 256) return false;
     p.natoms = p.N / 32;
-    p.w_rows = 3 * p.nck * p.natoms * 8;
+    p.w_lo_off = 3 * p.nck * p.natoms * 8 * 128;                 // hi part: a whole number of 1 KB blocks
+    p.w_rows = 3 * p.nck * p.natoms * 8 * (p.split ? 2 : 1);
     p.w_bytes = (int)round_up((size_t)p.w_rows * 128, (size_t)kWBox * 128);
-    if (p.w_bytes > 96 * 1024) return false;
+    if (p.w_bytes > 160 * 1024) return false;
     p.dil = dil;
     p.vw = (32 - 2 * dil) / 4 * 4;
     p.pad = (dil + 3) / 4 * 4;
@@ -364,14 +402,18 @@ static bool plan(int Cin, int Cout, int H, int W, int dil, int B, Params &p, siz
     int G = gmax;
     while (G > 1 && (long long)B * p.tw * ((H + 4 * G - 1) / (4 * G)) < 2ll * sms) G >>= 1;
     p.G = G;
+    // the ring must hold at least two stages beside the resident weights (split: hi + lo tile per stage)
+    const size_t avail = 226 * 1024 - 1024 - (size_t)p.w_bytes;
+    while (G > 1 && (size_t)(4 * G + 2 * dil) * kRowBlock * (p.split ? 2 : 1) * 2 > avail) G >>= 1;
+    p.G = G;
     p.RH = 4 * G + 2 * dil;
     if (p.RH > 256) return false;
+    p.lo_off = p.RH * kRowBlock;
     p.th = (H + 4 * G - 1) / (4 * G);
     const long long tiles = (long long)B * p.tw * p.th;
     if (tiles >= (1ll << 31)) return false;
     p.num_tiles = (int)tiles;
-    const size_t stage = (size_t)p.RH * kRowBlock;
-    const size_t avail = 226 * 1024 - 1024 - (size_t)p.w_bytes;
+    const size_t stage = (size_t)p.RH * kRowBlock * (p.split ? 2 : 1);
     p.stages = (int)(avail / stage);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (p.stages < 2) return false;
@@ -393,22 +435,29 @@ static thread_local int g_conv2dtc_dbg = 0;
 static thread_local long long *g_conv2dtc_prof = nullptr;
 void decnet_conv2d_tf32_debug(int flags, void *prof16) { g_conv2dtc_dbg = flags; g_conv2dtc_prof = static_cast<long long *>(prof16); }
 
-int decnet_conv2d_tf32_supported(int Cin, int Cout, int H, int W, int dilation)
+int decnet_conv2d_tc_supported(int Cin, int Cout, int H, int W, int dilation, int split)
 {
     Params p{};
     size_t smem = 0;
-    return plan(Cin, Cout, H, W, dilation, 1, p, smem) ? 1 : 0;
+    return plan(Cin, Cout, H, W, dilation, 1, split, p, smem) ? 1 : 0;
 }
 
-int decnet_conv2d_tf32_packed_floats(int Cin, int Cout)
+int decnet_conv2d_tc_packed_floats(int Cin, int Cout, int split)
 {
     const int nck = (Cin + 7) / 8, CP = Cout <= 4 ? 4 : (Cout + 7) / 8 * 8, N = (3 * CP + 31) / 32 * 32;
-    return 3 * nck * (N / 32) * 8 * 32;
+    return 3 * nck * (N / 32) * 8 * 32 * (split ? 2 : 1);
 }
 
-int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
-                                const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
-                                int relu, int w_valid, void *stream)
+int decnet_conv2d_tf32_supported(int Cin, int Cout, int H, int W, int dilation)
+{
+    return decnet_conv2d_tc_supported(Cin, Cout, H, W, dilation, 0);
+}
+
+int decnet_conv2d_tf32_packed_floats(int Cin, int Cout) { return decnet_conv2d_tc_packed_floats(Cin, Cout, 0); }
+
+int decnet_conv2d_tc_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
+                              const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
+                              int relu, int w_valid, int split, void *stream)
 {
     DECNET_REQUIRE(w_valid >= 0 && w_valid <= W, "w_valid=%d outside [0, W=%d]", w_valid, W);
     DECNET_REQUIRE(srcs && src_channels && w_packed && bias_padded && out, "null pointer");
@@ -424,9 +473,9 @@ int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channel
     DECNET_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0, "w_packed must be 16-byte aligned");
     Params p{};
     size_t smem = 0;
-    DECNET_REQUIRE(plan(cin_pad, Cout, H, W, dilation, B, p, smem),
-                   "conv2d_tf32_nchw: unsupported shape Cin=%d (padded per source) Cout=%d H=%d W=%d dilation=%d "
-                   "(see decnet_conv2d_tf32_supported)", cin_pad, Cout, H, W, dilation);
+    DECNET_REQUIRE(plan(cin_pad, Cout, H, W, dilation, B, split, p, smem),
+                   "conv2d_tc_nchw: unsupported shape Cin=%d (padded per source) Cout=%d H=%d W=%d dilation=%d split=%d "
+                   "(see decnet_conv2d_tc_supported)", cin_pad, Cout, H, W, dilation, split);
     p.ck1 = cks[0]; p.ck2 = cks[0] + cks[1];
     p.dbg = g_conv2dtc_dbg; p.prof = g_conv2dtc_prof;
     p.bias = bias_padded; p.out = out; p.B = B; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu;
@@ -467,10 +516,18 @@ int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channel
     return after_launch("conv2d_tcgen05_kernel");
 }
 
+int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
+                                const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
+                                int relu, int w_valid, void *stream)
+{
+    return decnet_conv2d_tc_nchw_cat(srcs, src_channels, nsrc, w_packed, bias_padded, out, B, Cout, H, W, dilation, relu,
+                                     w_valid, 0, stream);
+}
+
 int decnet_conv2d_tf32_nchw(const float *x, const float *w_packed, const float *bias_padded, float *out,
                             int B, int Cin, int Cout, int H, int W, int dilation, int relu, void *stream)
 {
-    return decnet_conv2d_tf32_nchw_cat(&x, &Cin, 1, w_packed, bias_padded, out, B, Cout, H, W, dilation, relu, 0, stream);
+    return decnet_conv2d_tc_nchw_cat(&x, &Cin, 1, w_packed, bias_padded, out, B, Cout, H, W, dilation, relu, 0, 0, stream);
 }
 
 }  // extern "C"

@@ -481,14 +481,14 @@ dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict
 // ---------------------------------------------------------------------------------------------
 // Layout bridges for the wide (72-channel) refinement layers of the 1/9 level, which run on the zero-bordered
 // channels-last TF32 kernel (conv2d_nhwc_tcgen05.cu):
-//   nchw_cat_to_nhwc_pad : cat of up to three NCHW sources -> [B, h+2, w+2, CP] (border and channel padding zero,
-//                          values rounded to TF32 like every operand of that kernel)
+//   nchw_cat_to_nhwc_pad : cat of up to three NCHW sources -> [B, h+2, w+2, CP] (border and channel padding zero;
+//                          round_tf32: values rounded to TF32 for the kernel's plain-TF32 mode)
 //   nhwc_pad_to_nchw     : interior of [B, h+2, w+2, NP], first C channels -> NCHW [B, C, h, w]
 // The tensors are small (52 k pixels at SceneFlow size); one thread per output element.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 nchw_cat_to_nhwc_pad_kernel(const float *__restrict__ s0, const float *__restrict__ s1, const float *__restrict__ s2,
-                            int c0, int c1, int c2, float *__restrict__ out, int h, int w, int CP, long long n)
+                            int c0, int c1, int c2, float *__restrict__ out, int h, int w, int CP, int round_tf32, long long n)
 {
     const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;      // over B*(h+2)*(w+2)*CP
     if (i >= n) return;
@@ -503,7 +503,7 @@ nchw_cat_to_nhwc_pad_kernel(const float *__restrict__ s0, const float *__restric
         if (c < c0) v = __ldg(s0 + (b * c0 + c) * plane + pix);
         else if (c < c0 + c1) v = __ldg(s1 + (b * c1 + (c - c0)) * plane + pix);
         else v = __ldg(s2 + (b * c2 + (c - c0 - c1)) * plane + pix);
-        v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        if (round_tf32) v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
     }
     out[i] = v;
 }
@@ -819,7 +819,7 @@ int decnet_dynup_glue(const float *logits, const float *disp, float *out, int B,
 }
 
 int decnet_nchw_cat_to_nhwc_pad(const float *const *srcs, const int *src_channels, int nsrc, float *out,
-                                int B, int h, int w, int CP, void *stream) {
+                                int B, int h, int w, int CP, int round_tf32, void *stream) {
     DECNET_REQUIRE(srcs && src_channels && out, "null pointer");
     DECNET_REQUIRE(nsrc >= 1 && nsrc <= 3 && B > 0 && h > 0 && w > 0, "bad size");
     int c[3] = {0, 0, 0};
@@ -829,7 +829,7 @@ int decnet_nchw_cat_to_nhwc_pad(const float *const *srcs, const int *src_channel
     DECNET_REQUIRE(CP >= sum, "CP=%d < %d channels", CP, sum);
     const long long n = (long long)B * (h + 2) * (w + 2) * CP;
     nchw_cat_to_nhwc_pad_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(s[0], s[1], s[2], c[0], c[1], c[2],
-                                                                                                     out, h, w, CP, n);
+                                                                                                     out, h, w, CP, round_tf32, n);
     return after_launch("nchw_cat_to_nhwc_pad_kernel");
 }
 

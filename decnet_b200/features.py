@@ -22,7 +22,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .model import Conv2dUnit, Deconv2dUnit, _reset_folded
+from .model import Conv2dUnit, Deconv2dUnit, set_precision
 
 
 class Deconv2dBlock(nn.Module):
@@ -57,7 +57,7 @@ class ASPP(nn.Module):
 class FeatExtNetChannelPlus(nn.Module):
     """Drop-in for modules/submodule.py:245-343 with num_stage = 4, down_scale = 3 (the shipped config)."""
 
-    def __init__(self, base_channels, num_stage=4, down_scale=3):
+    def __init__(self, base_channels, num_stage=4, down_scale=3, precision="fp32"):
         super().__init__()
         assert num_stage == 4 and down_scale == 3, "the shipped configuration (demo.sh:1) is 4 stages, x3"
         c, s = base_channels, down_scale
@@ -81,17 +81,13 @@ class FeatExtNetChannelPlus(nn.Module):
         self.addition_fusion = Conv2dUnit(2 * c * s ** 3, c * s ** 3, 1, stride=1, padding=0)
         self.deconv3 = Deconv2dBlock(c * s ** 3, c * s ** 2, kernel_size=3, stride=3)
         self.out_channels = [c * s ** 3, c * s ** 2, c * s, c]
+        # the strided / wide / ASPP layers at 1/9 and 1/27 resolution have no kernel of ours yet: library layers
+        for m in self.modules():
+            if isinstance(m, (Conv2dUnit, Deconv2dUnit)):
+                m.library_ok = True
+        set_precision(self, precision)
+        self.precision = precision
         self.eval()
-
-    def load_state_dict(self, *a, **kw):
-        res = super().load_state_dict(*a, **kw)
-        _reset_folded(self)
-        return res
-
-    def _apply(self, fn, *a, **kw):
-        out = super()._apply(fn, *a, **kw)
-        _reset_folded(self)
-        return out
 
     @torch.no_grad()
     def forward(self, x):

@@ -3,42 +3,84 @@
 Same class names, constructor arguments, forward signatures and state_dict keys as
 modules/submodule.py (GetCostVolume :428, CostRegNetNoDown :608, disparity_regression :766,
 GenerateSparseMask :347, DynamicUpsampling :566, SoftAttention :593, Refinement :666) so that a
-reference checkpoint loads unchanged and the reference's stage loop can call them.  What runs:
+reference checkpoint loads unchanged and the reference's stage loop can call them.  Every layer of
+the hot path runs on a hand-written sm_100a kernel behind the C ABI (include/decnet_b200.h):
+cost volume, 3-D aggregation (bf16 tcgen05 implicit GEMM), soft-argmin, the 2-D conv stacks of
+a5 / a8 / a13 / a14 (tcgen05 implicit GEMMs on NCHW or zero-bordered channels-last fp32; the few
+1..4-channel layers on a direct fp32 kernel), mask threshold, dynamic-upsampling pack + glue,
+SpaMat / SpaVar, soft-attention pack, sigmoid + blend, disparity warp.  There is ONE route: no library
+(cuDNN) branch, no global switch, no CPU path; a layer no kernel supports raises.
 
-  * hand-written sm_100a kernels (through the C ABI) for everything SURVEY.md section 8 marks
-    "ours": cost volume, 3-D aggregation (tcgen05 implicit GEMM), soft-argmin, mask threshold,
-    dynamic-upsampling pack + glue, SpaMat / SpaVar, soft-attention pack, sigmoid + blend,
-    disparity warp + refinement pack;
-  * cuDNN (through torch) for the tiny 2-D conv stacks the north star leaves to the library
-    (a5 / a8 / a13 / a14 convs), with eval-mode BatchNorm folded into the conv weights.
+`precision` (per unit; `DecompMatching(precision=...)` sets it on every unit) is an arithmetic mode of
+the SAME tensor-core kernels, not a backend:
+  "fp32"  (default) error-compensated 3xTF32: operands split into TF32 hi + lo parts, three MMAs per tap
+          into the fp32 accumulator -> fp32-class results (~2^-22 per product).  The parity gates against
+          the reference's fp32 execution (<= 1e-3, masks bit-exact) run on this mode, and so does bench.py.
+  "tf32"  plain TF32 operands, one MMA per tap: the precision class the reference itself gets from
+          cuDNN on a GPU (torch.backends.cudnn.allow_tf32 defaults to True); faster, gated against
+          cuDNN-TF32's own deviation from fp32.
 
-Inference only (eval-mode BN).  CUDA tensors only: there is no CPU path.
+Inference only (eval-mode BN folded into the weights; a unit in training mode raises).  CUDA tensors only.
 """
 from __future__ import annotations
-
-import math
 
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 from .modules import SpaMat, SpaVar
 
 BN_EPS = 1e-5
-# direct sm_100a kernels for the tiny-channel 2-D convs (section 8f rank 1); False = cuDNN everywhere
-USE_NATIVE_CONV2D = True
-# TF32 tcgen05 implicit GEMM for the GEMM-sized 2-D convs whenever torch.backends.cudnn.allow_tf32 is on
-_CUDNN_FUSED_RELU = True
-USE_TF32_TCGEN05 = True
+PRECISIONS = ("fp32", "tf32")
+
+
+def _sig_of(*mods):
+    """Identity of everything a folded / packed weight cache was built from: (storage pointer, in-place version) of
+    every parameter and buffer of the given modules.  load_state_dict (copy_ bumps the version), .to() / .cuda()
+    (new storage) and in-place edits all change it, whichever parent module they were called on."""
+    sig = []
+    for m in mods:
+        for t in list(m.parameters()) + list(m.buffers()):
+            sig.append((t.data_ptr(), t._version))
+    return tuple(sig)
+
+
+class _Cached:
+    """Weight caches keyed on _sig_of(self): rebuilt whenever a parameter or BN statistic changed."""
+
+    def _cached(self, key, build):
+        store = self.__dict__.setdefault("_wcache", {})
+        sig = _sig_of(self)
+        ent = store.get(key)
+        if ent is None or ent[0] != sig:
+            ent = (sig, build())
+            store[key] = ent
+        return ent[1]
+
+    def _check_inference(self):
+        if self.training:
+            raise RuntimeError(f"{type(self).__name__}: decnet_b200 units are inference-only (eval-mode BatchNorm is folded "
+                               "into the conv weights and no gradient reaches them); call .eval() first")
+
+
+def _split(unit) -> bool:
+    if unit.precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {unit.precision!r}")
+    return unit.precision == "fp32"
 
 
 # --------------------------------------------------------------------------------------
 # units with the reference's parameter names (conv.weight / conv.bias / bn.*)
 # --------------------------------------------------------------------------------------
-class Conv2dUnit(nn.Module):
+class Conv2dUnit(_Cached, nn.Module):
     """Conv2d [+ BN(eval)] [+ ReLU]; keys as modules/submodule.py:15-49."""
+
+    precision = "fp32"
+    # True only for the feature-extractor layers no kernel of ours covers yet (strided / 1x1 wide / ASPP convs at 1/9
+    # and 1/27 resolution, SURVEY.md 8f rank 2): those may run on the library.  Hot-path units never set it.
+    library_ok = False
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, dilation=1, relu=True, bn=True,
                  padding=0):
@@ -47,21 +89,28 @@ class Conv2dUnit(nn.Module):
                               padding=padding, bias=not bn)
         self.bn = nn.BatchNorm2d(out_channels) if bn else None
         self.relu = relu
-        self._folded = None
 
     def folded(self):
-        if self._folded is None:
+        self._check_inference()
+
+        def build():
             w = self.conv.weight.detach()
             b = self.conv.bias.detach() if self.conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
             if self.bn is not None:
                 scale = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + BN_EPS)
                 w = w * scale.view(-1, 1, 1, 1)
                 b = (b - self.bn.running_mean) * scale + self.bn.bias.detach()
-            self._folded = (w.contiguous(), b.contiguous())
-        return self._folded
+            return (w.contiguous(), b.contiguous())
+        return self._cached("folded", build)
+
+    def _same_pad_3x3(self):
+        c = self.conv
+        d = c.dilation[0]
+        return (c.kernel_size == (3, 3) and c.stride == (1, 1) and c.dilation == (d, d) and c.padding == (d, d)
+                and c.groups == 1)
 
     def native(self):
-        """Packed weights for the direct-conv kernel when this layer is one of its shapes (else None)."""
+        """Packed weights for the direct fp32 kernel when this layer is one of its shapes (else None)."""
         c = self.conv
         k, d = c.kernel_size[0], c.dilation[0]
         ok = (c.kernel_size[0] == c.kernel_size[1] and c.stride == (1, 1) and c.dilation[0] == c.dilation[1]
@@ -69,109 +118,113 @@ class Conv2dUnit(nn.Module):
               and ops.conv2d_small_supported(c.in_channels, c.out_channels, k))
         if not ok:
             return None
-        if getattr(self, "_native", None) is None or self._native[0] is not self._folded:
+
+        def build():
             w, b = self.folded()
-            self._native = (self._folded, ops.pack_conv2d_weights(w), b.float().contiguous())
-        return self._native
+            return (ops.pack_conv2d_weights(w), b.float().contiguous())
+        return self._cached("native", build)
 
     def tensor_core(self, x):
-        """Packed weights for the NCHW TF32 tcgen05 kernel when this layer / input is one of its shapes and
-        TF32 is allowed (PyTorch's default for cuDNN convolutions, i.e. what the reference runs), else None.
-        Thin layers (Cin < 8 with one output, or wide dilations on 4 channels) stay on the fp32 direct
+        """Packed weights for the NCHW tcgen05 kernel when this layer / input is one of its shapes, else None.
+        Thin layers (Cin < 8 with one output, or wide dilations on 4 channels) stay on the direct fp32
         kernel, which is faster there (scripts/exp_conv2d_tc.py)."""
         c = self.conv
         d = c.dilation[0]
         cin, cout = c.in_channels, c.out_channels
-        ok = (USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32 and c.kernel_size == (3, 3) and c.stride == (1, 1)
-              and c.dilation == (d, d) and c.padding == (d, d) and c.groups == 1
-              and ((d <= 4 and (cin >= 8 or cout >= 3)) or (d <= 8 and cin >= 8))
-              and ops.conv2d_tf32_supported(cin, cout, x.shape[2], x.shape[3], d))
+        split = _split(self)
+        ok = (self._same_pad_3x3() and ((d <= 4 and (cin >= 8 or cout >= 3)) or (d <= 8 and cin >= 8))
+              and ops.conv2d_tf32_supported(cin, cout, x.shape[2], x.shape[3], d, split))
         if not ok:
             return None
-        if getattr(self, "_tc", None) is None or self._tc[0] is not self._folded:
-            w, b = self.folded()
-            self._tc = (self._folded,) + ops.pack_conv2d_tf32_nchw_weights(w, b)
-        return self._tc
+        return self._cached(("tc", split), lambda: ops.pack_conv2d_tf32_nchw_weights(*self.folded(), split=split))
 
     def forward_cat(self, srcs, w_valid=None):
-        """forward(torch.cat(srcs, 1)) with single-channel maps given as [B,H,W]; on the tensor-core path the
-        concatenation is never materialised (the kernel reads each source through its own tensor map).
+        """forward(torch.cat(srcs, 1)) with single-channel maps given as [B,H,W]; the concatenation is never
+        materialised (the kernel reads each source through its own tensor map).
         w_valid: the tensors are right-padded to a 16-byte row pitch (see pad_pitch); columns >= w_valid of the
         result are zeros."""
         x0 = srcs[0]
         chans = tuple(1 if t.dim() == 3 else t.shape[1] for t in srcs)
         c = self.conv
         d = c.dilation[0]
-        ok = (len(srcs) <= 3 and x0.is_cuda and x0.dtype == torch.float32 and USE_NATIVE_CONV2D and USE_TF32_TCGEN05
-              and torch.backends.cudnn.allow_tf32 and c.kernel_size == (3, 3) and c.stride == (1, 1)
-              and c.dilation == (d, d) and c.padding == (d, d) and c.groups == 1 and sum(chans) == c.in_channels
-              and ops.conv2d_tf32_supported(ops.padded_cat_channels(chans), c.out_channels, x0.shape[-2], x0.shape[-1], d))
+        split = _split(self)
+        ok = (len(srcs) <= 3 and self._same_pad_3x3() and sum(chans) == c.in_channels
+              and ops.conv2d_tf32_supported(ops.padded_cat_channels(chans), c.out_channels, x0.shape[-2], x0.shape[-1], d, split))
         if not ok:
             return self.forward(torch.cat([t.unsqueeze(1) if t.dim() == 3 else t for t in srcs], 1), w_valid=w_valid)
-        cache = getattr(self, "_tc_cat", None)
-        if cache is None or cache[0] is not self._folded or cache[1] != chans:
-            w, b = self.folded()
-            self._tc_cat = (self._folded, chans) + ops.pack_conv2d_tf32_nchw_weights(w, b, chans)
-        return ops.conv2d_tf32_nchw_cat([t.contiguous() for t in srcs], self._tc_cat[2], self._tc_cat[3],
-                                        c.out_channels, d, self.relu, w_valid or 0)
+        wp, bp = self._cached(("tc_cat", split, chans),
+                              lambda: ops.pack_conv2d_tf32_nchw_weights(*self.folded(), chans, split=split))
+        return ops.conv2d_tf32_nchw_cat([t.contiguous() for t in srcs], wp, bp, c.out_channels, d, self.relu,
+                                        w_valid or 0, split=split)
 
     def forward(self, x, addend=None, w_valid=None):
-        fast = x.is_cuda and x.dtype == torch.float32 and USE_NATIVE_CONV2D
-        tc = self.tensor_core(x) if (fast and addend is None) else None
+        if not (x.is_cuda and x.dtype == torch.float32):
+            raise _lib.DecnetError("decnet_b200 units take float32 CUDA tensors (there is no CPU path)")
+        c = self.conv
+        tc = self.tensor_core(x) if addend is None else None
         if tc is not None:
-            c = self.conv
-            return ops.conv2d_tf32_nchw_cat([x.contiguous()], tc[1], tc[2], c.out_channels, c.dilation[0], self.relu,
-                                            w_valid or 0)
+            return ops.conv2d_tf32_nchw_cat([x.contiguous()], tc[0], tc[1], c.out_channels, c.dilation[0], self.relu,
+                                            w_valid or 0, split=_split(self))
         if w_valid:
             out = self.forward(x, addend)
             out[..., w_valid:] = 0                       # keep the pitch padding at zero behind a non-tensor-core layer
             return out
-        nat = self.native() if fast else None
+        nat = self.native()
         if nat is not None:
-            c = self.conv
-            return ops.conv2d_small(x.contiguous(), nat[1], nat[2], c.out_channels, c.kernel_size[0], c.dilation[0],
+            return ops.conv2d_small(x.contiguous(), nat[0], nat[1], c.out_channels, c.kernel_size[0], c.dilation[0],
                                     self.relu, addend)
+        if not self.library_ok:
+            raise _lib.DecnetError(f"Conv2dUnit {c.in_channels}->{c.out_channels} k{c.kernel_size} s{c.stride} d{c.dilation} on "
+                                   f"{tuple(x.shape)}: no decnet_b200 kernel covers this layer (and there is no library fallback)")
+        # feature-extractor layers outside the hot path (library_ok): cuDNN on the folded weights, in this unit's precision
         w, b = self.folded()
-        global _CUDNN_FUSED_RELU
-        if _CUDNN_FUSED_RELU and self.relu and addend is None and x.is_cuda:
-            # library layers (strided / 1x1 / wide convs): cuDNN's fused conv + bias + ReLU, one kernel instead of three
-            try:
-                return torch.cudnn_convolution_relu(x, w, b, self.conv.stride, self.conv.padding, self.conv.dilation, 1)
-            except RuntimeError:
-                _CUDNN_FUSED_RELU = False
-        x = F.conv2d(x, w, b, stride=self.conv.stride, padding=self.conv.padding, dilation=self.conv.dilation)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                        deterministic=torch.backends.cudnn.deterministic, allow_tf32=not _split(self)):
+            if self.relu and addend is None:
+                return torch.cudnn_convolution_relu(x, w, b, c.stride, c.padding, c.dilation, 1)
+            x = F.conv2d(x, w, b, stride=c.stride, padding=c.padding, dilation=c.dilation)
         x = F.relu_(x) if self.relu else x
         return x if addend is None else x + addend.unsqueeze(1)
 
 
-class Deconv2dUnit(nn.Module):
+class Deconv2dUnit(_Cached, nn.Module):
     """ConvTranspose2d [+ BN(eval)] + ReLU; keys as modules/submodule.py:52-87 (bn=False: bias, as in
-    GenerateSparseMask.deconv.0; bn=True: no bias, as in Deconv2dBlock.deconv of the feature extractor)."""
+    GenerateSparseMask.deconv.0; bn=True: no bias, as in Deconv2dBlock.deconv of the feature extractor).
+    Kernel 3, stride 3 (the only shape the model uses): deconv3x3s3_kernel, exact fp32."""
+
+    precision = "fp32"
+    library_ok = False
 
     def __init__(self, in_channels, out_channels, kernel_size, stride, bn=False):
         super().__init__()
         self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=stride, bias=not bn)
         self.bn = nn.BatchNorm2d(out_channels) if bn else None
-        self._folded = None
 
     def folded(self):
-        if self._folded is None:
+        self._check_inference()
+
+        def build():
             w = self.conv.weight.detach()                       # [Cin, Cout, k, k]
             b = self.conv.bias.detach() if self.conv.bias is not None else torch.zeros(w.shape[1], device=w.device)
             if self.bn is not None:
                 scale = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + BN_EPS)
                 w = w * scale.view(1, -1, 1, 1)
                 b = (b - self.bn.running_mean) * scale + self.bn.bias.detach()
-            self._folded = (w.contiguous(), b.contiguous())
-        return self._folded
+            return (w.contiguous(), b.contiguous())
+        return self._cached("folded", build)
 
     def forward(self, x):
+        if not (x.is_cuda and x.dtype == torch.float32):
+            raise _lib.DecnetError("decnet_b200 units take float32 CUDA tensors (there is no CPU path)")
         c = self.conv
         w, b = self.folded()
-        if (USE_NATIVE_CONV2D and x.is_cuda and x.dtype == torch.float32 and c.kernel_size == (3, 3)
-                and c.stride == (3, 3) and c.padding == (0, 0) and ops.deconv3x3s3_supported(c.out_channels)):
+        if c.kernel_size == (3, 3) and c.stride == (3, 3) and c.padding == (0, 0) and ops.deconv3x3s3_supported(c.out_channels):
             return ops.deconv3x3s3(x.contiguous(), w, b, True)
-        return F.relu_(F.conv_transpose2d(x, w, b, stride=c.stride))
+        if not self.library_ok:
+            raise _lib.DecnetError(f"Deconv2dUnit {c.in_channels}->{c.out_channels}: no decnet_b200 kernel covers this layer")
+        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                        deterministic=torch.backends.cudnn.deterministic, allow_tf32=not _split(self)):
+            return F.relu_(F.conv_transpose2d(x, w, b, stride=c.stride))
 
 
 class Conv3dUnit(nn.Module):
@@ -193,29 +246,13 @@ def pad_pitch(t):
     The tensor-core Conv2d reads images through TMA, which needs 16-byte row strides: a KITTI-sized level
     (W = 1269, 423, 141) runs its conv stacks on such padded copies and crops the result (unpad_pitch)."""
     W = t.shape[-1]
-    if W % 4 == 0 or not (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32 and t.is_cuda):
+    if W % 4 == 0:
         return t, None
     return F.pad(t, (0, 4 - W % 4)), W
 
 
 def unpad_pitch(t, w_valid):
     return t if w_valid is None else t[..., :w_valid].contiguous()
-
-
-def _reset_folded(module):
-    for m in module.modules():
-        if hasattr(m, "_folded"):
-            m._folded = None
-        if hasattr(m, "_packed"):
-            m._packed = None
-        if hasattr(m, "_native"):
-            m._native = None
-        if hasattr(m, "_tc"):
-            m._tc = None
-        if hasattr(m, "_tc_cat"):
-            m._tc_cat = None
-        if hasattr(m, "_head"):
-            m._head = None
 
 
 # --------------------------------------------------------------------------------------
@@ -255,16 +292,12 @@ def disparity_regression(cost_vol, disp_samples=None):
 # --------------------------------------------------------------------------------------
 # a3: 3-D aggregation
 # --------------------------------------------------------------------------------------
-class CostRegNetNoDown(nn.Module):
-    """Drop-in for modules/submodule.py:608-662 (cost_func 'cor').  forward([B,C,D,H,W]) -> [B,D,H,W].
+class CostRegNetNoDown(_Cached, nn.Module):
+    """Drop-in for modules/submodule.py:608-662 (cost_func 'cor').  forward([B,C,D,H,W]) -> [B,D,H,W] on the
+    hand-written bf16 implicit-GEMM kernel (decnet_conv3d_bf16: tcgen05, fp32 accumulation in TMEM); the north star's
+    tolerance for this stage is 0.05 px EPE on the regressed disparity."""
 
-    `impl`:
-      "tcgen05"  hand-written bf16 implicit-GEMM kernels (decnet_conv3d_*), fp32 accumulate
-      "cudnn"    torch/cuDNN Conv3d with folded BN (fp32 or bf16 per `dtype`): bring-up/compare only
-    """
-
-    def __init__(self, in_channels, base_channels=None, cost_func="cor", down_scale=3, impl="tcgen05",
-                 dtype=torch.float32):
+    def __init__(self, in_channels, base_channels=None, cost_func="cor", down_scale=3):
         super().__init__()
         if cost_func != "cor":
             raise NotImplementedError("cost_func 'cor' only")
@@ -272,49 +305,20 @@ class CostRegNetNoDown(nn.Module):
         self.conv0 = nn.Sequential(Conv3dUnit(c, c), Conv3dUnit(c, c))
         self.conv1 = nn.Sequential(Conv3dUnit(c, c), Conv3dUnit(c, c), Conv3dUnit(c, c))
         self.conv2 = nn.Sequential(Conv3dUnit(c, c), Conv3dUnit(c, c), Conv3dUnit(c, 1, relu=False))
-        self.impl = impl
-        self.dtype = dtype
-        self._folded = None
-        self._packed = None
 
     def units(self):
         return [*self.conv0, *self.conv1, *self.conv2]
 
-    # ---- cuDNN bring-up path --------------------------------------------------------
-    def _fold(self):
-        if self._folded is None:
-            out = []
-            for u in self.units():
-                s, b = u.scale_bias()
-                w = (u.conv.weight.detach() * s.view(-1, 1, 1, 1, 1)).to(self.dtype)
-                out.append((w.contiguous(memory_format=torch.channels_last_3d), b.to(self.dtype), u.relu))
-            self._folded = out
-        return self._folded
-
-    def _forward_cudnn(self, x):
-        f = self._fold()
-        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last_3d)
-
-        def run(x, i):
-            w, b, relu = f[i]
-            y = F.conv3d(x, w, b, padding=1)
-            return F.relu_(y) if relu else y
-        x = run(x, 0); o0 = run(x, 1)
-        x = run(o0, 2); x = run(x, 3); x = run(x, 4) + o0
-        x = run(x, 5); x = run(x, 6); x = run(x, 7)
-        return x.squeeze(1).float().contiguous()
-
     def forward(self, x):
-        if self.impl == "cudnn":
-            return self._forward_cudnn(x)
+        self._check_inference()
         from . import conv3d
         return conv3d.cost_regularizer_forward(self, x)
 
 
 # --------------------------------------------------------------------------------------
-# a5: learned lost-detail detector (convs stay cuDNN)
+# a5: learned lost-detail detector
 # --------------------------------------------------------------------------------------
-class GenerateSparseMask(nn.Module):
+class GenerateSparseMask(_Cached, nn.Module):
     """Drop-in for modules/submodule.py:347-372."""
 
     def __init__(self, in_channels, down_scale=3):
@@ -327,10 +331,12 @@ class GenerateSparseMask(nn.Module):
                                   Conv2dUnit(3, 1, 1, padding=0, relu=False))
 
     def forward(self, cur_fea, pre_fea):
-        pre = self.deconv(pre_fea)
-        cur = self.conv_sub(cur_fea)
+        cur_fea, wv = pad_pitch(cur_fea)
+        pre = self.deconv[1](pad_pitch(self.deconv[0](pre_fea))[0], w_valid=wv)
+        cur = self.conv_sub[1](self.conv_sub[0](cur_fea, w_valid=wv), w_valid=wv)
         res = (cur - pre) ** 2
-        return self.conv(res).squeeze(1), cur, pre
+        logit = self.conv[1](self.conv[0](res, w_valid=wv), w_valid=wv)
+        return unpad_pitch(logit, wv).squeeze(1), unpad_pitch(cur, wv), unpad_pitch(pre, wv)
 
     def masks_pair(self, cur_l, pre_l, cur_r, pre_r, thold):
         """Left and right masks `sigmoid(forward(.)) > thold` with the tail fused: one kernel for both
@@ -345,69 +351,68 @@ class GenerateSparseMask(nn.Module):
         cr = self.conv_sub[1](self.conv_sub[0](cur_r, w_valid=wv), w_valid=wv)
         rl, rr = ops.sqdiff_pair(cl, pl, cr, pr)
         xl, xr = self.conv[0](rl, w_valid=wv), self.conv[0](rr, w_valid=wv)
-        if getattr(self, "_head", None) is None or self._head[0] is not self.conv[1]._folded:
+
+        def build():
             w, b = self.conv[1].folded()                    # [1,3,1,1], [1]
-            self._head = (self.conv[1]._folded, [float(v) for v in w.flatten().cpu()], float(b.cpu()))
-        ml, mr = ops.detail_head(xl.contiguous(), xr.contiguous(), self._head[1], self._head[2],
-                                 ops.sigmoid_logit_threshold(thold, xl.device))
+            return ([float(v) for v in w.flatten().cpu()], float(b.cpu()))
+        w3, b1 = self._cached("head", build)
+        ml, mr = ops.detail_head(xl.contiguous(), xr.contiguous(), w3, b1, ops.sigmoid_logit_threshold(thold, xl.device))
         return unpad_pitch(ml, wv), unpad_pitch(mr, wv)
 
 
 # --------------------------------------------------------------------------------------
 # a8: dynamic up-sampling
 # --------------------------------------------------------------------------------------
-class DynamicUpsampling(nn.Module):
-    """Drop-in for modules/submodule.py:566-589: pack kernel -> 3 cuDNN convs -> glue kernel."""
+class DynamicUpsampling(_Cached, nn.Module):
+    """Drop-in for modules/submodule.py:566-589: channels-last pack kernel -> 3 tcgen05 convs on zero-bordered
+    channels-last fp32 (conv2d_nhwc_halo_kernel) -> softmax / gather / pixel-shuffle glue kernel."""
+
+    precision = "fp32"
 
     def __init__(self, in_channels, down_scale=3):
         super().__init__()
         assert down_scale == 3, "the reference hard-codes x3 (SURVEY.md D1)"
         n = down_scale ** 2 * 9
-        self._packed = None
         self.weight_learning = nn.Sequential(Conv2dUnit(in_channels * 9 + 1, n, 3, padding=1),
                                              Conv2dUnit(n, n, 3, padding=1),
                                              Conv2dUnit(n, n, 3, padding=1, relu=False))
 
-    def _tf32_pack(self):
-        """Weights of the three convs for the TF32 tcgen05 implicit GEMM (cached; reset with the folds)."""
-        if getattr(self, "_packed", None) is None:
+    def _pack(self):
+        """(cp0, [(w_packed, bias, relu)] of the three convs) for the channels-last kernel, in this unit's precision."""
+        self._check_inference()
+        split = _split(self)
+
+        def build():
             units = list(self.weight_learning)
             cin0 = units[0].conv.in_channels
             cp = (cin0 + 7) // 8 * 8
             packed = []
             for u in units:
                 w, b = u.folded()
-                wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp)
+                wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp, split=split)
                 packed.append((wp, bp, u.relu))
                 cp = np_
-            self._packed = ((cin0 + 7) // 8 * 8, packed)
-        return self._packed
+            return ((cin0 + 7) // 8 * 8, packed)
+        return self._cached(("pack", split), build)
 
     def prepack(self, left_fea):
-        """The feature channels of the conv input (everything but the disparity channel), or None when the TF32
-        tensor-core route is off.  Independent of the disparity: the stage loop runs it ahead, on its second stream."""
-        if USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32:
-            cp0, _ = self._tf32_pack()
-            return ops.dynup_pack_nhwc(None, left_fea.contiguous(), cp0, pad=True)
-        return None
+        """The feature channels of the conv input (everything but the disparity channel).  Independent of the
+        disparity: the stage loop runs it ahead, on its second stream."""
+        cp0, _ = self._pack()
+        return ops.dynup_pack_nhwc(None, left_fea.contiguous(), cp0, round_tf32=not _split(self), pad=True)
 
     def forward(self, disp_map, left_fea, packed=None):
         disp_map = disp_map.contiguous()
-        if USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32:
-            # TF32 allowed (PyTorch's default for convolutions): the three 81-channel convs run as tcgen05
-            # implicit GEMMs on channels-last fp32, between channels-last pack / glue kernels
-            cp0, packed_w = self._tf32_pack()
-            # the tensors carry a one-pixel zero border, so one TMA fill per row tap serves the three column taps
-            if packed is not None:
-                x = ops.dynup_set_disp_nhwc(packed, disp_map, pad=True)        # feature channels packed ahead (prepack)
-            else:
-                x = ops.dynup_pack_nhwc(disp_map, left_fea.contiguous(), cp0, pad=True)
-            for i, (wp, bp, relu) in enumerate(packed_w):
-                x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=i + 1 < len(packed_w))
-            return ops.dynup_glue_nhwc(x, disp_map, pad=True)
-        x = ops.dynup_pack(disp_map, left_fea.contiguous())
-        logits = self.weight_learning(x)
-        return ops.dynup_glue(logits.contiguous(), disp_map)
+        split = _split(self)
+        cp0, packed_w = self._pack()
+        # the tensors carry a one-pixel zero border, so one TMA fill per row tap serves the three column taps
+        if packed is not None:
+            x = ops.dynup_set_disp_nhwc(packed, disp_map, round_tf32=not split, pad=True)   # features packed ahead (prepack)
+        else:
+            x = ops.dynup_pack_nhwc(disp_map, left_fea.contiguous(), cp0, round_tf32=not split, pad=True)
+        for i, (wp, bp, relu) in enumerate(packed_w):
+            x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=(not split) and i + 1 < len(packed_w), split=split)
+        return ops.dynup_glue_nhwc(x, disp_map, pad=True)
 
 
 # --------------------------------------------------------------------------------------
@@ -415,7 +420,7 @@ class DynamicUpsampling(nn.Module):
 # --------------------------------------------------------------------------------------
 class SoftAttention(nn.Module):
     """Drop-in for modules/submodule.py:593-604.  forward(x=[B,C+4,H,W]) -> sigmoid mask like the
-    reference; `logits()` + ops.blend() is the fused route the pipeline uses."""
+    reference; `logits_cat()` + ops.blend() is the fused route the pipeline uses."""
 
     def __init__(self, in_channels, base_channels):
         super().__init__()
@@ -424,7 +429,10 @@ class SoftAttention(nn.Module):
                                   Conv2dUnit(base_channels, 1, 3, padding=1, relu=False))
 
     def logits(self, x):
-        return self.conv(x)
+        x, wv = pad_pitch(x)
+        for u in self.conv:
+            x = u(x, w_valid=wv)
+        return unpad_pitch(x, wv)
 
     def logits_cat(self, left_fea, aux):
         """logits(cat(left_fea, aux)) with aux = [dense, sparse, left_mask, -var] as one [B,4,H,W] tensor."""
@@ -434,7 +442,7 @@ class SoftAttention(nn.Module):
         return unpad_pitch(self.conv[2](self.conv[1](x, w_valid=wv), w_valid=wv), wv)
 
     def forward(self, x):
-        return torch.sigmoid(self.conv(x))
+        return torch.sigmoid(self.logits(x))
 
 
 # --------------------------------------------------------------------------------------
@@ -443,8 +451,11 @@ class SoftAttention(nn.Module):
 _REFINE_DIL = {0: (1,) * 6, 1: (1,) * 6, 2: (2, 1, 4, 1, 6, 1), 3: (3, 1, 6, 1, 9, 1)}
 
 
-class Refinement(nn.Module):
-    """Drop-in for modules/submodule.py:666-762: warp+pack kernel -> 7 cuDNN convs -> add."""
+class Refinement(_Cached, nn.Module):
+    """Drop-in for modules/submodule.py:666-762: warp kernel -> 7 convs (first one reading (left, warped, disp) as
+    three sources) -> add."""
+
+    precision = "fp32"
 
     def __init__(self, in_channels, base_channels=None, stage_id=-1, down_scale=3):
         super().__init__()
@@ -456,53 +467,71 @@ class Refinement(nn.Module):
         self.conv = nn.Sequential(*layers)
 
     def _wide_pack(self, n_wide):
-        """Weights of the first `n_wide` layers for the zero-bordered channels-last TF32 kernel (cached)."""
-        if getattr(self, "_packed", None) is None:
+        """Weights of the first `n_wide` layers for the zero-bordered channels-last kernel, in this unit's precision."""
+        self._check_inference()
+        split = _split(self)
+
+        def build():
             units = list(self.conv)
             cp = (units[0].conv.in_channels + 7) // 8 * 8
             packed = []
             for u in units[:n_wide]:
                 w, b = u.folded()
-                wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp)
+                wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp, split=split)
                 packed.append((wp, bp, u.relu))
                 cp = np_
-            self._packed = ((units[0].conv.in_channels + 7) // 8 * 8, packed)
-        return self._packed
+            return ((units[0].conv.in_channels + 7) // 8 * 8, packed)
+        return self._cached(("wide", split, n_wide), build)
+
+    def _is_wide(self):
+        units = list(self.conv)
+        return units[0].conv.out_channels >= 48 and all(u.conv.dilation == (1, 1) for u in units[:4])
+
+    def _wide_head(self, srcs):
+        """Wide level (1/9: 145 -> 72 -> 72 -> 72 -> 36 channels): GEMM-sized layers, too wide for the resident-weight NCHW
+        kernel -> zero-bordered channels-last kernel between two layout bridges; returns the NCHW input of layer 4."""
+        split = _split(self)
+        cp0, packed = self._wide_pack(4)
+        x = ops.nchw_cat_to_nhwc_pad(srcs, cp0, round_tf32=not split)
+        for i, (wp, bp, relu) in enumerate(packed):
+            x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=(not split) and i + 1 < len(packed), split=split)
+        return ops.nhwc_pad_to_nchw(x, self.conv[3].conv.out_channels)
+
+    def _tail(self, x, disp_map, start, wv):
+        for unit in list(self.conv)[start:-1]:
+            x = unit(x, w_valid=wv)
+        residual = unpad_pitch(self.conv[-1](x, w_valid=wv), wv).squeeze(1)
+        return disp_map + residual, residual
+
+    def forward_packed(self, packed, disp_map):
+        """The conv stack on an already packed input cat(left, warped right, disp) [B,2C+1,H,W] (row-band mode: the
+        warp needs global row coordinates, decnet_refine_pack_rows) -> (disp + residual, residual)."""
+        disp_map = disp_map.contiguous()
+        if self._is_wide():
+            x, wv = pad_pitch(self._wide_head([packed.contiguous()]))
+            return self._tail(x, disp_map, 4, wv)
+        x, wv = pad_pitch(packed.contiguous())
+        return self._tail(x, disp_map, 0, wv)
 
     def forward(self, left_fea, right_fea, disp_map):
         disp_map = disp_map.contiguous()
         units = list(self.conv)
         c0 = units[0].conv
         C = left_fea.shape[1]
-        if (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32 and C >= 48
-                and all(u.conv.dilation == (1, 1) for u in units[:4])):
-            # wide level (1/9: 145 -> 72 -> 72 -> 72 -> 36 channels): GEMM-sized layers, too wide for the resident-weight NCHW
-            # kernel -> zero-bordered channels-last TF32 kernel between two layout bridges, then back to NCHW for the rest
-            cp0, packed = self._wide_pack(4)
+        split = _split(self)
+        if self._is_wide():
             warped = ops.warp_bilinear(right_fea.contiguous(), disp_map)
-            x = ops.nchw_cat_to_nhwc_pad([left_fea.contiguous(), warped, disp_map], cp0)
-            for i, (wp, bp, relu) in enumerate(packed):
-                x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=i + 1 < len(packed))
-            x = ops.nhwc_pad_to_nchw(x, units[3].conv.out_channels)
-            for unit in units[4:-1]:
-                x = unit(x)
-            residual = self.conv[-1](x).squeeze(1)
-            return disp_map + residual, residual
+            x, wv = pad_pitch(self._wide_head([left_fea.contiguous(), warped, disp_map]))
+            return self._tail(x, disp_map, 4, wv)
         Wp = (left_fea.shape[3] + 3) // 4 * 4
-        wv = None
-        if (USE_NATIVE_CONV2D and USE_TF32_TCGEN05 and torch.backends.cudnn.allow_tf32
-                and ops.conv2d_tf32_supported(ops.padded_cat_channels((C, C, 1)), c0.out_channels, left_fea.shape[2],
-                                              Wp, c0.dilation[0])):
+        if ops.conv2d_tf32_supported(ops.padded_cat_channels((C, C, 1)), c0.out_channels, left_fea.shape[2], Wp,
+                                     c0.dilation[0], split):
             # first conv reads (left, warped right, disparity) as three sources: only the warp is materialised
             warped = ops.warp_bilinear(right_fea.contiguous(), disp_map)
             lp, wv = pad_pitch(left_fea.contiguous())
             x = units[0].forward_cat([lp, pad_pitch(warped)[0], pad_pitch(disp_map)[0]], w_valid=wv)
-        else:
-            x = units[0](ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map))
-        for unit in units[1:-1]:
-            x = unit(x, w_valid=wv)
-        residual = unpad_pitch(self.conv[-1](x, w_valid=wv), wv).squeeze(1)
-        return disp_map + residual, residual
+            return self._tail(x, disp_map, 1, wv)
+        return self.forward_packed(ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map), disp_map)
 
 
 # --------------------------------------------------------------------------------------
@@ -517,10 +546,11 @@ class DecompMatching(nn.Module):
     forward(left_feats, right_feats, left_mask_list=None, right_mask_list=None, is_check=False)
       left_feats/right_feats: {"stage0".."stage3"} NCHW fp32 CUDA tensors (C = 216,72,24,8)
       returns [pred] like the reference's inference path, or (pred, taps) with is_check.
+    precision: "fp32" (3xTF32 tensor-core convs, fp32-class: the parity-gated default) or "tf32" (see module docstring).
     """
 
     def __init__(self, max_disp=216, base_channels=8, num_stage=4, down_scale=3, skip_stage_id=4,
-                 use_detail=True, thold=0.9, conv3d_impl="tcgen05", channels=None):
+                 use_detail=True, thold=0.9, channels=None, precision="fp32"):
         super().__init__()
         assert down_scale == 3 and num_stage == 4, "shipped configuration (demo.sh:1)"
         assert max_disp % (down_scale ** (num_stage - 1)) == 0, "max_disp must be a multiple of 27"
@@ -532,25 +562,25 @@ class DecompMatching(nn.Module):
         self.get_cost_volume = GetCostVolume("homgrp", "cor")
         self.sparse_matching = nn.ModuleList([SpaMat() for _ in range(num_stage - 1)])
         self.sparse_var = nn.ModuleList([SpaVar() for _ in range(num_stage - 1)])
-        self.cost_regularizer = CostRegNetNoDown(ch[0], ch[0] * 2, "cor", down_scale, impl=conv3d_impl)
+        self.cost_regularizer = CostRegNetNoDown(ch[0], ch[0] * 2, "cor", down_scale)
         self.detail_detection = nn.ModuleList([GenerateSparseMask(ch[i + 1], down_scale) for i in range(num_stage - 1)])
         self.dynamic_upsampling = nn.ModuleList([DynamicUpsampling(ch[i + 1], down_scale) for i in range(num_stage - 1)])
         self.soft_attention = nn.ModuleList([SoftAttention(ch[i + 1] + 4, base_channels) for i in range(num_stage - 1)])
         self.refinement = nn.ModuleList([Refinement(ch[i + 1], base_channels // (2 ** i), stage_id=i + 1,
                                                     down_scale=down_scale) for i in range(num_stage - 1)])
+        self.set_precision(precision)
         self.eval()
+
+    def set_precision(self, precision):
+        """Arithmetic mode of every 2-D conv unit: "fp32" (3xTF32) or "tf32".  Returns self."""
+        set_precision(self, precision)
+        self.precision = precision
+        return self
 
     def load_state_dict(self, state_dict, strict=False, **kw):
         sd = {k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()}   # demo.py:124-135
         sd = {k: v for k, v in sd.items() if not k.startswith("feature_extractor")}
-        res = super().load_state_dict(sd, strict=strict, **kw)
-        _reset_folded(self)
-        return res
-
-    def _apply(self, fn, *a, **kw):
-        out = super()._apply(fn, *a, **kw)
-        _reset_folded(self)
-        return out
+        return super().load_state_dict(sd, strict=strict, **kw)
 
     # Masks (a5/a6) and the sparse ops (a9/a10) of every level depend on the features only, not on the disparity
     # coming up from the coarser level: they run on a second stream, forked at the start of forward() and joined
@@ -559,18 +589,27 @@ class DecompMatching(nn.Module):
     # parallel branches.  `overlap = False` restores the single-stream order.
     overlap = True
 
+    def _side_stream(self, main):
+        """One side stream per (device, caller's stream): two callers on different streams never share it."""
+        pool = self.__dict__.setdefault("_sides", {})
+        key = (main.device, main.cuda_stream)
+        if key not in pool:
+            pool[key] = torch.cuda.Stream(main.device)
+        return pool[key]
+
     @torch.no_grad()
-    def forward(self, left_feats, right_feats, left_mask_list=None, right_mask_list=None, is_check=False):
+    def forward(self, left_feats, right_feats, left_mask_list=None, right_mask_list=None, is_check=False,
+                coarse_pred=None):
+        """coarse_pred (test hook): a [B,H/27,W/27] disparity that replaces the result of the coarse dense stage, so the
+        fp32-class stages can be checked against the reference without the bf16 aggregation's 0.05 px tolerance."""
         taps = {k: [] for k in ("pred", "dense", "sparse", "var", "soft_mask", "fusion", "residual",
                                 "left_mask", "right_mask", "left_detail", "right_detail")} if is_check else None
         pred = None
-        branch = events = packs = pack_events = side = None
+        branch = events = packs = pack_events = side = main = None
         if self.overlap and not is_check:
             dev = left_feats["stage0"].device
             main = torch.cuda.current_stream(dev)
-            if getattr(self, "_side", None) is None or self._side.device != dev:
-                self._side = torch.cuda.Stream(dev)
-            side = self._side
+            side = self._side_stream(main)
             side.wait_stream(main)                       # fork: the features are ready on the main stream
             with torch.cuda.stream(side):
                 branch, events, packs, pack_events = [], [], [], []
@@ -579,6 +618,7 @@ class DecompMatching(nn.Module):
                     pk = None
                     if s < self.skip_stage_id:
                         pk = self.dynamic_upsampling[s - 1].prepack(left_feats[f"stage{s}"])
+                        pk.record_stream(main)           # allocated in the side stream's pool, consumed on the main stream
                     ev = None
                     if pk is not None:
                         ev = torch.cuda.Event()
@@ -598,6 +638,8 @@ class DecompMatching(nn.Module):
                     else:
                         lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
                     sparse, var, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm, rm, D)
+                    for t in (lm, rm, sparse, var):
+                        t.record_stream(main)
                     branch.append((lm, rm, sparse, var))
                     ev = torch.cuda.Event()
                     ev.record(side)
@@ -608,9 +650,12 @@ class DecompMatching(nn.Module):
             Rf = right_feats[f"stage{s}"].contiguous()
             D = self.max_disp // (self.down_scale ** (self.num_stage - s - 1))
             if s == 0:
-                pred, cost = self.dense_stage(Lf, Rf, D)
-                if is_check:
-                    taps["cost"] = cost
+                if coarse_pred is not None:
+                    pred = coarse_pred.contiguous()
+                else:
+                    pred, cost = self.dense_stage(Lf, Rf, D)
+                    if is_check:
+                        taps["cost"] = cost
                 pre_l, pre_r = Lf, Rf
             elif s >= self.skip_stage_id:
                 # SparseDenseNetRefinementMask.py:143-144 (Middlebury's finest level); single ATen kernel
@@ -619,9 +664,9 @@ class DecompMatching(nn.Module):
                 l = s - 1
                 if branch is not None:
                     if pack_events[l] is not None:
-                        torch.cuda.current_stream(Lf.device).wait_event(pack_events[l])
+                        main.wait_event(pack_events[l])
                     dense = self.dynamic_upsampling[l](pred, Lf, packed=packs[l])
-                    torch.cuda.current_stream(Lf.device).wait_event(events[l])      # join for this level
+                    main.wait_event(events[l])                                     # join for this level
                     lm, rm, sparse, var = branch[l]
                 else:
                     if self.use_detail:
@@ -647,18 +692,23 @@ class DecompMatching(nn.Module):
             if is_check:
                 taps["pred"].append(pred)
         if side is not None:
-            # join (a captured graph needs every forked stream back).  The side stream's tensors are consumed on the
-            # main stream; their memory returns to the side stream's pool and is reused only by the next forward's
-            # branch, which starts behind that forward's fork, i.e. behind everything enqueued here.
-            torch.cuda.current_stream(pred.device).wait_stream(side)
+            main.wait_stream(side)                       # join (a captured graph needs every forked stream back)
         return (pred, taps) if is_check else [pred]
 
     def dense_stage(self, Lf, Rf, D):
         """a1-a4: cost volume -> 3-D aggregation -> soft-argmin.  Returns (pred [B,H,W], cost [B,D,H,W])."""
-        if self.cost_regularizer.impl == "tcgen05":
-            from . import conv3d
-            cost = conv3d.dense_cost(self.cost_regularizer, Lf, Rf, D)
-        else:
-            vol = ops.cost_volume(Lf, Rf, D)
-            cost = self.cost_regularizer(vol)
+        from . import conv3d
+        self.cost_regularizer._check_inference()
+        cost = conv3d.dense_cost(self.cost_regularizer, Lf, Rf, D)
         return ops.softargmin(cost), cost
+
+
+def set_precision(module, precision):
+    """Sets the conv arithmetic mode ("fp32" = 3xTF32, "tf32") on every decnet_b200 unit below `module` -- also for a
+    reference model whose sub-modules were swapped for ours."""
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
+    for m in module.modules():
+        if isinstance(m, (Conv2dUnit, Deconv2dUnit, DynamicUpsampling, Refinement)):
+            m.precision = precision
+    return module

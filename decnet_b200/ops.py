@@ -445,14 +445,26 @@ def deconv3x3s3(x, w, bias, relu=True):
 # --------------------------------------------------------------------------------------
 # GEMM-sized 3x3 Conv2d on tensor cores (TF32 tcgen05 implicit GEMM, channels-last)
 # --------------------------------------------------------------------------------------
-def pack_conv2d_tf32_weights(w, bias, cp):
-    """[Cout,Cin,3,3] (+ bias [Cout]) -> ([9][NP][cp] fp32, bias [NP]); NP = Cout rounded up to 16."""
+def rna_tf32(t):
+    """Round an fp32 tensor to TF32 (nearest, ties away: cvt.rna) -- the MMA itself would truncate the low 13 mantissa bits."""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def split_tf32(t):
+    """(hi, lo) with hi = rna_tf32(t), lo = rna_tf32(t - hi): the operand split of the 3xTF32 ("fp32-class") conv mode
+    (t - hi is exact in fp32; hi*hi' + hi*lo' + lo*hi' reproduces the fp32 product to ~2^-22 relative)."""
+    hi = rna_tf32(t)
+    return hi, rna_tf32(t - hi)
+
+
+def pack_conv2d_tf32_weights(w, bias, cp, split=False):
+    """[Cout,Cin,3,3] (+ bias [Cout]) -> ([9][NP][cp] fp32, bias [NP]); NP = Cout rounded up to 16.
+    split: [18][NP][cp] -- taps 0-8 the TF32 hi parts, 9-17 the lo parts (3xTF32 mode of the halo kernel)."""
     cout, cin = w.shape[:2]
     np_ = (cout + 15) // 16 * 16
     out = torch.zeros((9, np_, cp), dtype=torch.float32, device=w.device)
     out[:, :cout, :cin] = w.float().permute(2, 3, 0, 1).reshape(9, cout, cin)
-    # round to TF32 (nearest, ties away: cvt.rna) -- the MMA would truncate the low 13 mantissa bits
-    out = ((out.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    out = torch.cat(split_tf32(out), 0) if split else rna_tf32(out)
     b = torch.zeros(np_, dtype=torch.float32, device=w.device)
     b[:cout] = bias.float()
     return out.contiguous(), b.contiguous(), np_
@@ -472,18 +484,19 @@ def conv2d_tf32_nhwc(x_nhwc, w_packed, bias, relu, round_out=False):
 # --------------------------------------------------------------------------------------
 # small 3x3 Conv2d on NCHW fp32 tensors, TF32 tensor cores with pixels as the MN-major M dimension
 # --------------------------------------------------------------------------------------
-def conv2d_tf32_supported(cin, cout, H, W, dilation=1):
-    return bool(_lib.lib().decnet_conv2d_tf32_supported(int(cin), int(cout), int(H), int(W), int(dilation)))
+def conv2d_tf32_supported(cin, cout, H, W, dilation=1, split=False):
+    return bool(_lib.lib().decnet_conv2d_tc_supported(int(cin), int(cout), int(H), int(W), int(dilation), 1 if split else 0))
 
 
 def padded_cat_channels(src_channels):
     return sum((c + 7) // 8 * 8 for c in src_channels)
 
 
-def pack_conv2d_tf32_nchw_weights(w, bias, src_channels=None):
+def pack_conv2d_tf32_nchw_weights(w, bias, src_channels=None, split=False):
     """[Cout,Cin,3,3] (+ bias [Cout]) -> (rows of 32 floats as include/decnet_b200.h describes, bias [CP]).
     src_channels: the input is a concatenation of tensors with these channel counts (sum = Cin), each
-    padded to whole 8-channel chunks for decnet_conv2d_tf32_nchw_cat."""
+    padded to whole 8-channel chunks for decnet_conv2d_tc_nchw_cat.
+    split: the hi rows followed by the lo rows (3xTF32 mode)."""
     cout, cin = w.shape[:2]
     wf = w.float()
     if src_channels is not None and len(src_channels) > 1:
@@ -503,8 +516,8 @@ def pack_conv2d_tf32_nchw_weights(w, bias, src_channels=None):
         bm[:, :cin, kw * cp: kw * cp + cout] = wf[:, :, :, kw].permute(2, 1, 0)       # [kh][ci][co]
     # -> [kh][chunk][atom][k][n]
     out = bm.view(3, nck, 8, natoms, 32).permute(0, 1, 3, 2, 4).contiguous()
-    out = ((out.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)            # cvt.rna to TF32
-    assert out.numel() == _lib.lib().decnet_conv2d_tf32_packed_floats(int(cin), int(cout))
+    out = torch.cat(split_tf32(out), 0) if split else rna_tf32(out)                   # cvt.rna to TF32
+    assert out.numel() == _lib.lib().decnet_conv2d_tc_packed_floats(int(cin), int(cout), 1 if split else 0)
     b = torch.zeros(cp, dtype=torch.float32, device=w.device)
     b[:cout] = bias.float()
     return out.contiguous(), b.contiguous()
@@ -519,8 +532,9 @@ def conv2d_tf32_nchw(x, w_packed, bias_padded, cout, dilation=1, relu=False):
     return out
 
 
-def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=False, w_valid=0):
-    """Conv over torch.cat(srcs, 1) without building it; srcs: 1..3 tensors [B,Ci,H,W] or [B,H,W] (one channel)."""
+def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=False, w_valid=0, split=False):
+    """Conv over torch.cat(srcs, 1) without building it; srcs: 1..3 tensors [B,Ci,H,W] or [B,H,W] (one channel).
+    split: 3xTF32 (w_packed from pack_conv2d_tf32_nchw_weights(split=True))."""
     import ctypes
     x0 = srcs[0]
     _chk("srcs[0]", x0)
@@ -536,9 +550,9 @@ def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=Fal
     ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
     cs = (ctypes.c_int * n)(*chans)
     out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x0.device)
-    _call("decnet_conv2d_tf32_nchw_cat", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
+    _call("decnet_conv2d_tc_nchw_cat", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
           w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(), B, int(cout), H, W, int(dilation), 1 if relu else 0,
-          int(w_valid))
+          int(w_valid), 1 if split else 0)
     return out
 
 
@@ -588,19 +602,23 @@ def conv2d_tf32_rows_nchw_cat(srcs, w_compact, bias8, cout, dilation=1, relu=Fal
     return out
 
 
-def conv2d_tf32_nhwc_halo(x_pad, w_packed, bias, relu, round_out=False):
-    """x fp32 [B,h+2,w+2,cp] channels-last with a zero border -> fp32 [B,h+2,w+2,NP] (border zeros)."""
+def conv2d_tf32_nhwc_halo(x_pad, w_packed, bias, relu, round_out=False, split=False):
+    """x fp32 [B,h+2,w+2,cp] channels-last with a zero border -> fp32 [B,h+2,w+2,NP] (border zeros).
+    split: 3xTF32 -- x unrounded fp32, w_packed [18][NP][cp] from pack_conv2d_tf32_weights(split=True)."""
     _chk("x_pad", x_pad)
     B, hp, wp, cp = x_pad.shape
     np_ = w_packed.shape[1]
+    if w_packed.shape[0] != (18 if split else 9) or w_packed.shape[2] != cp:
+        raise ValueError(f"w_packed {tuple(w_packed.shape)} does not match cp={cp}, split={split}")
     out = torch.empty((B, hp, wp, np_), dtype=torch.float32, device=x_pad.device)
-    _call("decnet_conv2d_tf32_nhwc_halo", x_pad, x_pad.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(),
-          B, hp - 2, wp - 2, cp, np_, 1 if relu else 0, 1 if round_out else 0)
+    _call("decnet_conv2d_tc_nhwc_halo", x_pad, x_pad.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(),
+          B, hp - 2, wp - 2, cp, np_, 1 if relu else 0, 1 if round_out else 0, 1 if split else 0)
     return out
 
 
-def nchw_cat_to_nhwc_pad(srcs, cp):
-    """cat(srcs, 1) (NCHW, single-channel maps as [B,H,W]) -> zero-bordered channels-last [B,H+2,W+2,cp], TF32-rounded."""
+def nchw_cat_to_nhwc_pad(srcs, cp, round_tf32=True):
+    """cat(srcs, 1) (NCHW, single-channel maps as [B,H,W]) -> zero-bordered channels-last [B,H+2,W+2,cp]
+    (round_tf32: values rounded to TF32 for the halo kernel's plain-TF32 mode; its 3xTF32 mode takes them unrounded)."""
     import ctypes
     x0 = srcs[0]
     _chk("srcs[0]", x0)
@@ -616,7 +634,7 @@ def nchw_cat_to_nhwc_pad(srcs, cp):
     cs = (ctypes.c_int * n)(*chans)
     out = torch.empty((B, H + 2, W + 2, int(cp)), dtype=torch.float32, device=x0.device)
     _call("decnet_nchw_cat_to_nhwc_pad", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
-          out.data_ptr(), B, H, W, int(cp))
+          out.data_ptr(), B, H, W, int(cp), 1 if round_tf32 else 0)
     return out
 
 

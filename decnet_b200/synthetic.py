@@ -32,21 +32,19 @@ def calibrate_mask_density(model, left_feats, right_feats, rho=0.10):
         logits, _, _ = det(cur, pre_l)
         q = torch.quantile(logits.flatten()[:: max(1, logits.numel() // 2_000_000)].float(), 1.0 - rho)
         unit = det.conv[1]
-        unit.bn.bias.add_(logit_t - q)
-        unit._folded = None
+        unit.bn.bias.add_(logit_t - q)                  # in-place: bumps the version the weight caches are keyed on
         logits, _, _ = det(cur, pre_l)
         dens.append(float((torch.sigmoid(logits) > model.thold).float().mean()))
         pre_l = cur
     return dens
 
 
-def build_workload(name="sceneflow", batch=8, seed=17, device="cuda", rho=0.10, conv3d_impl="tcgen05"):
+def build_workload(name="sceneflow", batch=8, seed=17, device="cuda", rho=0.10, precision="fp32"):
     """(model, left_feats, right_feats, info) for one rank: random-init DecNet hot path + synthetic
     N(0,1)*0.3 feature pyramids of the named shape, mask density calibrated to `rho`."""
     from .model import DecompMatching
     H, W, max_disp, skip = WORKLOADS[name]
-    model = DecompMatching(max_disp=max_disp, skip_stage_id=skip, use_detail=True, thold=0.9,
-                           conv3d_impl=conv3d_impl)
+    model = DecompMatching(max_disp=max_disp, skip_stage_id=skip, use_detail=True, thold=0.9, precision=precision)
     model.load_state_dict(make_hotpath_state(seed))
     model = model.to(device)
     left, right = make_features(batch, H, W, seed=seed, device=device)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DECNET_ABI_VERSION 1
+#define DECNET_ABI_VERSION 2
 
 #define DECNET_OK 0
 #define DECNET_ERR_INVALID 1      /* bad argument (null pointer, non-positive size, ...) */
@@ -204,6 +204,19 @@ int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channel
                                 const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
                                 int relu, int w_valid, void *stream);
 
+/* Precision-selectable forms of the two entry points above (the ones the model calls).
+ *   split = 0: plain TF32 (operands rounded to TF32: cuDNN's default convolution precision on a GPU);
+ *   split = 1: error-compensated "3xTF32": both operands are split into TF32 hi + lo parts (x: in the kernel; weights:
+ *              by the caller, w_packed = the hi rows followed by the lo rows, 2x decnet_conv2d_tf32_packed_floats values)
+ *              and every tap issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator.  The result is fp32-class
+ *              (~2^-22 relative per product): the mode on which the 1e-3 parity gates against the reference's fp32
+ *              execution run (the layers the reference computes with F.conv2d: modules/submodule.py:15-49). */
+int decnet_conv2d_tc_supported(int Cin, int Cout, int H, int W, int dilation, int split);
+int decnet_conv2d_tc_packed_floats(int Cin, int Cout, int split);
+int decnet_conv2d_tc_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
+                              const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
+                              int relu, int w_valid, int split, void *stream);
+
 /* Second formulation of the same convolution for C_out <= 8, dilation <= 4 (conv2d_rows_tcgen05.cu): pixels on the
  * GEMM N dimension, block-Toeplitz weights on M, column taps as accumulator column offsets -- the epilogue needs no
  * shuffles and stores 128 bits per thread.  Same sources / output contract as decnet_conv2d_tf32_nchw_cat.
@@ -222,11 +235,18 @@ int decnet_conv2d_tf32_rows_nchw_cat(const float *const *srcs, const int *src_ch
 int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                  int B, int h, int w, int cp, int np, int relu, int round_out_tf32, void *stream);
 
+/* split = 1: 3xTF32 mode of the same kernel (see decnet_conv2d_tc_nchw_cat): x_pad is plain fp32 (NOT pre-rounded; four
+ * converter warps split it into hi + lo tiles in shared memory), w_packed is [18][np][cp] (taps 0-8 the TF32 hi parts of
+ * the weights, 9-17 the lo parts), round_out_tf32 should be 0. */
+int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                               int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream);
+
 /* Layout bridges around decnet_conv2d_tf32_nhwc_halo for layers whose neighbours are NCHW (the 72-channel refinement
  * layers of the 1/9 level): concatenation of up to three NCHW fp32 sources -> zero-bordered channels-last
- * [B,h+2,w+2,CP] (TF32-rounded, channel padding zero), and back: interior / first C channels -> NCHW [B,C,h,w]. */
+ * [B,h+2,w+2,CP] (channel padding zero; round_tf32 != 0 rounds the values to TF32 for the kernel's plain-TF32 mode),
+ * and back: interior / first C channels -> NCHW [B,C,h,w]. */
 int decnet_nchw_cat_to_nhwc_pad(const float *const *srcs, const int *src_channels, int nsrc, float *out,
-                                int B, int h, int w, int CP, void *stream);
+                                int B, int h, int w, int CP, int round_tf32, void *stream);
 int decnet_nhwc_pad_to_nchw(const float *in_pad, float *out, int B, int C, int NP, int h, int w, void *stream);
 
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread

@@ -30,18 +30,3 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def repo_root():
     return ROOT
-
-
-@pytest.fixture(autouse=True)
-def _default_tf32_state():
-    """Every test starts from PyTorch's default (cuDNN TF32 allowed: the route the product takes); tests that need
-    the fp32 route switch it off themselves, and the switch does not leak into the next test."""
-    try:
-        import torch
-    except Exception:
-        yield
-        return
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = True
-    yield
-    torch.backends.cudnn.allow_tf32 = old

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol(repo_root):
     assert len(names) >= 10
     for n in names:
         assert hasattr(handle, n), f"{n} declared in the header but not exported"
-    assert handle.decnet_abi_version() == 1
+    assert handle.decnet_abi_version() == 2
 
 
 def test_binding_table_matches_header(repo_root):

@@ -10,7 +10,6 @@ pytestmark = pytest.mark.gpu
 def _build(H, W, max_disp, skip, use_detail, seed=31, B=1):
     from decnet_b200.model import DecompMatching
     from decnet_b200.params import make_features, make_hotpath_state
-    torch.backends.cudnn.allow_tf32 = False
     m = DecompMatching(max_disp=max_disp, skip_stage_id=skip, use_detail=use_detail, thold=0.6)
     m.load_state_dict(make_hotpath_state(seed))
     m = m.cuda()
@@ -35,7 +34,7 @@ def test_bands_match_single_device(world, H, W, max_disp, skip, use_detail):
         assert got.shape == want.shape
         scale = float(want.abs().max())
         err = float((got - want).abs().max())
-        # cuDNN picks different algorithms for band-sized inputs; ~20 random-init layers amplify that noise
+        # band-sized tiles change the accumulation grouping; ~20 random-init layers amplify that noise
         assert err <= 1e-3 + 5e-3 * scale, (r, err, scale)
         assert float((got - want).abs().mean()) <= 1e-3 + 1e-4 * scale
 

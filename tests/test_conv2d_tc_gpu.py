@@ -1,6 +1,8 @@
-"""GPU parity of the NCHW TF32 tcgen05 Conv2d (conv2d_tcgen05.cu) through the C ABI.
+"""GPU parity of the NCHW tcgen05 Conv2d (conv2d_tcgen05.cu) through the C ABI, in both arithmetic modes: plain TF32 and the
+error-compensated 3xTF32 ("fp32" precision, the product default).
 
-Two checks per shape:
+Checks per shape:
+  * 3xTF32: raw fp32 operands against an fp64 convolution at fp32 level (1e-5 of the output scale);
   * exactness of the data path: with operands that are already TF32 values the kernel must agree with an
     fp64 convolution up to fp32 accumulation error (any wrong tap, swizzle, halo or padding shows as O(1));
   * precision class: with arbitrary fp32 operands the deviation from the fp32 result must stay at TF32
@@ -66,6 +68,25 @@ def test_conv2d_tf32_nchw(B, Cin, Cout, H, W, dil, relu):
     assert torch.equal(got, got2) or (got - got2).abs().max().item() <= 4 * 2 ** -11 * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W,dil", SHAPES + [(1, 36, 36, 60, 108, 1), (1, 36, 1, 60, 108, 1), (2, 28, 8, 180, 324, 1)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv2d_3xtf32_nchw_is_fp32_class(B, Cin, Cout, H, W, dil, relu):
+    """split mode: hi/lo operand split in the kernel (activations) and on the host (weights), three MMAs per tap.  Raw fp32
+    operands must reproduce the fp64 result at fp32 level -- two orders of magnitude below the TF32 class."""
+    from decnet_b200 import ops
+    assert ops.conv2d_tf32_supported(Cin, Cout, H, W, dil, split=True)
+    g = torch.Generator(device="cuda").manual_seed(5 + Cin + 7 * Cout + dil)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    wp, bp = ops.pack_conv2d_tf32_nchw_weights(w, b, split=True)
+    got = ops.conv2d_tf32_nchw_cat([x], wp, bp, Cout, dil, relu, split=True)
+    y = F.conv2d(x.double(), w.double(), b.double(), padding=dil, dilation=dil)
+    want = (F.relu(y) if relu else y).float()
+    err = (got - want).abs().max().item()
+    assert err <= 1e-5 * max(1.0, want.abs().max().item()), ("3xTF32", err, want.abs().max().item())
+
+
 def test_conv2d_tf32_unsupported_shapes_are_refused():
     from decnet_b200 import ops
     assert not ops.conv2d_tf32_supported(8, 8, 64, 97, 1)         # W*4 not a multiple of 16 (TMA stride rule)
@@ -121,13 +142,12 @@ def test_model_units_use_the_cat_path_and_match_packed_path():
         b = att.logits(ops.attn_pack(L, dense, sparse, mask, var))
         assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
         p1, r1 = ref(L, R, dense)
-        old = dm.USE_TF32_TCGEN05
-        try:
-            dm.USE_TF32_TCGEN05 = False          # packed route, fp32 direct kernels
-            p0, r0 = ref(L, R, dense)
-        finally:
-            dm.USE_TF32_TCGEN05 = old
-        assert (r1 - r0).abs().max().item() <= 4e-3 * max(1.0, r0.abs().max().item())     # TF32 vs fp32 through 7 layers
+        p0, r0 = ref.forward_packed(ops.refine_pack(L, R, dense), dense)      # materialised cat, single-source first conv
+        assert (r1 - r0).abs().max().item() <= 2e-5 * max(1.0, r0.abs().max().item())     # same 3xTF32 arithmetic, other chunking
+        from oracle import glue as og
+        P = {f"rf.{k}": v.detach().cpu().double() for k, v in ref.state_dict().items()}
+        _, r64 = og.refinement(L.cpu().double(), R.cpu().double(), dense.cpu().double(), P, "rf", 3)
+        assert (r1.cpu() - r64.float()).abs().max().item() <= 1e-4 * max(1.0, float(r64.abs().max()))   # fp32 class through 7 layers
 
 
 @pytest.mark.parametrize("chans,Cout,H,W,dil", [((8,), 8, 64, 96, 1), ((8,), 8, 37, 100, 1), ((8, 8, 1), 8, 50, 120, 3),
@@ -151,10 +171,10 @@ def test_conv2d_tf32_rows_formulation(chans, Cout, H, W, dil):
 
 def test_widths_not_multiple_of_4_run_on_pitch_padded_copies():
     """KITTI-style widths (1269, 423, 141): the unit pads the row pitch to 16 bytes, keeps the padding at zero through
-    a stack (w_valid) and crops; result = the fp32 route on the unpadded tensor, at TF32 tolerance."""
+    a stack (w_valid) and crops; result = an fp64 evaluation of the reference arithmetic on the unpadded tensor, at fp32 level."""
     from decnet_b200 import model as dm, ops
+    from oracle import glue as og
     torch.manual_seed(4)
-    torch.backends.cudnn.allow_tf32 = True              # the route under test (PyTorch's default; other tests switch it off)
     B, C, H, W = 2, 8, 42, 141
     L, R = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
     disp = torch.rand(B, H, W, device="cuda") * 20
@@ -166,14 +186,18 @@ def test_widths_not_multiple_of_4_run_on_pitch_padded_copies():
         y = ref.conv[1](ref.conv[1](xp, w_valid=wv), w_valid=wv)            # two layers deep: padding must stay zero
         assert float(y[..., W:].abs().max()) == 0 and float(y[..., :W].abs().max()) > 0
         p1, r1 = ref(L, R, disp)
-        a1 = att.logits_cat(L, ops.attn_pack(None, disp, disp, (disp > 10).float(), disp))
-        old = dm.USE_TF32_TCGEN05
-        try:
-            dm.USE_TF32_TCGEN05 = False                                     # fp32 direct kernels on the unpadded tensors
-            p0, r0 = ref(L, R, disp)
-            a0 = att.logits(ops.attn_pack(L, disp, disp, (disp > 10).float(), disp))
-        finally:
-            dm.USE_TF32_TCGEN05 = old
-    assert r1.shape == r0.shape == (B, H, W) and a1.shape == a0.shape
-    assert (r1 - r0).abs().max().item() <= 4e-3 * max(1.0, r0.abs().max().item())
-    assert (a1 - a0).abs().max().item() <= 4e-3 * max(1.0, a0.abs().max().item())
+        msk = (disp > 10).float()
+        a1 = att.logits_cat(L, ops.attn_pack(None, disp, disp, msk, disp))
+        a2 = att.logits(ops.attn_pack(L, disp, disp, msk, disp))
+        d64 = lambda t: t.cpu().double()
+        Pr = {f"rf.{k}": d64(v.detach()) for k, v in ref.state_dict().items()}
+        _, r0 = og.refinement(d64(L), d64(R), d64(disp), Pr, "rf", 3)
+        Pa = {f"sa.{k}": d64(v.detach()) for k, v in att.state_dict().items()}
+        x = torch.cat((d64(L), d64(disp)[:, None], d64(disp)[:, None], d64(msk)[:, None], -d64(disp)[:, None]), 1)
+        for i in range(3):
+            x = og.conv_bn(x, Pa, f"sa.conv.{i}", relu=i < 2)
+        r0, a0 = r0.float().cuda(), x.float().cuda()
+    assert r1.shape == r0.shape == (B, H, W) and a1.shape == a0.shape == a2.shape
+    assert (r1 - r0).abs().max().item() <= 1e-4 * max(1.0, r0.abs().max().item())
+    assert (a1 - a0).abs().max().item() <= 1e-4 * max(1.0, a0.abs().max().item())
+    assert (a2 - a0).abs().max().item() <= 1e-4 * max(1.0, a0.abs().max().item())

@@ -63,7 +63,7 @@ def test_stack_vs_reference_golden(name):
     from decnet_b200.model import DecompMatching
     z, P, left, right, lmasks, rmasks, cfg = load_case(name, device="cuda")
     m = DecompMatching(max_disp=cfg["max_disp"], skip_stage_id=cfg["skip_stage_id"], use_detail=cfg["use_detail"],
-                       thold=cfg["thold"], conv3d_impl="tcgen05")
+                       thold=cfg["thold"])
     m.load_state_dict(P)
     m = m.cuda()
     pred0, cost = m.dense_stage(left["stage0"], right["stage0"], cfg["max_disp"] // 27)
@@ -124,5 +124,33 @@ def test_conv2d_tf32_tcgen05_vs_fp32(B, H, W, Cin, Cout, relu):
     assert got.shape == (B, H, W, np_)
     err = (got[..., :Cout].permute(0, 3, 1, 2) - want).abs().max().item()
     assert err <= 2e-3 * want.abs().max().item() + 1e-4, (err, want.abs().max().item())
+    if np_ > Cout:
+        assert got[..., Cout:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 60, 108, 217, 81), (1, 20, 36, 649, 81), (2, 45, 50, 81, 81), (1, 180, 324, 73, 81),
+                                            (1, 60, 108, 145, 72), (1, 21, 47, 72, 36), (1, 7, 5, 16, 16)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv2d_3xtf32_nhwc_halo_is_fp32_class(B, H, W, Cin, Cout, relu):
+    """decnet_conv2d_tc_nhwc_halo, split = 1 (the product default): unrounded fp32 activations, hi/lo weights, three MMAs per
+    tap -> an fp64 convolution reproduced at fp32 level; the zero border is kept."""
+    import torch.nn.functional as F
+    from decnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(22)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    want = (F.relu(want) if relu else want).float()
+    cp = (Cin + 7) // 8 * 8
+    xn = ops.nchw_cat_to_nhwc_pad([x], cp, round_tf32=False)
+    wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp, split=True)
+    assert wp.shape == (18, np_, cp)
+    got = ops.conv2d_tf32_nhwc_halo(xn, wp, bp, relu, split=True)
+    assert got.shape == (B, H + 2, W + 2, np_)
+    assert float(got[:, 0].abs().max()) == 0 and float(got[:, -1].abs().max()) == 0
+    assert float(got[:, :, 0].abs().max()) == 0 and float(got[:, :, -1].abs().max()) == 0
+    err = (got[:, 1:-1, 1:-1, :Cout].permute(0, 3, 1, 2) - want).abs().max().item()
+    assert err <= 1e-5 * max(1.0, want.abs().max().item()), (err, want.abs().max().item())
     if np_ > Cout:
         assert got[..., Cout:].abs().max().item() == 0

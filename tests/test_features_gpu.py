@@ -17,26 +17,21 @@ pytestmark = pytest.mark.gpu
 GOLD = ROOT / "tests" / "golden" / "features.npz"
 
 
-def _model(seed):
+def _model(seed, precision="fp32"):
     from decnet_b200.features import FeatExtNetChannelPlus
-    m = FeatExtNetChannelPlus(8)
+    m = FeatExtNetChannelPlus(8, precision=precision)
     m.load_state_dict(make_featext_state(seed), strict=True)
     return m.cuda()
 
 
 @pytest.mark.parametrize("tf32", [False, True])
 def test_features_match_reference_golden(tf32):
-    """fp32 route: <= 1e-4 of the map's scale (accumulation order only).  TF32 route (PyTorch's default for
-    convolutions, what the reference runs on a GPU): 10-bit mantissa operands through up to 14 layers,
+    """precision "fp32" (3xTF32 tensor-core layers, the default): <= 1e-4 of the map's scale (accumulation order only).
+    precision "tf32" (what the reference runs on a GPU by default): 10-bit mantissa operands through up to 14 layers,
     tolerance 1e-2 of the scale (measured ~2e-3)."""
     z = np.load(GOLD)
     seed, B, H, W = (int(v) for v in z["meta"])
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = tf32
-    try:
-        out = _model(seed)(make_image(seed, B, H, W).cuda())
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
+    out = _model(seed, "tf32" if tf32 else "fp32")(make_image(seed, B, H, W).cuda())
     tol = 1e-2 if tf32 else 1e-4
     for k in ("stage0", "stage1", "stage2", "stage3"):
         want = torch.from_numpy(z[k]).cuda()
@@ -46,18 +41,14 @@ def test_features_match_reference_golden(tf32):
 
 
 def test_features_full_size_tensor_core_route_vs_fp32_route():
-    """540x972 (SceneFlow padded), B=2: every level of the pyramid, TF32 tensor-core route vs fp32 route."""
+    """540x972 (SceneFlow padded), B=2: every level of the pyramid, tf32 mode vs the default 3xTF32 mode."""
+    from decnet_b200.model import set_precision
     m = _model(5)
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(2, 3, 540, 972, device="cuda", generator=g)
-    old = torch.backends.cudnn.allow_tf32
-    try:
-        torch.backends.cudnn.allow_tf32 = True
-        a = m(x)
-        torch.backends.cudnn.allow_tf32 = False
-        b = m(x)
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
+    b = m(x)
+    set_precision(m, "tf32")
+    a = m(x)
     for k, shape in (("stage0", (2, 216, 20, 36)), ("stage1", (2, 72, 60, 108)), ("stage2", (2, 24, 180, 324)),
                      ("stage3", (2, 8, 540, 972))):
         assert tuple(a[k].shape) == shape

@@ -140,7 +140,6 @@ def test_middlebury_bands_match_single_device():
     """BASELINE.json configs[3] at full size: 8 row bands (simulated in one process) vs one device."""
     from decnet_b200 import bands
     from decnet_b200.synthetic import build_workload
-    torch.backends.cudnn.allow_tf32 = False
     model, left, right, info = build_workload("middlebury", 1, rho=0.1)
     want = model(left, right)[0]
     full = bands.forward_bands(model, left, right, bands.LocalTransport(8))

@@ -27,14 +27,14 @@ def test_images_to_disparity_vs_reference_model(tf32):
     from decnet_b200.params import make_featext_state, make_hotpath_state
     z = np.load(ROOT / "tests" / "golden" / "pipeline_images.npz")
     seed, B, H, W, max_disp = (int(v) for v in z["meta"])
-    fe = FeatExtNetChannelPlus(8)
+    prec = "tf32" if tf32 else "fp32"
+    fe = FeatExtNetChannelPlus(8, precision=prec)
     fe.load_state_dict(make_featext_state(seed), strict=True)
     fe = fe.cuda()
-    model = DecompMatching(max_disp=max_disp, use_detail=True, thold=0.9)
+    model = DecompMatching(max_disp=max_disp, use_detail=True, thold=0.9, precision=prec)
     model.load_state_dict(make_hotpath_state(seed))
     model = model.cuda()
     left, right = (t.cuda() for t in make_images(seed, B, H, W))
-    torch.backends.cudnn.allow_tf32 = tf32
     pred, taps = model(fe(left), fe(right), is_check=True)
     want0 = torch.from_numpy(z["pred0"]).cuda()
     assert float((taps["pred"][0] - want0).abs().mean()) <= 0.05                 # coarse stage: north-star EPE gate
@@ -45,9 +45,9 @@ def test_images_to_disparity_vs_reference_model(tf32):
         diff = (got - want).abs()
         if not tf32:
             assert chain_close(got, want, rel=1e-2, abs_=5e-2), (i, float(diff.max()), float(want.abs().max()))
-        # TF32 route (what the reference itself runs on a GPU by default): a flipped mask pixel or a 1e-3 logit change
+        # tf32 mode (what the reference itself runs on a GPU by default): a flipped mask pixel or a 1e-3 logit change
         # moves single pixels by tens of px in this random-init chain, so the gates are the mean and the median
-        # (measured: fp32 route max 0.31 px / mean 0.009 at a 163 px scale with 100 % mask agreement; TF32 route mean
+        # (measured in round 1: fp32 route max 0.31 px / mean 0.009 at a 163 px scale with 100 % mask agreement; TF32 route mean
         # 1.1 % / median 0.6 % of the scale at the last stage -- the same class as running the reference's own cuDNN
         # layers in TF32, which tests/test_conv3d_gpu.py and test_conv2d_tc_gpu.py bound layer by layer)
         assert float(diff.mean()) <= (2e-2 if tf32 else 5e-3) * max(1.0, float(want.abs().max())), i
