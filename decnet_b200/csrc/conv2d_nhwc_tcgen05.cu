@@ -19,6 +19,11 @@
 // converter warps write hi = rna_tf32(x) in place and lo = rna_tf32(x - hi) beside it, the weights arrive as hi and lo
 // parts ([18][NP][cp]: taps 0-8 hi, 9-17 lo), and every column tap issues lo*hi + hi*lo + hi*hi into the same accumulator
 // (36 MMAs per stage).  A stage is then 2 x 17 KB of A and 2 x 3 x NP x 128 B of B.
+// The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the accumulation
+// chain (measured: 5e-8 x K relative, i.e. 3e-4 at K = 9 x 649 -- irrelevant for TF32, not for an fp32-class result).  In
+// split mode the chain is therefore cut at every stage: each stage's 36 MMAs start a fresh accumulator in one of the two
+// TMEM slots, and the epilogue warps drain the other slot into REGISTERS with round-to-nearest fp32 adds while the next
+// stage's MMAs run (two-level accumulation); the registers are biased, activated and stored once per tile.  NP <= 128.
 //
 // Warp roles as in conv3d_tcgen05.cu: 0 TMA producer, 1 MMA issuer, 2-5 epilogue, 6-9 converters (split mode only);
 // persistent CTAs, two TMEM slots.
@@ -173,41 +178,61 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const uint32_t smem_base = smem_u32(base);
         const uint32_t empty_base = smem_u32(&empty_bar[0]);
         const uint32_t db_tap_step = (uint32_t)(b_tap_bytes >> 4);
-        uint64_t *const go_bar = p.split ? ready_bar : full_bar;   // what the MMAs of a stage wait for
-        int s = 0; uint32_t ph = 0; int j = 0;
+        int s = 0; uint32_t ph = 0;
         bool ready = false;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-            const int slot = j & 1;
-            mbar_wait(&tmem_empty_bar[slot], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
-            uint32_t first = 0u;                              // 0: overwrite the accumulator
-            for (int kh = 0; kh < 3; ++kh)
-                for (int ck = 0; ck < p.nchunks; ++ck) {
-                    if (!ready) mbar_wait(&go_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
-                    const uint64_t da = make_desc_sw128(sa);
-                    const uint64_t db = make_desc_sw128(sa + (uint32_t)b_off);
-                    int sn = s + 1; uint32_t phn = ph;
-                    if (sn == kStages) { sn = 0; phn ^= 1u; }
-                    ready = mbar_test_wait(&go_bar[sn], phn);
-                    const int ks = ck == p.nchunks - 1 ? p.last_ksteps : 4;
-                    if (p.split) {
-                        // small terms first: lo(x)*hi(w) + hi(x)*lo(w), then hi(x)*hi(w)
-                        const uint64_t da_lo = make_desc_sw128(sa + (uint32_t)kABytes);
+        if (p.split) {
+            // two-level accumulation: every stage is its own accumulation chain in TMEM slot it & 1
+            const uint32_t full_base = smem_u32(&tmem_full_bar[0]);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
+                        const uint32_t slot = it & 1u;
+                        mbar_wait(&tmem_empty_bar[slot], ((it >> 1) & 1u) ^ 1u);
+                        if (!ready) mbar_wait(&ready_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t acc = tmem_base + slot * (uint32_t)acc_stride;
+                        const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
+                        const uint64_t da = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + (uint32_t)kABytes);
+                        const uint64_t db = make_desc_sw128(sa + (uint32_t)b_off);
                         const uint64_t db_lo = make_desc_sw128(sa + (uint32_t)(b_off + 3 * b_tap_bytes));
-                        umma_taps3(ks, acc, da_lo, db, db_tap_step, idesc, first);
+                        int sn = s + 1; uint32_t phn = ph;
+                        if (sn == kStages) { sn = 0; phn ^= 1u; }
+                        ready = mbar_test_wait(&ready_bar[sn], phn);
+                        const int ks = ck == p.nchunks - 1 ? p.last_ksteps : 4;
+                        // small terms first: lo(x)*hi(w) + hi(x)*lo(w), then hi(x)*hi(w)
+                        umma_taps3(ks, acc, da_lo, db, db_tap_step, idesc, 0u);
                         umma_taps3(ks, acc, da, db_lo, db_tap_step, idesc, 1u);
                         umma_taps3(ks, acc, da, db, db_tap_step, idesc, 1u);
-                    } else {
-                        umma_taps3(ks, acc, da, db, db_tap_step, idesc, first);
+                        umma_commit_elect(empty_base + (uint32_t)(s * 8));
+                        umma_commit_elect(full_base + slot * 8u);
+                        s = sn; ph = phn;
                     }
-                    umma_commit_elect(empty_base + (uint32_t)(s * 8));
-                    first = 1u;
-                    s = sn; ph = phn;
-                }
-            umma_commit_elect(smem_u32(&tmem_full_bar[slot]));
+        } else {
+            int j = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+                const int slot = j & 1;
+                mbar_wait(&tmem_empty_bar[slot], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
+                uint32_t first = 0u;                              // 0: overwrite the accumulator
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int ck = 0; ck < p.nchunks; ++ck) {
+                        if (!ready) mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
+                        const uint64_t da = make_desc_sw128(sa);
+                        const uint64_t db = make_desc_sw128(sa + (uint32_t)b_off);
+                        int sn = s + 1; uint32_t phn = ph;
+                        if (sn == kStages) { sn = 0; phn ^= 1u; }
+                        ready = mbar_test_wait(&full_bar[sn], phn);
+                        umma_taps3(ck == p.nchunks - 1 ? p.last_ksteps : 4, acc, da, db, db_tap_step, idesc, first);
+                        umma_commit_elect(empty_base + (uint32_t)(s * 8));
+                        first = 1u;
+                        s = sn; ph = phn;
+                    }
+                umma_commit_elect(smem_u32(&tmem_full_bar[slot]));
+            }
         }
     } else if (warp >= 6) {
         // ===================== converters (warps 6..9, split mode): hi in place, lo beside it =====================
@@ -244,44 +269,87 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const long long per_img = (long long)(p.h + 2) * pitch;
-        int j = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-            const long long pix = (long long)tile * kTileM + r;
-            const bool inside = pix < p.P;
-            const long long rem = pix % per_img;
-            const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
-            const bool interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;   // border pixels are stored as zeros
-            const int slot = j & 1;
-            mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * acc_stride);
-            for (int c0 = 0; c0 < p.np; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + (uint32_t)c0, v);
-                if (inside) {
-                    const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
-                    float4 *op = reinterpret_cast<float4 *>(p.out + pix * p.np + c0);
+        // bias / ReLU / optional TF32 rounding / zero border, 16 channels from c0
+        auto store16 = [&](const float (&v)[16], long long pix, bool interior, int c0) {
+            const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
+            float4 *op = reinterpret_cast<float4 *>(p.out + pix * p.np + c0);
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) {
-                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (interior) {
-                            const float4 bv = __ldg(bp + i4);
-                            o = make_float4(v[4 * i4] + bv.x, v[4 * i4 + 1] + bv.y, v[4 * i4 + 2] + bv.z, v[4 * i4 + 3] + bv.w);
-                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            if (p.round_tf32) {
-                                o.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
-                                o.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
-                                o.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u);
-                                o.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
-                            }
-                        }
-                        op[i4] = o;
+            for (int i4 = 0; i4 < 4; ++i4) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (interior) {
+                    const float4 bv = __ldg(bp + i4);
+                    o = make_float4(v[4 * i4] + bv.x, v[4 * i4 + 1] + bv.y, v[4 * i4 + 2] + bv.z, v[4 * i4 + 3] + bv.w);
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.round_tf32) {
+                        o.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
+                        o.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
+                        o.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u);
+                        o.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
                     }
                 }
+                op[i4] = o;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
+        };
+        if (p.split) {
+            // two-level accumulation: drain every stage's accumulator into registers with round-to-nearest adds
+            constexpr int kMaxChunks = 8;                             // NP <= 128
+            float acc[kMaxChunks][16];
+            const int nstages = 3 * p.nchunks;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const long long pix = (long long)tile * kTileM + r;
+                const bool inside = pix < p.P;
+                const long long rem = pix % per_img;
+                const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
+                const bool interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;
+#pragma unroll
+                for (int c = 0; c < kMaxChunks; ++c)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[c][i] = 0.f;
+                for (int g = 0; g < nstages; ++g, ++it) {
+                    const uint32_t slot = it & 1u;
+                    mbar_wait(&tmem_full_bar[slot], (it >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)acc_stride;
+#pragma unroll
+                    for (int c = 0; c < kMaxChunks; ++c)
+                        if (c * 16 < p.np) {
+                            float v[16];
+                            tmem_ld16(trow + (uint32_t)(c * 16), v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[c][i] += v[i];
+                        }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
+                }
+                if (inside) {
+#pragma unroll
+                    for (int c = 0; c < kMaxChunks; ++c)
+                        if (c * 16 < p.np) store16(acc[c], pix, interior, c * 16);
+                }
+            }
+        } else {
+            int j = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+                const long long pix = (long long)tile * kTileM + r;
+                const bool inside = pix < p.P;
+                const long long rem = pix % per_img;
+                const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
+                const bool interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;   // border pixels are stored as zeros
+                const int slot = j & 1;
+                mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * acc_stride);
+                for (int c0 = 0; c0 < p.np; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + (uint32_t)c0, v);
+                    if (inside) store16(v, pix, interior, c0);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
+            }
         }
     }
     tc_fence_before();
@@ -306,6 +374,7 @@ int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const 
     DECNET_REQUIRE(B > 0 && h > 0 && w > 0, "non-positive size");
     DECNET_REQUIRE(cp % 8 == 0 && cp >= 8 && cp <= 4096, "cp=%d must be a multiple of 8", cp);
     DECNET_REQUIRE(np % 16 == 0 && np >= 16 && np <= 256, "np=%d must be a multiple of 16 in [16,256]", np);
+    DECNET_REQUIRE(!split || np <= 128, "split (3xTF32) mode accumulates in registers: np=%d must be <= 128", np);
     DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x_pad) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0 &&
                    (reinterpret_cast<uintptr_t>(out_pad) & 15u) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0,
                    "pointers must be 16-byte aligned");

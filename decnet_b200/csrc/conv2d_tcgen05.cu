@@ -92,6 +92,61 @@ __device__ __forceinline__ void umma_tf32_elect(uint32_t tmem_d, uint64_t da, ui
         "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The three row taps kh of one row group behind ONE election: descriptors advance by a_step (kh*dil image rows) and
+// b_step (one row tap of the weights), both in 16-byte units of the descriptor's address field.
+__device__ __forceinline__ void umma_tf32_kh3(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t a_step, uint32_t b_step,
+                                              uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b, sa, sb;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "cvt.u64.u32 sa, %3;\n\t"
+        "cvt.u64.u32 sb, %4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %5, p;\n\t"
+        "add.u64 a, %1, sa;\n\t"
+        "add.u64 b, %2, sb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %5, t;\n\t"
+        "add.u64 a, a, sa;\n\t"
+        "add.u64 b, b, sb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %5, t;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+// 3xTF32: per row tap lo(x)*hi(w) + hi(x)*lo(w) + hi(x)*hi(w), small terms first; a_lo / b_lo are the descriptor offsets
+// of the lo tile / lo weights (16-byte units).
+__device__ __forceinline__ void umma_tf32_kh3_split(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t a_step, uint32_t b_step,
+                                                    uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b, al, bl, sa, sb, la, lb;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %8, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "cvt.u64.u32 sa, %3;\n\t"
+        "cvt.u64.u32 sb, %4;\n\t"
+        "cvt.u64.u32 la, %5;\n\t"
+        "cvt.u64.u32 lb, %6;\n\t"
+        "add.u64 al, %1, la;\n\t"
+        "add.u64 bl, %2, lb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, %2, %7, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, bl, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %7, t;\n\t"
+        "add.u64 a, %1, sa;\n\t"
+        "add.u64 b, %2, sb;\n\t"
+        "add.u64 al, al, sa;\n\t"
+        "add.u64 bl, bl, sb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, b, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, bl, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %7, t;\n\t"
+        "add.u64 a, a, sa;\n\t"
+        "add.u64 b, b, sb;\n\t"
+        "add.u64 al, al, sa;\n\t"
+        "add.u64 bl, bl, sb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, b, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, bl, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %7, t;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -278,6 +333,9 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t ring_base = smem_u32(ring);
         const uint32_t w_base = smem_u32(wsm);
         const uint32_t empty_base = smem_u32(&empty_bar[0]);
+        // descriptor steps in 16-byte units: kh*dil image rows of the tile / one row tap of the weights / lo parts
+        const uint32_t a_step = (uint32_t)(p.dil * kRowBlock) >> 4, b_step = (uint32_t)(p.nck * p.natoms * kRowBlock) >> 4;
+        const uint32_t a_lo = (uint32_t)p.lo_off >> 4, b_lo = (uint32_t)p.w_lo_off >> 4;
         mbar_wait(&w_bar, 0);
         int s = 0; uint32_t ph = 0; int j = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
@@ -293,23 +351,21 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 prof_acc[1] += clock64() - tq0;
                 tc_fence_after();
                 const uint32_t sa = ring_base + (uint32_t)(s * stage_bytes);
-                for (int g = 0; g < ((p.dbg & 4) ? 0 : p.G); ++g) {
-#pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const uint32_t a_off = sa + (uint32_t)((4 * g + kh * p.dil) * kRowBlock);
-                        const uint32_t b_off = w_base + (uint32_t)(((kh * p.nck + ck) * p.natoms) * kRowBlock);
-                        const uint64_t da = make_desc_mn(a_off), db = make_desc_mn(b_off);
-                        const uint32_t d = acc + (uint32_t)(g * p.N);
-                        const uint32_t accum = (ck | kh) != 0 ? 1u : 0u;
-                        if (p.split) {
-                            // small terms first: lo(x)*hi(w) + hi(x)*lo(w) + hi(x)*hi(w)
-                            umma_tf32_elect(d, make_desc_mn(a_off + (uint32_t)p.lo_off), db, idesc, accum);
-                            umma_tf32_elect(d, da, make_desc_mn(b_off + (uint32_t)p.w_lo_off), idesc, 1u);
-                            umma_tf32_elect(d, da, db, idesc, 1u);
-                        } else {
-                            umma_tf32_elect(d, da, db, idesc, accum);
-                        }
-                    }
+                // per row group: the three row taps (x3 in split mode) behind one election
+                const uint64_t da0 = make_desc_mn(sa);
+                const uint64_t db0 = make_desc_mn(w_base + (uint32_t)(ck * p.natoms * kRowBlock));
+                const uint32_t accum = ck != 0 ? 1u : 0u;
+                const int Gn = (p.dbg & 4) ? 0 : p.G;
+                if (p.split) {
+#pragma unroll 1
+                    for (int g = 0; g < Gn; ++g)
+                        umma_tf32_kh3_split(acc + (uint32_t)(g * p.N), da0 + (uint64_t)(g * (4 * kRowBlock >> 4)), db0, a_step, b_step,
+                                            a_lo, b_lo, idesc, accum);
+                } else {
+#pragma unroll 1
+                    for (int g = 0; g < Gn; ++g)
+                        umma_tf32_kh3(acc + (uint32_t)(g * p.N), da0 + (uint64_t)(g * (4 * kRowBlock >> 4)), db0, a_step, b_step,
+                                      idesc, accum);
                 }
                 umma_commit_elect(empty_base + (uint32_t)(s * 8));
                 if (++s == kStages) { s = 0; ph ^= 1u; }
