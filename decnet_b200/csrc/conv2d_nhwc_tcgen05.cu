@@ -21,9 +21,11 @@
 // (36 MMAs per stage).  A stage is then 2 x 17 KB of A and 2 x 3 x NP x 128 B of B.
 // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the accumulation
 // chain (measured: 5e-8 x K relative, i.e. 3e-4 at K = 9 x 649 -- irrelevant for TF32, not for an fp32-class result).  In
-// split mode the chain is therefore cut at every stage: each stage's 36 MMAs start a fresh accumulator in one of the two
-// TMEM slots, and the epilogue warps drain the other slot into REGISTERS with round-to-nearest fp32 adds while the next
-// stage's MMAs run (two-level accumulation); the registers are biased, activated and stored once per tile.  NP <= 128.
+// split mode the hi*hi products therefore accumulate in chains of kGroup stages (24 MMAs) that alternate between two
+// TMEM slots; the epilogue warps drain the finished slot into REGISTERS with round-to-nearest fp32 adds while the next
+// chain runs (two-level accumulation).  The two small terms go to a third accumulator that lives for the whole tile
+// (its values, and so its truncation steps, are 2^-11 of the big one's) and is added last; the registers are biased,
+// activated and stored once per tile.  NP <= 128 (4 x NP TMEM columns).
 //
 // Warp roles as in conv3d_tcgen05.cu: 0 TMA producer, 1 MMA issuer, 2-5 epilogue, 6-9 converters (split mode only);
 // persistent CTAs, two TMEM slots.
@@ -37,6 +39,7 @@ namespace conv2dnhwc {
 constexpr int kMaxStages = 6;
 constexpr int kThreads = 320;
 constexpr int kConvWarps = 4;
+constexpr int kGroup = 2;                          // split mode: stages per hi*hi accumulation chain
 constexpr int kTileM = 128;
 constexpr int kARows = 130;                        // 128 pixels + one halo pixel on each side
 constexpr int kABytes = 17 * 1024;                 // 130 rows x 128 B rounded up to the 1 KB swizzle period
@@ -123,6 +126,8 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __shared__ __align__(8) uint64_t ready_bar[kMaxStages];   // split mode: hi/lo tiles written by the converters
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t small_full_bar[2];       // split mode: the per-tile accumulator of the small terms
+    __shared__ __align__(8) uint64_t small_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,13 +139,16 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int stage_bytes = nsplit * (kABytes + 3 * b_tap_bytes);
     const int tx_bytes = kARows * 128 + nsplit * 3 * b_tap_bytes;   // bytes TMA actually delivers per stage
     const int kStages = p.stages;
-    const int acc_stride = p.tmem_cols >> 1;
+    const int acc_stride = p.split ? p.tmem_cols >> 2 : p.tmem_cols >> 1;   // split: 2 chain slots + 2 small-term slots
     const int pitch = p.w + 2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4);
+            mbar_init(&small_full_bar[a], 1); mbar_init(&small_empty_bar[a], 4);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -181,17 +189,28 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         int s = 0; uint32_t ph = 0;
         bool ready = false;
         if (p.split) {
-            // two-level accumulation: every stage is its own accumulation chain in TMEM slot it & 1
+            // two-level accumulation: hi*hi in chains of kGroup stages alternating between TMEM slots 0/1 (drained by the
+            // epilogue into registers), the small terms in slot 2 + (tile & 1) for the whole tile
             const uint32_t full_base = smem_u32(&tmem_full_bar[0]);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            const int nst = 3 * p.nchunks;
+            uint32_t it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+                const uint32_t sj = j & 1u;
+                mbar_wait(&small_empty_bar[sj], ((j >> 1) & 1u) ^ 1u);
+                const uint32_t acc_s = tmem_base + (2u + sj) * (uint32_t)acc_stride;
+                uint32_t acc_b = 0, slot = 0, first_s = 0u, first_b = 0u;
+                int st = 0;
                 for (int kh = 0; kh < 3; ++kh)
-                    for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
-                        const uint32_t slot = it & 1u;
-                        mbar_wait(&tmem_empty_bar[slot], ((it >> 1) & 1u) ^ 1u);
+                    for (int ck = 0; ck < p.nchunks; ++ck, ++st) {
+                        const int gpos = st % kGroup;
+                        if (gpos == 0) {
+                            slot = it & 1u;
+                            mbar_wait(&tmem_empty_bar[slot], ((it >> 1) & 1u) ^ 1u);
+                            acc_b = tmem_base + slot * (uint32_t)acc_stride;
+                            first_b = 0u;
+                        }
                         if (!ready) mbar_wait(&ready_bar[s], ph);
                         tc_fence_after();
-                        const uint32_t acc = tmem_base + slot * (uint32_t)acc_stride;
                         const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
                         const uint64_t da = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + (uint32_t)kABytes);
                         const uint64_t db = make_desc_sw128(sa + (uint32_t)b_off);
@@ -200,14 +219,16 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         if (sn == kStages) { sn = 0; phn ^= 1u; }
                         ready = mbar_test_wait(&ready_bar[sn], phn);
                         const int ks = ck == p.nchunks - 1 ? p.last_ksteps : 4;
-                        // small terms first: lo(x)*hi(w) + hi(x)*lo(w), then hi(x)*hi(w)
-                        umma_taps3(ks, acc, da_lo, db, db_tap_step, idesc, 0u);
-                        umma_taps3(ks, acc, da, db_lo, db_tap_step, idesc, 1u);
-                        umma_taps3(ks, acc, da, db, db_tap_step, idesc, 1u);
+                        umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s);     // lo(x) * hi(w)
+                        umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u);          // hi(x) * lo(w)
+                        umma_taps3(ks, acc_b, da, db, db_tap_step, idesc, first_b);        // hi(x) * hi(w)
+                        first_s = 1u; first_b = 1u;
                         umma_commit_elect(empty_base + (uint32_t)(s * 8));
-                        umma_commit_elect(full_base + slot * 8u);
+                        if (gpos == kGroup - 1 || st == nst - 1) { umma_commit_elect(full_base + slot * 8u); ++it; }
                         s = sn; ph = phn;
                     }
+                umma_commit_elect(smem_u32(&small_full_bar[sj]));
+            }
         } else {
             int j = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
@@ -291,12 +312,26 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
         };
         if (p.split) {
-            // two-level accumulation: drain every stage's accumulator into registers with round-to-nearest adds
+            // two-level accumulation: drain every finished hi*hi chain into registers with round-to-nearest adds, the small
+            // terms' accumulator once at the end of the tile
             constexpr int kMaxChunks = 8;                             // NP <= 128
             float acc[kMaxChunks][16];
-            const int nstages = 3 * p.nchunks;
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int ngroups = (3 * p.nchunks + kGroup - 1) / kGroup;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+            auto drain = [&](uint32_t trow) {
+#pragma unroll
+                for (int c = 0; c < kMaxChunks; ++c)
+                    if (c * 16 < p.np) {
+                        float v[16];
+                        tmem_ld16(trow + (uint32_t)(c * 16), v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[c][i] += v[i];
+                    }
+                tc_fence_before();
+                __syncwarp();
+            };
+            uint32_t it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
                 const long long pix = (long long)tile * kTileM + r;
                 const bool inside = pix < p.P;
                 const long long rem = pix % per_img;
@@ -306,23 +341,18 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 for (int c = 0; c < kMaxChunks; ++c)
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[c][i] = 0.f;
-                for (int g = 0; g < nstages; ++g, ++it) {
+                for (int g = 0; g < ngroups; ++g, ++it) {
                     const uint32_t slot = it & 1u;
                     mbar_wait(&tmem_full_bar[slot], (it >> 1) & 1u);
                     tc_fence_after();
-                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)acc_stride;
-#pragma unroll
-                    for (int c = 0; c < kMaxChunks; ++c)
-                        if (c * 16 < p.np) {
-                            float v[16];
-                            tmem_ld16(trow + (uint32_t)(c * 16), v);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[c][i] += v[i];
-                        }
-                    tc_fence_before();
-                    __syncwarp();
+                    drain(lane_base + slot * (uint32_t)acc_stride);
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
                 }
+                const uint32_t sj = j & 1u;
+                mbar_wait(&small_full_bar[sj], (j >> 1) & 1u);
+                tc_fence_after();
+                drain(lane_base + (2u + sj) * (uint32_t)acc_stride);
+                if (lane == 0) mbar_arrive(&small_empty_bar[sj]);
                 if (inside) {
 #pragma unroll
                     for (int c = 0; c < kMaxChunks; ++c)
@@ -386,6 +416,7 @@ int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const 
     DECNET_REQUIRE(p.P + 2ll * (w + 3) < (1ll << 31), "tensor too large for 32-bit TMA coordinates");
     p.relu = relu; p.round_tf32 = round_out_tf32; p.split = split ? 1 : 0;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;
+    if (p.split) p.tmem_cols *= 2;                                  // two chain slots + two small-term slots
     p.num_tiles = (int)((p.P + kTileM - 1) / kTileM);
     const size_t stage_bytes = ((size_t)kABytes + (size_t)3 * np * 128) * (p.split ? 2 : 1);
     p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
