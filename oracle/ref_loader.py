@@ -1,5 +1,5 @@
-"""oracle/ref_loader.py -- TEST INFRASTRUCTURE (build container only; /root/reference does not
-exist on the GPU box).  Imports the UNMODIFIED reference package from /root/reference:
+"""oracle/ref_loader.py -- TEST INFRASTRUCTURE.  Imports the UNMODIFIED reference package from /root/reference (build
+container) or from baseline/_ref (the git-ignored copy __graft_entry__.build() stages so that it travels to the GPU box):
 stubs the missing matplotlib / visdom modules (utils/utils.py:8, eval.py:10) and registers
 `modules.Sparse{Matching,Var}.build.lib` with an extension object of the caller's choice
 (the CPU oracle by default) so `from ..build.lib import SpaMat` resolves
@@ -11,7 +11,8 @@ import sys
 import types
 from pathlib import Path
 
-REF = Path("/root/reference")
+_ROOT = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference") if (Path("/root/reference") / "modules" / "submodule.py").exists() else _ROOT / "baseline" / "_ref"
 
 
 class _OracleSpaMatExt:
@@ -55,7 +56,8 @@ def available() -> bool:
 def install(spamat_ext=None, spavar_ext=None):
     """Make `import modules` (the reference package) work; returns the imported package."""
     if not available():
-        raise RuntimeError("/root/reference is not present (GPU box?)")
+        raise RuntimeError("the reference tree is present neither at /root/reference nor at baseline/_ref "
+                           "(run __graft_entry__.build() in the build container)")
     for m in ("matplotlib", "matplotlib.pyplot", "visdom"):
         if m not in sys.modules:
             sys.modules[m] = types.ModuleType(m)

@@ -1,5 +1,9 @@
-"""GPU, BASELINE.json's full sizes: the oracle is too slow there, so parity is checked through
-size-independent properties of the sparse ops and of the pipeline (SceneFlow B=8, KITTI, Middlebury)."""
+"""GPU, BASELINE.json's full sizes (SceneFlow 540x972 B=8, KITTI 378x1269, Middlebury 2025x2916 D=783): parity against the
+CPU oracle at those sizes -- the whole stage loop of one SceneFlow and one KITTI pair, Middlebury's 1/9 and 1/3 levels op by
+op, the C/OpenMP sparse oracle on the B=8 finest level and on the C=32/64 sweep shapes -- plus size-independent properties
+of the sparse ops and of the pipeline."""
+import math
+
 import pytest
 import torch
 
@@ -147,3 +151,116 @@ def test_middlebury_bands_match_single_device():
     scale = float(want.abs().max())
     assert float((got - want).abs().max()) <= 1e-3 + 5e-3 * scale
     assert float((got - want).abs().mean()) <= 1e-3 + 1e-4 * scale
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Full-size parity against the oracle (the CPU restatement of the reference, oracle/): masks bit-equal, sparse / var
+# <= 1e-3, coarse disparity <= 0.05 px EPE (bf16 aggregation), fp32-class stages chained from the oracle's own coarse
+# disparity at the chained tolerance of test_glue_gpu.py.
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu(d):
+    return {k: v.detach().cpu() for k, v in d.items()}
+
+
+def _var_close(got, want):
+    return torch.allclose(got, want, atol=1e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("workload", ["sceneflow", "kitti"])
+def test_pipeline_full_size_vs_oracle(workload):
+    """One pair at BASELINE.json's size through oracle.pipeline.forward (learned detectors, thold 0.9, masks calibrated to
+    10 %) against DecompMatching on the product route.  KITTI's 1269 / 423 / 141 widths take the pitch-padded route."""
+    from decnet_b200.synthetic import build_workload
+    from golden_util import chain_close
+    from oracle import pipeline as opipe
+    model, left, right, info = build_workload(workload, 1, rho=0.1)
+    pred, taps = model(left, right, is_check=True)
+    P = _cpu(model.state_dict())                               # after the density calibration: what the model really runs
+    with torch.no_grad():
+        want, otaps = opipe.forward(P, _cpu(left), _cpu(right), info["max_disp"], use_detail=True, thold=0.9,
+                                    skip_stage_id=info["skip_stage_id"])
+    for l in range(3):
+        assert torch.equal(taps["left_mask"][l].cpu(), otaps["left_mask"][l]), ("left mask", l)     # mask selection: bit-exact
+        assert torch.equal(taps["right_mask"][l].cpu(), otaps["right_mask"][l]), ("right mask", l)
+        # the sparse ops see identical features and identical masks: exact quantities
+        assert torch.allclose(taps["sparse"][l].cpu(), otaps["sparse"][l], atol=1e-3, rtol=1e-5), ("sparse", l)
+        assert _var_close(taps["var"][l].cpu(), otaps["var"][l]), ("var", l)
+        dens = float(otaps["left_mask"][l].mean())
+        assert abs(dens - 0.1) < 0.02, dens
+    epe0 = float((taps["pred"][0].cpu() - otaps["pred"][0]).abs().mean())
+    assert epe0 <= 0.05, f"coarse EPE delta {epe0}"
+    # fp32-class stages: chained from the oracle's coarse disparity
+    pred_f, taps_f = model(left, right, is_check=True, coarse_pred=otaps["pred"][0].cuda())
+    for key in ("dense", "fusion", "residual", "soft_mask", "pred"):
+        for i, (g_, w_) in enumerate(zip(taps_f[key][-3:] if key == "pred" else taps_f[key], otaps[key][-3:] if key == "pred" else otaps[key])):
+            g_ = g_.cpu()
+            assert chain_close(g_, w_, rel=3e-3, abs_=3e-3), f"{key}[{i}] max diff {(g_ - w_).abs().max()} of {w_.abs().max()}"
+            assert float((g_ - w_).abs().mean()) <= 1e-3 + 2e-4 * float(w_.abs().max()), (key, i)
+
+
+def test_middlebury_levels_vs_oracle_teacher_forced():
+    """Middlebury 2025x2916, D = 783 (BASELINE.json configs[3]): the 1/9 (225x324, C72, D87) and 1/3 (675x972, C24, D261)
+    levels op by op against the oracle, each op fed with OUR upstream values (the CPU oracle's 4 TFLOP coarse aggregation
+    at this size is what makes a chained comparison too slow; the coarse stage's parity is size-independent and gated on
+    SceneFlow / KITTI above)."""
+    from decnet_b200.synthetic import build_workload
+    from oracle import glue as og, sparse as osp
+    model, left, right, info = build_workload("middlebury", 1, rho=0.1)
+    pred, taps = model(left, right, is_check=True)
+    P = _cpu(model.state_dict())
+    assert len(taps["dense"]) == 2                           # finest level skipped (bicubic)
+    for l in range(2):
+        s = l + 1
+        Lf, Rf = left[f"stage{s}"].cpu(), right[f"stage{s}"].cpu()
+        D = info["max_disp"] // 3 ** (3 - s)
+        tol = lambda w: 1e-3 + 1e-5 * float(w.abs().max())
+        with torch.no_grad():
+            # mask selection: identical except where a logit sits ON the threshold within fp32 summation-order noise
+            # (1.5 M logits per level here; the oracle's ATen convs and our kernels add in different orders)
+            logit_t = math.log(0.9 / 0.1)
+            masks = []
+            for mine, cur, prev in ((taps["left_mask"][l], Lf, left[f"stage{s - 1}"]), (taps["right_mask"][l], Rf, right[f"stage{s - 1}"])):
+                lg = og.detail_logits(cur, prev.cpu(), P, f"detail_detection.{l}")
+                want_m = og.threshold_mask(torch.sigmoid(lg), 0.9)
+                flips = mine.cpu() != want_m
+                assert int(flips.sum()) <= 4, int(flips.sum())
+                if flips.any():
+                    assert float((lg[flips] - logit_t).abs().max()) <= 2e-5 * max(1.0, float(lg.abs().max())), "a flipped pixel away from the threshold"
+                masks.append(mine.cpu())                           # downstream ops are teacher-forced with OUR masks
+            lm, rm = masks
+            dense = og.dynamic_upsampling(taps["pred"][s - 1].cpu(), Lf, P, f"dynamic_upsampling.{l}")
+            assert float((taps["dense"][l].cpu() - dense).abs().max()) <= tol(dense), ("dense", l)
+            sp, _, mx = osp.spamat_forward(Lf, Rf, lm, rm, D)
+            vr, _, _ = osp.spavar_forward(Lf, Rf, lm, rm, sp, D)
+            assert torch.allclose(taps["sparse"][l].cpu(), sp, atol=1e-3, rtol=1e-5), ("sparse", l)
+            assert _var_close(taps["var"][l].cpu(), vr), ("var", l)
+            m = og.soft_attention(Lf, taps["dense"][l].cpu(), taps["sparse"][l].cpu(), lm, taps["var"][l].cpu(), P, f"soft_attention.{l}")
+            assert float((taps["soft_mask"][l].cpu() - m).abs().max()) <= 1e-3, ("soft mask", l)
+            p_, r_ = og.refinement(Lf, Rf, taps["fusion"][l].cpu(), P, f"refinement.{l}", s)
+            assert float((taps["residual"][l].cpu() - r_).abs().max()) <= tol(p_), ("residual", l)
+            assert float((taps["pred"][s].cpu() - p_).abs().max()) <= tol(p_), ("pred", l)
+    up = og.bicubic_skip(taps["pred"][2].cpu(), left["stage3"].shape[-2:])
+    assert float((pred.cpu() - up).abs().max()) <= 1e-3 + 1e-5 * float(up.abs().max())
+
+
+@pytest.mark.parametrize("name,B,C,H,W,D,rho", [("sceneflow_s3_b8", 8, 8, 540, 972, 216, 0.1), ("sceneflow_s3_b8_dense", 8, 8, 540, 972, 216, 0.3),
+                                                 ("sweep_c32_third", 2, 32, 180, 324, 72, 0.1), ("sweep_c64_third", 2, 64, 180, 324, 72, 0.3),
+                                                 ("sweep_c32_full", 1, 32, 540, 972, 216, 0.1), ("sweep_c64_full", 1, 64, 540, 972, 216, 0.03),
+                                                 ("kitti_s3_b8", 8, 8, 378, 1269, 216, 0.1), ("middlebury_s2", 1, 24, 675, 972, 261, 0.1)])
+def test_sparse_full_size_vs_c_oracle(name, B, C, H, W, D, rho):
+    """The C/OpenMP restatement of the reference kernels (oracle/sparse_oracle.c) at BASELINE.json's sizes: configs[1]'s
+    finest level at B = 8, the C = 32 / 64 sweep shapes of configs[4], KITTI's and Middlebury's largest sparse levels."""
+    from decnet_b200 import ops
+    from oracle import sparse as osp
+    L, R = make_feats(B, C, H, W, device="cuda")
+    ml, mr = make_masks(B, H, W, rho, rho, device="cuda", clustered=(name.endswith("b8")))
+    out, var, ssim, mx = ops.spamat_spavar_forward(L, R, ml, mr, D)
+    o_out, o_ssim, o_mx = osp.spamat_forward(L, R, ml, mr, D)
+    o_var, _, _ = osp.spavar_forward(L, R, ml, mr, o_out, D)
+    assert torch.equal(mx.cpu(), o_mx)                                       # same FMA chain: bit-identical
+    assert torch.allclose(out.cpu(), o_out, atol=1e-3, rtol=1e-5)
+    assert torch.allclose(ssim.cpu(), o_ssim, atol=1e-3, rtol=1e-5)
+    assert _var_close(var.cpu(), o_var)
+    cnt, hsh = ops.candidate_signature(ml, mr, D)
+    o_cnt, o_hsh = osp.candidate_signature(ml, mr, D)
+    assert torch.equal(cnt.cpu(), o_cnt) and torch.equal(hsh.cpu(), o_hsh)    # candidate index sets: bit-exact
