@@ -42,6 +42,12 @@ SIGNATURES = {
     "decnet_conv2d_tc_packed_floats": (_i, [_i] * 3),
     "decnet_conv2d_tc_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 8 + [C.c_void_p]),
     "decnet_conv2d_tc_nhwc_halo": (_i, [_f32p] * 4 + [_i] * 8 + [C.c_void_p]),
+    "decnet_conv2d_tc_nhwc_halo_ldc": (_i, [_f32p] * 4 + [_i] * 8 + [C.c_void_p]),
+    "decnet_gemm_tc_nhwc": (_i, [_f32p] * 4 + [C.c_longlong] + [_i] * 10 + [C.c_void_p]),
+    "decnet_im2col3x3": (_i, [_f32p] * 2 + [_i] * 4 + [C.c_longlong] * 4 + [_i] * 5 + [C.c_void_p]),
+    "decnet_deconv3x3s3_shuffle": (_i, [_f32p] * 2 + [_i] * 7 + [C.c_void_p]),
+    "decnet_nhwc_to_nchw": (_i, [_f32p] * 2 + [_i] * 6 + [C.c_void_p]),
+    "decnet_conv3x3s3_nchw": (_i, [_f32p] * 4 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv2d_tf32_rows_supported": (_i, [_i] * 5),
     "decnet_conv2d_tf32_rows_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv2d_tf32_nhwc_halo": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),

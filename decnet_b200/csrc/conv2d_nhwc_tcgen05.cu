@@ -53,6 +53,11 @@ struct Params {
     long long P;                                   // B * (h+2) * (w+2) padded pixels
     int relu, round_tf32, tmem_cols, num_tiles, stages;
     int split;                                     // 1: 3xTF32 (hi/lo split of both operands)
+    int taps;                                      // 3: 3x3 conv on the zero-bordered layout; 1: plain GEMM (1x1 conv) over P rows
+    int border;                                    // 1: rows are pixels of [B, h+2, w+2] and border pixels are stored as zeros
+    int ldc;                                       // output row stride in floats (>= np: writes a channel slice of a wider tensor)
+    int dst_h, dst_w;                              // > 0 (GEMM mode, border = 0): row p = (b, y, x) of a flat [B, dst_h, dst_w]
+                                                   // grid is stored at the interior pixel (b, y+1, x+1) of a zero-bordered one
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -84,10 +89,11 @@ __device__ __forceinline__ void umma_tap(uint32_t tmem_d, uint64_t da, uint64_t 
         asm volatile(DN_HEAD "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
 }
 __device__ __forceinline__ void umma_taps3(int ksteps, uint32_t acc, uint64_t da, uint64_t db, uint32_t db_tap_step,
-                                           uint32_t idesc, uint32_t first) {
-    // three column taps: A moves one pixel row (128 B = 8 sixteen-byte units), B one tap block
+                                           uint32_t idesc, uint32_t first, int ntaps = 3) {
+    // the column taps (3, or 1 in GEMM mode): A moves one pixel row (128 B = 8 sixteen-byte units), B one tap block
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
+        if (kw >= ntaps) break;
         const uint64_t a = da + (uint64_t)(8 * kw), b = db + (uint64_t)(kw * db_tap_step);
         const uint32_t acc_first = (kw == 0) ? first : 1u;
         switch (ksteps) {
@@ -135,9 +141,11 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_tap_bytes = p.np * 128;                       // one column tap of the weights: NP rows x 128 B
     const int nsplit = p.split ? 2 : 1;
-    const int b_off = nsplit * kABytes;                       // stage: [A hi][A lo][B hi (3 taps)][B lo (3 taps)]
-    const int stage_bytes = nsplit * (kABytes + 3 * b_tap_bytes);
-    const int tx_bytes = kARows * 128 + nsplit * 3 * b_tap_bytes;   // bytes TMA actually delivers per stage
+    const int T = p.taps;                                     // taps per dimension: 3 (conv) or 1 (GEMM)
+    const int a_rows = T == 3 ? kARows : kTileM;
+    const int b_off = nsplit * kABytes;                       // stage: [A hi][A lo][B hi (T taps)][B lo (T taps)]
+    const int stage_bytes = nsplit * (kABytes + T * b_tap_bytes);
+    const int tx_bytes = a_rows * 128 + nsplit * T * b_tap_bytes;   // bytes TMA actually delivers per stage
     const int kStages = p.stages;
     const int acc_stride = p.split ? p.tmem_cols >> 2 : p.tmem_cols >> 1;   // split: 2 chain slots + 2 small-term slots
     const int pitch = p.w + 2;
@@ -167,14 +175,14 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int p0 = tile * kTileM;
-                for (int kh = 0; kh < 3; ++kh)
+                for (int kh = 0; kh < T; ++kh)
                     for (int ck = 0; ck < p.nchunks; ++ck) {
                         mbar_wait(&empty_bar[s], ph ^ 1u);
                         unsigned char *sa = base + (size_t)s * stage_bytes;
                         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)tx_bytes);
-                        tma_load_2d(sa, &tmA, ck * 32, p0 + (kh - 1) * pitch - 1, &full_bar[s]);
-                        tma_load_3d(sa + b_off, &tmB, ck * 32, 0, kh * 3, &full_bar[s]);
-                        if (p.split) tma_load_3d(sa + b_off + 3 * b_tap_bytes, &tmB, ck * 32, 0, 9 + kh * 3, &full_bar[s]);
+                        tma_load_2d(sa, &tmA, ck * 32, T == 3 ? p0 + (kh - 1) * pitch - 1 : p0, &full_bar[s]);
+                        tma_load_3d(sa + b_off, &tmB, ck * 32, 0, kh * T, &full_bar[s]);
+                        if (p.split) tma_load_3d(sa + b_off + T * b_tap_bytes, &tmB, ck * 32, 0, T * T + kh * T, &full_bar[s]);
                         if (++s == kStages) { s = 0; ph ^= 1u; }
                     }
             }
@@ -192,7 +200,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             // two-level accumulation: hi*hi in chains of kGroup stages alternating between TMEM slots 0/1 (drained by the
             // epilogue into registers), the small terms in slot 2 + (tile & 1) for the whole tile
             const uint32_t full_base = smem_u32(&tmem_full_bar[0]);
-            const int nst = 3 * p.nchunks;
+            const int nst = T * p.nchunks;
             uint32_t it = 0, j = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
                 const uint32_t sj = j & 1u;
@@ -200,7 +208,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 const uint32_t acc_s = tmem_base + (2u + sj) * (uint32_t)acc_stride;
                 uint32_t acc_b = 0, slot = 0, first_s = 0u, first_b = 0u;
                 int st = 0;
-                for (int kh = 0; kh < 3; ++kh)
+                for (int kh = 0; kh < T; ++kh)
                     for (int ck = 0; ck < p.nchunks; ++ck, ++st) {
                         const int gpos = st % kGroup;
                         if (gpos == 0) {
@@ -214,14 +222,14 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
                         const uint64_t da = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + (uint32_t)kABytes);
                         const uint64_t db = make_desc_sw128(sa + (uint32_t)b_off);
-                        const uint64_t db_lo = make_desc_sw128(sa + (uint32_t)(b_off + 3 * b_tap_bytes));
+                        const uint64_t db_lo = make_desc_sw128(sa + (uint32_t)(b_off + T * b_tap_bytes));
                         int sn = s + 1; uint32_t phn = ph;
                         if (sn == kStages) { sn = 0; phn ^= 1u; }
                         ready = mbar_test_wait(&ready_bar[sn], phn);
                         const int ks = ck == p.nchunks - 1 ? p.last_ksteps : 4;
-                        umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s);     // lo(x) * hi(w)
-                        umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u);          // hi(x) * lo(w)
-                        umma_taps3(ks, acc_b, da, db, db_tap_step, idesc, first_b);        // hi(x) * hi(w)
+                        umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s, T);     // lo(x) * hi(w)
+                        umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u, T);          // hi(x) * lo(w)
+                        umma_taps3(ks, acc_b, da, db, db_tap_step, idesc, first_b, T);        // hi(x) * hi(w)
                         first_s = 1u; first_b = 1u;
                         umma_commit_elect(empty_base + (uint32_t)(s * 8));
                         if (gpos == kGroup - 1 || st == nst - 1) { umma_commit_elect(full_base + slot * 8u); ++it; }
@@ -237,7 +245,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
                 uint32_t first = 0u;                              // 0: overwrite the accumulator
-                for (int kh = 0; kh < 3; ++kh)
+                for (int kh = 0; kh < T; ++kh)
                     for (int ck = 0; ck < p.nchunks; ++ck) {
                         if (!ready) mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
@@ -247,7 +255,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         int sn = s + 1; uint32_t phn = ph;
                         if (sn == kStages) { sn = 0; phn ^= 1u; }
                         ready = mbar_test_wait(&full_bar[sn], phn);
-                        umma_taps3(ck == p.nchunks - 1 ? p.last_ksteps : 4, acc, da, db, db_tap_step, idesc, first);
+                        umma_taps3(ck == p.nchunks - 1 ? p.last_ksteps : 4, acc, da, db, db_tap_step, idesc, first, T);
                         umma_commit_elect(empty_base + (uint32_t)(s * 8));
                         first = 1u;
                         s = sn; ph = phn;
@@ -259,10 +267,10 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         // ===================== converters (warps 6..9, split mode): hi in place, lo beside it =====================
         if (p.split) {
             const int ctid = threadIdx.x - 6 * 32;
-            constexpr int n16 = kARows * 128 / 16;                // 16-byte words TMA delivered for A
+            const int n16 = a_rows * 128 / 16;                    // 16-byte words TMA delivered for A
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
-                for (int it = 0; it < 3 * p.nchunks; ++it) {
+                for (int it = 0; it < T * p.nchunks; ++it) {
                     mbar_wait(&full_bar[s], ph);
                     uint4 *st = reinterpret_cast<uint4 *>(base + (size_t)s * stage_bytes);
                     uint4 *sl = reinterpret_cast<uint4 *>(base + (size_t)s * stage_bytes + kABytes);
@@ -290,10 +298,23 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const long long per_img = (long long)(p.h + 2) * pitch;
+        // where row `pix` lands, and whether it carries a value (border pixels of the bordered layout are stored as zeros)
+        auto place = [&](long long pix, bool inside, long long &dst, bool &interior) {
+            dst = pix; interior = inside;
+            if (p.border) {
+                const long long rem = pix % per_img;
+                const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
+                interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;
+            } else if (p.dst_h > 0 && inside) {
+                const long long hw = (long long)p.dst_h * p.dst_w, b = pix / hw, rem = pix - b * hw;
+                const int yy = (int)(rem / p.dst_w), xx = (int)(rem - (long long)yy * p.dst_w);
+                dst = (b * (p.dst_h + 2) + yy + 1) * (p.dst_w + 2) + xx + 1;
+            }
+        };
         // bias / ReLU / optional TF32 rounding / zero border, 16 channels from c0
         auto store16 = [&](const float (&v)[16], long long pix, bool interior, int c0) {
             const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
-            float4 *op = reinterpret_cast<float4 *>(p.out + pix * p.np + c0);
+            float4 *op = reinterpret_cast<float4 *>(p.out + pix * p.ldc + c0);
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -316,7 +337,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             // terms' accumulator once at the end of the tile
             constexpr int kMaxChunks = 8;                             // NP <= 128
             float acc[kMaxChunks][16];
-            const int ngroups = (3 * p.nchunks + kGroup - 1) / kGroup;
+            const int ngroups = (T * p.nchunks + kGroup - 1) / kGroup;
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
             auto drain = [&](uint32_t trow) {
 #pragma unroll
@@ -334,9 +355,8 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
                 const long long pix = (long long)tile * kTileM + r;
                 const bool inside = pix < p.P;
-                const long long rem = pix % per_img;
-                const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
-                const bool interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;
+                long long dst; bool interior;
+                place(pix, inside, dst, interior);
 #pragma unroll
                 for (int c = 0; c < kMaxChunks; ++c)
 #pragma unroll
@@ -356,7 +376,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (inside) {
 #pragma unroll
                     for (int c = 0; c < kMaxChunks; ++c)
-                        if (c * 16 < p.np) store16(acc[c], pix, interior, c * 16);
+                        if (c * 16 < p.np) store16(acc[c], dst, interior, c * 16);
                 }
             }
         } else {
@@ -364,9 +384,8 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
                 const long long pix = (long long)tile * kTileM + r;
                 const bool inside = pix < p.P;
-                const long long rem = pix % per_img;
-                const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
-                const bool interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;   // border pixels are stored as zeros
+                long long dst; bool interior;
+                place(pix, inside, dst, interior);
                 const int slot = j & 1;
                 mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
                 tc_fence_after();
@@ -374,7 +393,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 for (int c0 = 0; c0 < p.np; c0 += 16) {
                     float v[16];
                     tmem_ld16(trow + (uint32_t)c0, v);
-                    if (inside) store16(v, pix, interior, c0);
+                    if (inside) store16(v, dst, interior, c0);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -397,28 +416,35 @@ using namespace decnet::conv2dnhwc;
 
 extern "C" {
 
-int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
-                               int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream)
+// Shared launcher.  taps = 3: 3x3 conv on the zero-bordered layout [B, h+2, w+2, cp] -> [B, h+2, w+2, ldc] (np channels
+// written from out_pad); taps = 1: GEMM over P rows of cp channels (border = 1: the rows are the pixels of such a bordered
+// tensor and border rows are stored as zeros; dst_h > 0: the P = B*dst_h*dst_w rows of a flat grid are stored at the interior
+// pixels of a bordered [B, dst_h+2, dst_w+2, ldc] tensor).
+static int launch_nhwc(const float *x, const float *w_packed, const float *bias, float *out, long long P, int B, int h, int w,
+                       int cp, int np, int taps, int border, int relu, int round_out_tf32, int split, int ldc, int dst_h, int dst_w,
+                       void *stream)
 {
-    DECNET_REQUIRE(x_pad && w_packed && bias && out_pad, "null pointer");
-    DECNET_REQUIRE(B > 0 && h > 0 && w > 0, "non-positive size");
-    DECNET_REQUIRE(cp % 8 == 0 && cp >= 8 && cp <= 4096, "cp=%d must be a multiple of 8", cp);
+    DECNET_REQUIRE(x && w_packed && bias && out, "null pointer");
+    DECNET_REQUIRE(P > 0, "non-positive size");
+    DECNET_REQUIRE(cp % 8 == 0 && cp >= 8 && cp <= 8192, "cp=%d must be a multiple of 8", cp);
     DECNET_REQUIRE(np % 16 == 0 && np >= 16 && np <= 256, "np=%d must be a multiple of 16 in [16,256]", np);
     DECNET_REQUIRE(!split || np <= 128, "split (3xTF32) mode accumulates in registers: np=%d must be <= 128", np);
-    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x_pad) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0 &&
-                   (reinterpret_cast<uintptr_t>(out_pad) & 15u) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0,
+    DECNET_REQUIRE(ldc >= np && ldc % 4 == 0, "ldc=%d must be a multiple of 4 and >= np=%d", ldc, np);
+    DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0,
                    "pointers must be 16-byte aligned");
     Params p{};
-    p.bias = bias; p.out = out_pad; p.B = B; p.h = h; p.w = w; p.cp = cp; p.np = np;
+    p.bias = bias; p.out = out; p.B = B; p.h = h; p.w = w; p.cp = cp; p.np = np;
+    p.taps = taps; p.border = border; p.ldc = ldc; p.dst_h = dst_h; p.dst_w = dst_w;
     p.nchunks = (cp + 31) / 32;
     p.last_ksteps = (cp - (p.nchunks - 1) * 32) / 8;
-    p.P = (long long)B * (h + 2) * (w + 2);
+    p.P = P;
     DECNET_REQUIRE(p.P + 2ll * (w + 3) < (1ll << 31), "tensor too large for 32-bit TMA coordinates");
     p.relu = relu; p.round_tf32 = round_out_tf32; p.split = split ? 1 : 0;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;
     if (p.split) p.tmem_cols *= 2;                                  // two chain slots + two small-term slots
     p.num_tiles = (int)((p.P + kTileM - 1) / kTileM);
-    const size_t stage_bytes = ((size_t)kABytes + (size_t)3 * np * 128) * (p.split ? 2 : 1);
+    const size_t stage_bytes = ((size_t)kABytes + (size_t)taps * np * 128) * (p.split ? 2 : 1);
     p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     DECNET_REQUIRE(p.stages >= 2, "stage too large (np=%d)", np);
@@ -427,15 +453,15 @@ int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const 
     {
         const uint64_t dims[2] = {(uint64_t)cp, (uint64_t)p.P};
         const uint64_t strides[1] = {(uint64_t)cp * 4};
-        const uint32_t box[2] = {32u, (uint32_t)kARows};
-        int rc = encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x_pad, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+        const uint32_t box[2] = {32u, (uint32_t)(taps == 3 ? kARows : kTileM)};
+        int rc = encode_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, p.split ? 18u : 9u};
+        const uint64_t dims[3] = {(uint64_t)cp, (uint64_t)np, (uint64_t)(taps * taps * (p.split ? 2 : 1))};
         const uint64_t strides[2] = {(uint64_t)cp * 4, (uint64_t)np * cp * 4};
-        const uint32_t box[3] = {32u, (uint32_t)np, 3u};
+        const uint32_t box[3] = {32u, (uint32_t)np, (uint32_t)taps};
         int rc = encode_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, w_packed, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
@@ -455,6 +481,34 @@ int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const 
     const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
     conv2d_nhwc_halo_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
     return after_launch("conv2d_nhwc_halo_kernel");
+}
+
+int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                               int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream)
+{
+    DECNET_REQUIRE(B > 0 && h > 0 && w > 0, "non-positive size");
+    return launch_nhwc(x_pad, w_packed, bias, out_pad, (long long)B * (h + 2) * (w + 2), B, h, w, cp, np, 3, 1, relu,
+                       round_out_tf32, split, np, 0, 0, stream);
+}
+
+int decnet_conv2d_tc_nhwc_halo_ldc(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                                   int B, int h, int w, int cp, int np, int ldc, int relu, int split, void *stream)
+{
+    DECNET_REQUIRE(B > 0 && h > 0 && w > 0, "non-positive size");
+    return launch_nhwc(x_pad, w_packed, bias, out_pad, (long long)B * (h + 2) * (w + 2), B, h, w, cp, np, 3, 1, relu, 0, split,
+                       ldc, 0, 0, stream);
+}
+
+int decnet_gemm_tc_nhwc(const float *x, const float *w_packed, const float *bias, float *out, long long P, int cp, int np,
+                        int ldc, int relu, int split, int border_B, int border_h, int border_w, int dst_h, int dst_w, void *stream)
+{
+    const int border = border_B > 0 ? 1 : 0;
+    if (border)
+        DECNET_REQUIRE(P == (long long)border_B * (border_h + 2) * (border_w + 2) && dst_h == 0,
+                       "bordered rows: P=%lld must be B*(h+2)*(w+2)", P);
+    if (dst_h > 0) DECNET_REQUIRE(dst_w > 0 && P % ((long long)dst_h * dst_w) == 0, "P=%lld is not a whole number of %dx%d grids", P, dst_h, dst_w);
+    return launch_nhwc(x, w_packed, bias, out, P, border_B, border_h, border ? border_w : 0, cp, np, 1, border, relu, 0, split, ldc,
+                       dst_h, dst_w, stream);
 }
 
 int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,

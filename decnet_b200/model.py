@@ -132,11 +132,20 @@ class Conv2dUnit(_Cached, nn.Module):
         d = c.dilation[0]
         cin, cout = c.in_channels, c.out_channels
         split = _split(self)
-        ok = (self._same_pad_3x3() and ((d <= 4 and (cin >= 8 or cout >= 3)) or (d <= 8 and cin >= 8))
-              and ops.conv2d_tf32_supported(cin, cout, x.shape[2], x.shape[3], d, split))
+        one = c.kernel_size == (1, 1) and c.stride == (1, 1) and c.padding == (0, 0) and c.groups == 1 and cin >= 8
+        ok = ((one or (self._same_pad_3x3() and ((d <= 4 and (cin >= 8 or cout >= 3)) or (d <= 8 and cin >= 8))))
+              and ops.conv2d_tf32_supported(cin, cout, x.shape[2], x.shape[3], 1 if one else d, split))
         if not ok:
             return None
-        return self._cached(("tc", split), lambda: ops.pack_conv2d_tf32_nchw_weights(*self.folded(), split=split))
+
+        def build():
+            w, b = self.folded()
+            if one:                                  # a 1x1 conv is the centre tap of a 3x3 one
+                w3 = torch.zeros((cout, cin, 3, 3), dtype=w.dtype, device=w.device)
+                w3[:, :, 1, 1] = w[:, :, 0, 0]
+                w = w3
+            return ops.pack_conv2d_tf32_nchw_weights(w, b, split=split)
+        return self._cached(("tc", split), build)
 
     def forward_cat(self, srcs, w_valid=None):
         """forward(torch.cat(srcs, 1)) with single-channel maps given as [B,H,W]; the concatenation is never
@@ -161,7 +170,8 @@ class Conv2dUnit(_Cached, nn.Module):
         if not (x.is_cuda and x.dtype == torch.float32):
             raise _lib.DecnetError("decnet_b200 units take float32 CUDA tensors (there is no CPU path)")
         c = self.conv
-        tc = self.tensor_core(x) if addend is None else None
+        nat_first = c.kernel_size == (1, 1) and self.native() is not None      # tiny 1x1 layers: the direct kernel
+        tc = self.tensor_core(x) if (addend is None and not nat_first) else None
         if tc is not None:
             return ops.conv2d_tf32_nchw_cat([x.contiguous()], tc[0], tc[1], c.out_channels, c.dilation[0], self.relu,
                                             w_valid or 0, split=_split(self))

@@ -690,3 +690,108 @@ def dynup_glue_nhwc(logits_nhwc, disp, pad=False):
     _call("decnet_dynup_glue_nhwc", disp, logits_nhwc.data_ptr(), disp.data_ptr(), out.data_ptr(), B, h, w, NP,
           1 if pad else 0)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# feature extractor on the tensor-core GEMM (SURVEY.md section 8f rank 2): GEMM mode of the halo kernel + data movement
+# --------------------------------------------------------------------------------------
+def pack_gemm_weights(w2d, bias, cp, split=False, n0=0, n1=None):
+    """[N, K] (+ bias [N]) rows n0..n1 -> ([1 or 2][NP][cp] fp32, bias [NP]), NP = (n1 - n0) rounded up to 16, K zero-padded to
+    cp; split: the TF32 hi parts then the lo parts (3xTF32)."""
+    n1 = w2d.shape[0] if n1 is None else n1
+    n, k = n1 - n0, w2d.shape[1]
+    np_ = (n + 15) // 16 * 16
+    out = torch.zeros((1, np_, cp), dtype=torch.float32, device=w2d.device)
+    out[0, :n, :k] = w2d[n0:n1].float()
+    out = torch.cat(split_tf32(out), 0) if split else rna_tf32(out)
+    b = torch.zeros(np_, dtype=torch.float32, device=w2d.device)
+    b[:n] = bias[n0:n1].float()
+    return out.contiguous(), b.contiguous(), np_
+
+
+def gemm_tc(x, w_packed, bias, out, relu, split=False, col=0, border=None, dst_hw=None):
+    """out[:, col:col+NP] = act(x @ w^T + bias) on the tensor cores.  x [..., cp] rows (all leading dims flattened), out rows of
+    out.shape[-1] floats.  border=(B,h,w): x and out are zero-bordered [B,h+2,w+2,.] tensors, border rows stay zero;
+    dst_hw=(h,w): x is a flat [B*h*w, cp] grid, out a zero-bordered [B,h+2,w+2,.] tensor (interior written)."""
+    _chk("x", x)
+    _chk("out", out, x)
+    cp, ldc, np_ = x.shape[-1], out.shape[-1], w_packed.shape[1]
+    P = x.numel() // cp
+    if w_packed.shape[0] != (2 if split else 1) or w_packed.shape[2] != cp:
+        raise ValueError(f"w_packed {tuple(w_packed.shape)} does not match cp={cp}, split={split}")
+    if col % 4 or col + np_ > ldc:
+        raise ValueError(f"column slice [{col}, {col + np_}) does not fit rows of {ldc}")
+    bB, bh, bw = border if border is not None else (0, 0, 0)
+    dh, dw = dst_hw if dst_hw is not None else (0, 0)
+    rows_out = out.numel() // ldc
+    want = P if dst_hw is None else (P // (dh * dw)) * (dh + 2) * (dw + 2)
+    if rows_out != want:
+        raise ValueError(f"out has {rows_out} rows, expected {want}")
+    _call("decnet_gemm_tc_nhwc", x, x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr() + 4 * col, P, cp, np_, ldc,
+          1 if relu else 0, 1 if split else 0, bB, bh, bw, dh, dw)
+    return out
+
+
+def conv2d_nhwc_halo_into(x_pad, w_packed, bias, out_pad, relu, split=False, col=0):
+    """3x3 conv on the zero-bordered layout writing channels [col, col+NP) of the wider bordered tensor out_pad."""
+    _chk("x_pad", x_pad)
+    _chk("out_pad", out_pad, x_pad)
+    B, hp, wp, cp = x_pad.shape
+    np_, ldc = w_packed.shape[1], out_pad.shape[-1]
+    if tuple(out_pad.shape[:3]) != (B, hp, wp) or col % 4 or col + np_ > ldc:
+        raise ValueError(f"out_pad {tuple(out_pad.shape)} / col {col} do not fit x_pad {tuple(x_pad.shape)}, NP {np_}")
+    _call("decnet_conv2d_tc_nhwc_halo_ldc", x_pad, x_pad.data_ptr(), w_packed.data_ptr(), bias.data_ptr(),
+          out_pad.data_ptr() + 4 * col, B, hp - 2, wp - 2, cp, np_, ldc, 1 if relu else 0, 1 if split else 0)
+    return out_pad
+
+
+def im2col3x3(src, layout, C, stride=1, dilation=1, kp=None):
+    """3x3 windows (zero padding = dilation) as GEMM rows [B*Ho*Wo, kp], column tap*C + c.
+    layout: "nchw" [B,C,H,W]; "nhwc" flat [B,H,W,ld]; "nhwc_pad" zero-bordered [B,H+2,W+2,ld] (its interior is the grid)."""
+    _chk("src", src)
+    if layout == "nchw":
+        B, _, H, W = src.shape
+        sb, sc, sy, sx, off = src.shape[1] * H * W, H * W, W, 1, 0
+    elif layout == "nhwc":
+        B, H, W, ld = src.shape
+        sb, sc, sy, sx, off = H * W * ld, 1, W * ld, ld, 0
+    elif layout == "nhwc_pad":
+        B, hp, wp, ld = src.shape
+        H, W = hp - 2, wp - 2
+        sb, sc, sy, sx, off = hp * wp * ld, 1, wp * ld, ld, (wp + 1) * ld
+    else:
+        raise ValueError(layout)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1                # k 3, pad = dilation = 1 for the strided convs
+    kp = (9 * C + 7) // 8 * 8 if kp is None else kp
+    out = torch.empty((B * Ho * Wo, kp), dtype=torch.float32, device=src.device)
+    _call("decnet_im2col3x3", src, src.data_ptr() + 4 * off, out.data_ptr(), B, int(C), H, W, sb, sc, sy, sx, int(stride),
+          int(dilation), Ho, Wo, kp)
+    return out, Ho, Wo
+
+
+def deconv3x3s3_shuffle(x, out_pad, B, h, w, cout, col=0):
+    """GEMM-form ConvTranspose2d(k3, s3) result [B*h*w, ld] (column tap*cout + co) -> interior of out_pad [B,3h+2,3w+2,ldc]."""
+    _chk("x", x)
+    _chk("out_pad", out_pad, x, (B, 3 * h + 2, 3 * w + 2, out_pad.shape[-1]))
+    _call("decnet_deconv3x3s3_shuffle", x, x.data_ptr(), out_pad.data_ptr(), B, h, w, int(cout), x.shape[-1], out_pad.shape[-1], int(col))
+    return out_pad
+
+
+def nhwc_to_nchw(x, B, C, h, w, pad=False):
+    """Channels-last rows of x.shape[-1] floats (pad: zero-bordered [B,h+2,w+2,ld]) -> NCHW [B,C,h,w]."""
+    _chk("x", x)
+    out = torch.empty((B, int(C), h, w), dtype=torch.float32, device=x.device)
+    _call("decnet_nhwc_to_nchw", x, x.data_ptr(), out.data_ptr(), B, int(C), x.shape[-1], h, w, 1 if pad else 0)
+    return out
+
+
+def conv3x3s3_nchw(x, w, bias, relu=True):
+    """Conv2d(3x3, stride 3, pad 1) + bias [+ ReLU] on NCHW, direct fp32 (w [24,Cin,3,3], BN folded)."""
+    _chk("x", x)
+    B, cin, H, W = x.shape
+    cout = w.shape[0]
+    wpk = w.float().permute(1, 2, 3, 0).reshape(cin, 9, cout).contiguous()
+    out = torch.empty((B, cout, (H - 1) // 3 + 1, (W - 1) // 3 + 1), dtype=torch.float32, device=x.device)
+    _call("decnet_conv3x3s3_nchw", x, x.data_ptr(), wpk.data_ptr(), bias.float().contiguous().data_ptr(), out.data_ptr(), B, cin, H, W,
+          cout, 1 if relu else 0)
+    return out

@@ -241,6 +241,39 @@ int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, cons
 int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream);
 
+/* The same kernel writing a channel slice of a wider bordered tensor (row stride ldc floats, np channels from out_pad). */
+int decnet_conv2d_tc_nhwc_halo_ldc(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
+                                   int B, int h, int w, int cp, int np, int ldc, int relu, int split, void *stream);
+
+/* GEMM mode of the same kernel (one tap): out[p, 0..np) = act(bias + sum_k x[p, k] * w[n, k]) over P rows of cp channels --
+ * the 1x1 convs of the feature extractor, and (behind decnet_im2col3x3) its stride-3, dilated and 1/27-resolution 3x3 convs
+ * and the GEMM form of its 216 -> 72 transposed conv (modules/submodule.py:225-241, 272-286, 162-177).
+ *   x fp32 [P, cp] (cp multiple of 8, rows 16-byte aligned), w_packed fp32 [1 or 2 (split: hi, lo)][np][cp], bias [np],
+ *   out rows of ldc floats (np <= ldc: writes a channel slice of a wider tensor; np <= 128 in split mode).
+ *   border_B > 0: the rows are the pixels of a zero-bordered [border_B, border_h+2, border_w+2] tensor; border rows are
+ *                 stored as zeros (same pixel index in and out).
+ *   dst_h > 0   : the P = B*dst_h*dst_w rows of a flat grid are stored at the interior pixels of a zero-bordered
+ *                 [B, dst_h+2, dst_w+2, ldc] tensor (whose border the caller zeroed). */
+int decnet_gemm_tc_nhwc(const float *x, const float *w_packed, const float *bias, float *out, long long P, int cp, int np,
+                        int ldc, int relu, int split, int border_B, int border_h, int border_w, int dst_h, int dst_w, void *stream);
+
+/* Feature-extractor data movement (featext.cu).
+ *   decnet_im2col3x3: out[(b*Ho+yo)*Wo+xo][tap*C + c] = src(b, c, yo*stride + (ky-1)*dil, xo*stride + (kx-1)*dil), zero outside
+ *     the logical HxW grid, columns 9C..Kp-1 zero; src is addressed as src[b*sb + c*sc + y*sy + x*sx] (element strides; sc = 1:
+ *     channels-last, flat or the interior of a bordered tensor; sx = 1: NCHW).
+ *   decnet_deconv3x3s3_shuffle: in [B*h*w, ld_in] with column (ky*3+kx)*Cout + co -> out_pad[b, 3y+ky+1, 3x+kx+1, c_off+co]
+ *     of a zero-bordered channels-last [B, 3h+2, 3w+2, ldc] tensor (ConvTranspose2d k 3 s 3 as a GEMM + this shuffle).
+ *   decnet_nhwc_to_nchw: channels-last rows of ld floats (pad = 1: interior of a bordered tensor) -> NCHW [B, C, h, w].
+ *   decnet_conv3x3s3_nchw: Conv2d(3x3, stride 3, pad 1) + bias [+ ReLU] on NCHW, direct fp32, Cout = 24;
+ *     w_packed [Cin][9][Cout]. */
+int decnet_im2col3x3(const float *src, float *out, int B, int C, int H, int W, long long sb, long long sc, long long sy,
+                     long long sx, int stride, int dilation, int Ho, int Wo, int Kp, void *stream);
+int decnet_deconv3x3s3_shuffle(const float *in, float *out_pad, int B, int h, int w, int Cout, int ld_in, int ldc, int c_off,
+                               void *stream);
+int decnet_nhwc_to_nchw(const float *in, float *out, int B, int C, int ld, int h, int w, int pad, void *stream);
+int decnet_conv3x3s3_nchw(const float *x, const float *w_packed, const float *bias, float *out, int B, int Cin, int H, int W,
+                          int Cout, int relu, void *stream);
+
 /* Layout bridges around decnet_conv2d_tf32_nhwc_halo for layers whose neighbours are NCHW (the 72-channel refinement
  * layers of the 1/9 level): concatenation of up to three NCHW fp32 sources -> zero-bordered channels-last
  * [B,h+2,w+2,CP] (channel padding zero; round_tf32 != 0 rounds the values to TF32 for the kernel's plain-TF32 mode),
