@@ -172,9 +172,16 @@ class FeatExtNetChannelPlus(_Cached, nn.Module):
         return self._cached(("coarse", split), build)
 
     def _gemm(self, x, packs, out, split, col0=0, **kw):
+        if not split:
+            x = ops.rna_tf32(x)          # plain-TF32 mode: operands rounded to nearest (the MMA itself would truncate)
         for wp, bp, np_, a, relu in packs:
             ops.gemm_tc(x, wp, bp, out, relu, split=split, col=col0 + a, **kw)
         return out
+
+    @staticmethod
+    def _halo(x, pack, split):
+        wp, bp, _, relu = pack
+        return ops.conv2d_tf32_nhwc_halo(x if split else ops.rna_tf32(x), wp, bp, relu, split=split)
 
     @torch.no_grad()
     def forward(self, x):
@@ -202,8 +209,7 @@ class FeatExtNetChannelPlus(_Cached, nn.Module):
         a, _, _ = ops.im2col3x3(conv1, "nchw", c1, stride=3)
         t2 = self._gemm(a, pk["conv2_0"], z(B, h2 + 2, w2 + 2, np2), split, dst_hw=(h2, w2))
         for key in ("conv2_1", "conv2_2"):
-            wp, bp, _, relu = pk[key]
-            t2 = ops.conv2d_tf32_nhwc_halo(t2, wp, bp, relu, split=split)
+            t2 = self._halo(t2, pk[key], split)
         conv2 = t2                                              # [B, h2+2, w2+2, 80] (72 channels + zero padding)
         # ---- 1/27 resolution: flat channels-last rows of ld3 = 224 floats (216 channels + zero padding)
         a, _, _ = ops.im2col3x3(conv2, "nhwc_pad", c2, stride=3)
@@ -226,10 +232,7 @@ class FeatExtNetChannelPlus(_Cached, nn.Module):
         dcat = z(B, h2 + 2, w2 + 2, pk["ld_dcat"])
         ops.deconv3x3s3_shuffle(up, dcat, B, h3, w3, c2, col=0)
         self._gemm(conv2, pk["trans2"], dcat, split, col0=c2, border=(B, h2, w2))
-        wp, bp, _, relu = pk["dconv0"]
-        r = ops.conv2d_tf32_nhwc_halo(dcat, wp, bp, relu, split=split)
-        wp, bp, _, relu = pk["dconv1"]
-        r = ops.conv2d_tf32_nhwc_halo(r, wp, bp, relu, split=split)
+        r = self._halo(self._halo(dcat, pk["dconv0"], split), pk["dconv1"], split)
         res = ops.nhwc_to_nchw(r, B, c2, h2, w2, pad=True)
         out["stage1"] = res
         # ---- 1/3 and full resolution: NCHW again

@@ -153,6 +153,10 @@ class Conv2dUnit(_Cached, nn.Module):
         w_valid: the tensors are right-padded to a 16-byte row pitch (see pad_pitch); columns >= w_valid of the
         result are zeros."""
         x0 = srcs[0]
+        if w_valid is None and x0.shape[-1] % 4:
+            # a width that is not a multiple of 4 (16-byte row pitch for TMA): run on right-padded copies and crop
+            padded = [pad_pitch(t) for t in srcs]
+            return unpad_pitch(self.forward_cat([t for t, _ in padded], w_valid=padded[0][1]), padded[0][1])
         chans = tuple(1 if t.dim() == 3 else t.shape[1] for t in srcs)
         c = self.conv
         d = c.dilation[0]
@@ -170,6 +174,9 @@ class Conv2dUnit(_Cached, nn.Module):
         if not (x.is_cuda and x.dtype == torch.float32):
             raise _lib.DecnetError("decnet_b200 units take float32 CUDA tensors (there is no CPU path)")
         c = self.conv
+        if w_valid is None and addend is None and x.shape[-1] % 4 and self.native() is None:
+            xp, wv = pad_pitch(x)                      # see forward_cat: pitch-padded copy, cropped result
+            return unpad_pitch(self.forward(xp, w_valid=wv), wv)
         nat_first = c.kernel_size == (1, 1) and self.native() is not None      # tiny 1x1 layers: the direct kernel
         tc = self.tensor_core(x) if (addend is None and not nat_first) else None
         if tc is not None:
