@@ -25,6 +25,7 @@ SIGNATURES = {
     "decnet_spamat_fwd": (_i, [_f32p] * 7 + [_i] * 5 + [C.c_void_p]),
     "decnet_spavar_fwd": (_i, [_f32p] * 8 + [_i] * 5 + [C.c_void_p]),
     "decnet_spamat_spavar_fwd": (_i, [_f32p] * 8 + [_i] * 5 + [C.c_void_p]),
+    "decnet_spamat_spavar_fwd_levels": (_i, [_i] + [C.c_void_p] * 13 + [C.c_void_p]),
     "decnet_spamat_bwd": (_i, [_f32p] * 10 + [_i] * 5 + [C.c_void_p]),
     "decnet_spavar_bwd": (_i, [_f32p] * 12 + [_i] * 5 + [C.c_void_p]),
     "decnet_candidate_signature": (_i, [_f32p] * 4 + [_i] * 4 + [C.c_void_p]),

@@ -38,6 +38,29 @@ im2col3x3_cl_kernel(const float *__restrict__ src, float *__restrict__ out, int 
     out[i] = v;
 }
 
+// the same with four channels per thread (C, Kp, strides and base all multiples of 4 floats): 128-bit loads and stores
+__global__ void __launch_bounds__(kBlock)
+im2col3x3_cl4_kernel(const float *__restrict__ src, float *__restrict__ out, int C, int H, int W, long long sb, long long sy,
+                     long long sx, int stride, int dil, int Ho, int Wo, int Kp, long long n4)
+{
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;      // over P * Kp / 4
+    if (i >= n4) return;
+    const int kq = Kp >> 2;
+    const int k = (int)(i % kq) * 4;
+    long long p = i / kq;
+    const int xo = (int)(p % Wo); p /= Wo;
+    const int yo = (int)(p % Ho);
+    const long long b = p / Ho;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < 9 * C) {
+        const int tap = k / C, c = k - tap * C;
+        const int y = yo * stride + (tap / 3 - 1) * dil, x = xo * stride + (tap % 3 - 1) * dil;
+        if (y >= 0 && y < H && x >= 0 && x < W)
+            v = __ldg(reinterpret_cast<const float4 *>(src + b * sb + (long long)y * sy + (long long)x * sx + c));
+    }
+    reinterpret_cast<float4 *>(out)[i] = v;
+}
+
 // ---- im2col, x-contiguous source (NCHW: sx == 1): 32 output pixels of one row x 32 k per block, transposed through smem
 __global__ void __launch_bounds__(1024)
 im2col3x3_xc_kernel(const float *__restrict__ src, float *__restrict__ out, int C, int H, int W, long long sb, long long sc,
@@ -171,6 +194,13 @@ int decnet_im2col3x3(const float *src, float *out, int B, int C, int H, int W, l
     DECNET_REQUIRE(Kp >= 9 * C, "Kp=%d < 9*C=%d", Kp, 9 * C);
     DECNET_REQUIRE(sc == 1 || sx == 1, "the source must be channels-last (sc = 1) or x-contiguous (sx = 1)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (sc == 1 && C % 4 == 0 && Kp % 4 == 0 && sb % 4 == 0 && sy % 4 == 0 && sx % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        const long long n4 = (long long)B * Ho * Wo * (Kp / 4);
+        im2col3x3_cl4_kernel<<<(unsigned)((n4 + kBlock - 1) / kBlock), kBlock, 0, st>>>(src, out, C, H, W, sb, sy, sx, stride, dilation,
+                                                                                    Ho, Wo, Kp, n4);
+        return after_launch("im2col3x3_cl4_kernel");
+    }
     if (sc == 1) {
         const long long n = (long long)B * Ho * Wo * Kp;
         im2col3x3_cl_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(src, out, C, H, W, sb, sy, sx, stride, dilation,

@@ -242,15 +242,12 @@ __device__ inline void gather_columns_global(const uint32_t *__restrict__ list, 
     }
 }
 
-template <int MODE, int NT, int NB>
-__global__ void __launch_bounds__(NT, NB)
-sparse_row_gather_kernel(const __grid_constant__ RowArgs a)
+template <int MODE, int NT>
+__device__ __forceinline__ void gather_row(const RowArgs &a, const int row, unsigned char *smem_raw)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int C = a.C, W = a.W, D = a.D;
     const int Cp = (C + 3) & ~3;
-    const int row = blockIdx.x;
     const int b = row / a.H, h = row - b * a.H;
     const size_t plane = (size_t)a.H * W;
     const size_t m0 = (size_t)row * W;
@@ -285,6 +282,37 @@ sparse_row_gather_kernel(const __grid_constant__ RowArgs a)
         process_row<MODE, 0>(s, Lrow, Rrow, (int)plane, C, Cp, D, disp_row,
                              a.out_a + m0, a.out_b + m0, a.sum_sim + m0, a.max_cost + m0, tid, NT);
     }
+}
+
+template <int MODE, int NT, int NB>
+__global__ void __launch_bounds__(NT, NB)
+sparse_row_gather_kernel(const __grid_constant__ RowArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    gather_row<MODE, NT>(a, blockIdx.x, smem_raw);
+}
+
+// The rows of SEVERAL pyramid levels in one launch (SparseDenseNetRefinementMask.py:183-192 runs the ops level after
+// level; their inputs -- features and masks -- do not depend on each other).  C*W is the same at every level, so a row is
+// the same amount of data everywhere, but the coarse levels have few rows (480 and 1440 against 4320 at B = 8): as launches
+// of their own they are one or two waves of latency (0.20 / 0.55 of the HBM roofline against 0.63 for the finest level).
+// Here the blocks of the finest level come first and the coarse rows fill the machine behind them.
+constexpr int kMaxLevels = 4;
+struct MultiArgs {
+    RowArgs lv[kMaxLevels];
+    int first_row[kMaxLevels + 1];        // block index of each level's first row (levels in launch order)
+    int nlev;
+};
+
+template <int MODE, int NT, int NB>
+__global__ void __launch_bounds__(NT, NB)
+sparse_row_gather_multi_kernel(const __grid_constant__ MultiArgs m)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int lvl = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i) lvl += (i < m.nlev && (int)blockIdx.x >= m.first_row[i]) ? 1 : 0;
+    gather_row<MODE, NT>(m.lv[lvl], (int)blockIdx.x - m.first_row[lvl], smem_raw);
 }
 
 // -------------------------------------------------------------------------------------
@@ -675,6 +703,45 @@ static int launch_gather(const float *L, const float *R, const float *ml, const 
     return after_launch("sparse_row_gather_kernel");
 }
 
+// Fused SpaMat + SpaVar over the rows of up to kMaxLevels levels, one launch (levels given finest first).
+static int launch_gather_multi(int nlev, const float *const *L, const float *const *R, const float *const *ml,
+                               const float *const *mr, float *const *out, float *const *var, float *const *ssim,
+                               float *const *mx, const int *B, const int *C, const int *H, const int *W, const int *D,
+                               cudaStream_t st)
+{
+    constexpr int NT = 256, NB = 4;
+    MultiArgs m{};
+    m.nlev = nlev;
+    size_t smem = 0;
+    int rows = 0;
+    for (int i = 0; i < nlev; ++i) {
+        RowArgs &a = m.lv[i];
+        const size_t need = gather_smem(C[i], W[i], NB, a.rc_cap);
+        smem = need > smem ? need : smem;
+        a.L = L[i]; a.R = R[i]; a.lmask = ml[i]; a.rmask = mr[i]; a.disp_in = nullptr;
+        a.out_a = out[i]; a.out_b = var[i]; a.sum_sim = ssim[i]; a.max_cost = mx[i];
+        a.C = C[i]; a.H = H[i]; a.W = W[i]; a.D = D[i] < 0 ? 0 : D[i]; a.nrows = B[i] * H[i];
+        a.vec_ok = (W[i] % 4 == 0) && aligned16(out[i]) && aligned16(ssim[i]) && aligned16(mx[i]) && aligned16(var[i]);
+        m.first_row[i] = rows;
+        rows += a.nrows;
+    }
+    m.first_row[nlev] = rows;
+    auto kern = sparse_row_gather_multi_kernel<MODE_FUSED, NT, NB>;
+    {
+        static std::mutex mu;
+        static size_t set_for[64] = {0};
+        int dev = 0;
+        DECNET_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || set_for[dev] < smem) {
+            DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) set_for[dev] = smem;
+        }
+    }
+    kern<<<rows, NT, smem, st>>>(m);
+    return after_launch("sparse_row_gather_multi_kernel");
+}
+
 // Shared memory of the pipelined kernel: mask staging + two list sets + two operand buffers in a 1/NB share of the SM.
 static size_t stream_smem(int C, int W, int nb, int &rc_cap)
 {
@@ -862,6 +929,24 @@ int decnet_spamat_spavar_fwd(const float *L, const float *R, const float *ml, co
                              float *out, float *var, float *ssim, float *mx,
                              int B, int C, int H, int W, int D, void *stream) {
     return forward_dispatch(MODE_FUSED, L, R, ml, mr, nullptr, out, var, ssim, mx, B, C, H, W, D, stream);
+}
+
+int decnet_spamat_spavar_fwd_levels(int nlev, const float *const *L, const float *const *R, const float *const *ml,
+                                    const float *const *mr, float *const *out, float *const *var, float *const *ssim,
+                                    float *const *mx, const int *B, const int *C, const int *H, const int *W, const int *D,
+                                    void *stream) {
+    DECNET_REQUIRE(nlev >= 1 && nlev <= kMaxLevels, "1..%d levels, got %d", kMaxLevels, nlev);
+    DECNET_REQUIRE(L && R && ml && mr && out && var && ssim && mx && B && C && H && W && D, "null pointer");
+    long long rows = 0;
+    for (int i = 0; i < nlev; ++i) {
+        DECNET_REQUIRE(L[i] && R[i] && ml[i] && mr[i] && out[i] && var[i] && ssim[i] && mx[i], "level %d: null pointer", i);
+        DECNET_REQUIRE(B[i] > 0 && C[i] > 0 && H[i] > 0 && W[i] > 0 && W[i] <= 65535, "level %d: bad size", i);
+        DECNET_REQUIRE((long long)C[i] * H[i] * W[i] < (1ll << 31), "level %d: C*H*W too large for the gather kernel", i);
+        rows += (long long)B[i] * H[i];
+    }
+    DECNET_REQUIRE(rows < (1ll << 31), "too many rows");
+    g_last_path = 3; g_last_variant = 3;
+    return launch_gather_multi(nlev, L, R, ml, mr, out, var, ssim, mx, B, C, H, W, D, static_cast<cudaStream_t>(stream));
 }
 
 int decnet_spamat_bwd(const float *L, const float *R, const float *ml, const float *mr, const float *out,

@@ -630,21 +630,24 @@ class DecompMatching(nn.Module):
             side.wait_stream(main)                       # fork: the features are ready on the main stream
             with torch.cuda.stream(side):
                 branch, events, packs, pack_events = [], [], [], []
-                # first what the main chain needs first: the feature channels of every level's up-sampling input
-                for s in range(1, self.num_stage):
-                    pk = None
+                # first what the main chain needs first: the feature channels of the first level's up-sampling input (the
+                # other levels' packs follow the sparse launch below)
+                packs, pack_events = [None] * (self.num_stage - 1), [None] * (self.num_stage - 1)
+
+                def prepack(s):
                     if s < self.skip_stage_id:
                         pk = self.dynamic_upsampling[s - 1].prepack(left_feats[f"stage{s}"])
                         pk.record_stream(main)           # allocated in the side stream's pool, consumed on the main stream
-                    ev = None
-                    if pk is not None:
                         ev = torch.cuda.Event()
                         ev.record(side)
-                    packs.append(pk); pack_events.append(ev)
+                        packs[s - 1], pack_events[s - 1] = pk, ev
+                prepack(1)
+                # masks of every level first, then SpaMat + SpaVar of all levels in ONE launch (finest level's rows first: the
+                # few rows of the coarse levels fill the machine behind them instead of being one-wave launches of their own)
                 pre = (left_feats["stage0"].contiguous(), right_feats["stage0"].contiguous())
+                lv = []
                 for s in range(1, self.num_stage):
                     if s >= self.skip_stage_id:
-                        branch.append(None); events.append(None)
                         continue
                     l = s - 1
                     Lf, Rf = left_feats[f"stage{s}"].contiguous(), right_feats[f"stage{s}"].contiguous()
@@ -654,13 +657,21 @@ class DecompMatching(nn.Module):
                         pre = (Lf, Rf)
                     else:
                         lm, rm = left_mask_list[l].contiguous(), right_mask_list[l].contiguous()
-                    sparse, var, _, _ = ops.spamat_spavar_forward(Lf, Rf, lm, rm, D)
+                    lv.append((Lf, Rf, lm, rm, D))
+                outs = ops.spamat_spavar_forward_levels(lv[::-1])[::-1] if lv else []
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for s in range(1, self.num_stage):
+                    if s >= self.skip_stage_id:
+                        branch.append(None); events.append(None)
+                        continue
+                    (_, _, lm, rm, _), (sparse, var, _, _) = lv[s - 1], outs[s - 1]
                     for t in (lm, rm, sparse, var):
                         t.record_stream(main)
                     branch.append((lm, rm, sparse, var))
-                    ev = torch.cuda.Event()
-                    ev.record(side)
                     events.append(ev)
+                for s in range(2, self.num_stage):
+                    prepack(s)
         pre_l = pre_r = None
         for s in range(self.num_stage):
             Lf = left_feats[f"stage{s}"].contiguous()

@@ -87,6 +87,29 @@ def spamat_spavar_forward(ref_feas, tar_feas, ref_mask, tar_mask, max_disp):
     return tuple(outs)
 
 
+def spamat_spavar_forward_levels(levels):
+    """Fused SpaMat + SpaVar of several pyramid levels in ONE launch.  levels: [(ref_feas, tar_feas, ref_mask, tar_mask,
+    max_disp), ...] (finest level first for the best schedule) -> [(disp, var, sum_sim, max_cost), ...] in the same order."""
+    import ctypes
+    n = len(levels)
+    if not 1 <= n <= 4:
+        raise ValueError("1..4 levels")
+    outs, dims = [], []
+    for (Lf, Rf, ml, mr, D) in levels:
+        dims.append(_feat_args(Lf, Rf, ml, mr) + (int(D),))
+        if Lf.device != levels[0][0].device:
+            raise ValueError("all levels must live on one device")
+        outs.append(tuple(torch.empty_like(ml) for _ in range(4)))
+    vp = ctypes.c_void_p * n
+    ia = ctypes.c_int * n
+    ptrs = [vp(*[lv[k].data_ptr() for lv in levels]) for k in range(4)] + [vp(*[o[k].data_ptr() for o in outs]) for k in range(4)]
+    ints = [ia(*[d[k] for d in dims]) for k in range(5)]
+    t0 = levels[0][0]
+    _call("decnet_spamat_spavar_fwd_levels", t0, n, *[ctypes.cast(p, ctypes.c_void_p) for p in ptrs],
+          *[ctypes.cast(i, ctypes.c_void_p) for i in ints])
+    return outs
+
+
 def spamat_backward(ref_feas, tar_feas, ref_mask, tar_mask, output, sum_sim, max_cost, grad_output,
                     max_disp, grad_ref=None, grad_tar=None):
     B, Cc, H, W = _feat_args(ref_feas, tar_feas, ref_mask, tar_mask)

@@ -84,6 +84,15 @@ int decnet_spamat_spavar_fwd(const float *ref_feas, const float *tar_feas,
                              float *sum_similarities, float *max_cost,
                              int B, int C, int H, int W, int max_disp, void *stream);
 
+/* The same fused pass over the rows of SEVERAL pyramid levels in ONE launch (nlev <= 4; arrays of nlev HOST entries, one
+ * per level, each with its own B, C, H, W, max_disp): the model runs the op at three levels whose inputs do not depend on each
+ * other, and the coarse levels alone are one or two waves of latency.  Give the finest level first. */
+int decnet_spamat_spavar_fwd_levels(int nlev, const float *const *ref_feas, const float *const *tar_feas,
+                                    const float *const *ref_mask, const float *const *tar_mask,
+                                    float *const *disp_out, float *const *var_out,
+                                    float *const *sum_similarities, float *const *max_cost,
+                                    const int *B, const int *C, const int *H, const int *W, const int *max_disp, void *stream);
+
 /* Replaces sparse_matching_cuda_backward (SM_cuda.cpp:17-27, SM_kernel.cu:143-195,300-355). */
 int decnet_spamat_bwd(const float *ref_feas, const float *tar_feas,
                       const float *ref_mask, const float *tar_mask,

@@ -164,3 +164,21 @@ def test_reference_cuda_pins_oracle_and_ours(name, B, C, H, W, D):
         scale = max(1.0, b.abs().max().item())
         assert torch.allclose(a, b.cpu(), atol=1e-4 * scale, rtol=1e-4)
         assert torch.allclose(c.cpu(), b.cpu(), atol=1e-4 * scale, rtol=1e-4)
+
+
+def test_multi_level_launch_equals_per_level_launches():
+    """decnet_spamat_spavar_fwd_levels: the rows of several levels in one launch -- same row code, so the same bits as one
+    launch per level (the model's three SceneFlow levels, a KITTI-style odd width, and a single level)."""
+    from decnet_b200 import ops
+    shapes = [(2, 8, 54, 972, 216), (2, 24, 18, 324, 72), (2, 72, 6, 108, 24), (1, 8, 9, 141, 24)]
+    levels = []
+    for i, (B, C, H, W, D) in enumerate(shapes):
+        L, R = make_feats(B, C, H, W, seed=30 + i, device="cuda")
+        ml, mr = make_masks(B, H, W, 0.15, 0.2, seed=40 + i, device="cuda")
+        levels.append((L, R, ml, mr, D))
+    for sel in (levels, levels[:3], levels[2:3], levels[::-1]):
+        got = ops.spamat_spavar_forward_levels(sel)
+        for lv, out in zip(sel, got):
+            want = ops.spamat_spavar_forward(*lv)
+            for a, b in zip(out, want):
+                assert torch.equal(a, b)
