@@ -130,11 +130,26 @@ struct Params {
     float *out_f32_full;               // [M][np] (mode 2)
     int round_tf32;                    // mode 2: round the stored activations to TF32 (nearest) for the next tf32 conv
     int num_tiles, stages;
+    // Wave-quantisation tail: the persistent CTAs walk num_items work items; items [0, tail_first) are whole tiles, the rest
+    // are the tail_tiles tiles of the last, partial round split in two along N (np/2 output channels each) when they then
+    // still fit one round -- 360 tiles on 148 SMs become 2 full rounds + 128 half tiles instead of 3 rounds.
+    int num_items, tail_first, tail_tiles;
     long long *dbg;                    // optional per-CTA timing (decnet_conv3d_debug_timing), else null
 };
 
+// work item -> (tile, first output channel, number of output channels)
+__device__ __forceinline__ void decode_item(const Params &p, int item, int &tile, int &n0, int &nlen) {
+    if (item < p.tail_first) { tile = item; n0 = 0; nlen = p.np; return; }
+    const int k = item - p.tail_first;
+    const int half = k >= p.tail_tiles ? 1 : 0;
+    tile = p.tail_first + k - half * p.tail_tiles;
+    nlen = p.np >> 1;
+    n0 = half * nlen;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
+conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmBh, const Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -152,7 +167,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int acc_stride = p.tmem_cols >> 1;              // two accumulator slots (double buffering)
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBh);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_mbar_init();
@@ -174,7 +189,11 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;                   // ring slot / phase, advanced without divisions
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                int tile, n0, nlen;
+                decode_item(p, item, tile, n0, nlen);
+                const CUtensorMap *tb = nlen == p.np ? &tmB : &tmBh;
+                const uint32_t tx = (uint32_t)(kABytes + nlen * kRowBytes);
                 int t = tile;
                 const int w0 = (t % p.tw) * p.bw; t /= p.tw;
                 const int h0 = (t % p.th) * p.bh; t /= p.th;
@@ -187,11 +206,11 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             for (int ck = 0; ck < p.nchunks; ++ck) {
                                 mbar_wait(&empty_bar[s], ph ^ 1u);
                                 unsigned char *sa = base + (size_t)s * stage_bytes;
-                                if (p.skip_tma && (ph || tile != (int)blockIdx.x)) { mbar_arrive(&full_bar[s]); }
+                                if (p.skip_tma && (ph || item != (int)blockIdx.x)) { mbar_arrive(&full_bar[s]); }
                                 else {
-                                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                                mbar_arrive_expect_tx(&full_bar[s], tx);
                                 tma_load_5d(sa, &tmA, ck * p.chunk_ch, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, b, &full_bar[s]);
-                                tma_load_3d(sa + kABytes, &tmB, ck * p.chunk_ch, 0, tap, &full_bar[s]);
+                                tma_load_3d(sa + kABytes, tb, ck * p.chunk_ch, n0, tap, &full_bar[s]);
                                 }
                                 if (++s == kStages) { s = 0; ph ^= 1u; }
                             }
@@ -200,7 +219,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         {
-            const uint32_t idesc = make_idesc(p.fmt, kTileM, p.np);
+            const uint32_t idesc_full = make_idesc(p.fmt, kTileM, p.np), idesc_half = make_idesc(p.fmt, kTileM, p.np >> 1);
             int it = 0, j = 0;
             int s = 0; uint32_t ph = 0;                   // ring slot / phase, advanced without divisions
             const uint32_t smem_base = smem_u32(base);
@@ -208,7 +227,8 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             bool ready = false;
             long long t_begin = clock64(), t_wait = 0;
             unsigned long long ns_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++j) {
+                const uint32_t idesc = item < p.tail_first ? idesc_full : idesc_half;
                 const int slot = j & 1;
                 mbar_wait(&tmem_empty_bar[slot], ((uint32_t)(j >> 1) & 1u) ^ 1u);   // epilogue drained this slot
                 tc_fence_after();
@@ -258,7 +278,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int r = q * 32 + lane;                      // accumulator row = voxel within the tile
         const int dw = r % p.bw, dh = (r / p.bw) % p.bh, dd = r / (p.bw * p.bh);
         int j = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++j) {
+            int tile, n0, nlen;
+            decode_item(p, item, tile, n0, nlen);
             int t = tile;
             const int w = (t % p.tw) * p.bw + dw; t /= p.tw;
             const int h = (t % p.th) * p.bh + dh; t /= p.th;
@@ -275,9 +297,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tmem_ld16(trow, v);
                 if (valid) { float x = v[0] + p.bias[0]; if (p.relu) x = fmaxf(x, 0.f); p.out_f32[m] = x; }
             } else if (p.mode == 2) {
-                for (int c0 = 0; c0 < p.np; c0 += 16) {
+                for (int cc = 0; cc < nlen; cc += 16) {
+                    const int c0 = n0 + cc;
                     float v[16];
-                    tmem_ld16(trow + (uint32_t)c0, v);
+                    tmem_ld16(trow + (uint32_t)cc, v);
                     if (valid) {
                         const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
                         float4 *op = reinterpret_cast<float4 *>(p.out_f32_full + m * p.np + c0);
@@ -292,9 +315,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                 }
             } else {
-                for (int c0 = 0; c0 < p.np; c0 += 16) {
+                for (int cc = 0; cc < nlen; cc += 16) {
+                    const int c0 = n0 + cc;
                     float v[16];
-                    tmem_ld16(trow + (uint32_t)c0, v);    // warp-collective: every lane takes part
+                    tmem_ld16(trow + (uint32_t)cc, v);    // warp-collective: every lane takes part
                     if (valid) {
                         __align__(16) __nv_bfloat16 o[16];
                         __align__(16) __nv_bfloat16 rs[16];
@@ -686,7 +710,15 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
     DECNET_REQUIRE(p.stages >= 2, "stage too large");
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     const CUtensorMapDataType dt = esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    CUtensorMap tmA, tmB;
+    // split the last, partial round of tiles in two along N when that round then still fits the machine (single-CTA kernel)
+    p.num_items = p.num_tiles; p.tail_first = p.num_tiles; p.tail_tiles = 0;
+    if (!two_cta && g_conv3d_variant % 10 != 1 && np % 32 == 0 && out_mode != 1) {
+        const int tail = p.num_tiles % sms;
+        if (tail > 0 && 2 * tail <= sms) {
+            p.tail_tiles = tail; p.tail_first = p.num_tiles - tail; p.num_items = p.num_tiles + tail;
+        }
+    }
+    CUtensorMap tmA, tmB, tmBh;
     {
         const uint64_t dims[5] = {(uint64_t)cp, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)B};
         const uint64_t strides[4] = {(uint64_t)cp * esize, (uint64_t)W * cp * esize, (uint64_t)H * W * cp * esize,
@@ -702,6 +734,10 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
         const uint32_t box[3] = {(uint32_t)chunk_ch, (uint32_t)(two_cta ? np / 2 : np), 1u};
         int rc = encode_tensor_map(&tmB, dt, 3, w_packed, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+        const uint32_t boxh[3] = {(uint32_t)chunk_ch, (uint32_t)(p.tail_tiles ? np / 2 : np), 1u};
+        rc = encode_tensor_map(&tmBh, dt, 3, w_packed, dims, strides, boxh, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
     if (two_cta) {
@@ -732,8 +768,8 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
             if (dev >= 0 && dev < 64) set_for[dev] = smem;
         }
     }
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);       // persistent: one CTA per SM
-    conv3d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+    const unsigned grid = (unsigned)(p.num_items < sms ? p.num_items : sms);       // persistent: one CTA per SM
+    conv3d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmBh, p);
     return after_launch("conv3d_tcgen05_kernel");
 }
 
