@@ -85,6 +85,36 @@ __device__ __forceinline__ void umma_stage_elect(uint32_t tmem_d, uint64_t desc_
                      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(bar_addr) : "memory");
     }
 }
+// Two consecutive stages (4 K-steps, then K2 K-steps) behind ONE election: eight MMAs and both commits in one block, so the
+// issuing warp pays its wait / fence / descriptor set-up once per 128 channels instead of once per 64.
+#define DECNET_MMA_NEXT2(OFF)                                                      \
+        "add.u64 a, %6, " #OFF ";\n\t"                                              \
+        "add.u64 b, %7, " #OFF ";\n\t"                                              \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+template <int K2>
+__device__ __forceinline__ void umma_stage_pair_elect(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc,
+                                                      uint32_t accumulate_first, uint32_t bar0, uint64_t da1, uint64_t db1,
+                                                      uint32_t bar1) {
+    static_assert(K2 >= 1 && K2 <= 4, "1..4 K-steps in the second stage");
+#define DECNET_PAIR_MID                                                            \
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t" \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %6, %7, %3, t;\n\t"
+#define DECNET_PAIR_TAIL                                                           \
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}"
+#define DECNET_PAIR_ARGS ::"r"(tmem_d), "l"(da0), "l"(db0), "r"(idesc), "r"(accumulate_first), "r"(bar0), "l"(da1), "l"(db1), "r"(bar1) : "memory"
+    if constexpr (K2 == 4)
+        asm volatile(DECNET_STAGE_HEAD DECNET_MMA_NEXT(2) DECNET_MMA_NEXT(4) DECNET_MMA_NEXT(6) DECNET_PAIR_MID
+                     DECNET_MMA_NEXT2(2) DECNET_MMA_NEXT2(4) DECNET_MMA_NEXT2(6) DECNET_PAIR_TAIL DECNET_PAIR_ARGS);
+    else if constexpr (K2 == 3)
+        asm volatile(DECNET_STAGE_HEAD DECNET_MMA_NEXT(2) DECNET_MMA_NEXT(4) DECNET_MMA_NEXT(6) DECNET_PAIR_MID
+                     DECNET_MMA_NEXT2(2) DECNET_MMA_NEXT2(4) DECNET_PAIR_TAIL DECNET_PAIR_ARGS);
+    else if constexpr (K2 == 2)
+        asm volatile(DECNET_STAGE_HEAD DECNET_MMA_NEXT(2) DECNET_MMA_NEXT(4) DECNET_MMA_NEXT(6) DECNET_PAIR_MID
+                     DECNET_MMA_NEXT2(2) DECNET_PAIR_TAIL DECNET_PAIR_ARGS);
+    else
+        asm volatile(DECNET_STAGE_HEAD DECNET_MMA_NEXT(2) DECNET_MMA_NEXT(4) DECNET_MMA_NEXT(6) DECNET_PAIR_MID
+                     DECNET_PAIR_TAIL DECNET_PAIR_ARGS);
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -235,6 +265,37 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const uint32_t acc = tmem_base + (uint32_t)(slot * acc_stride);
                 uint32_t first = 1u;
                 const int last_ck = p.nchunks - 1;
+                if ((p.nchunks & 1) == 0 && kStages >= 4 && !p.dbg) {
+                    // even number of chunks: two stages per issue block
+                    const int npairs = 9 * p.taps_d * (p.nchunks >> 1);
+                    const int pairs_per_tap = p.nchunks >> 1;
+                    int pc = 0;                                        // pair index within the tap
+                    for (int pr = 0; pr < npairs; ++pr, it += 2) {
+                        int s1 = s + 1; uint32_t ph1 = ph;
+                        if (s1 == kStages) { s1 = 0; ph1 ^= 1u; }
+                        if (!ready) mbar_wait(&full_bar[s], ph);
+                        mbar_wait(&full_bar[s1], ph1);
+                        tc_fence_after();
+                        const uint32_t sa0 = smem_base + (uint32_t)(s * stage_bytes), sa1 = smem_base + (uint32_t)(s1 * stage_bytes);
+                        const uint64_t da0 = make_smem_desc_sw128(sa0), db0 = make_smem_desc_sw128(sa0 + kABytes);
+                        const uint64_t da1 = make_smem_desc_sw128(sa1), db1 = make_smem_desc_sw128(sa1 + kABytes);
+                        const uint32_t e0 = empty_base + (uint32_t)(s * 8), e1 = empty_base + (uint32_t)(s1 * 8);
+                        int sn = s1 + 1; uint32_t phn = ph1;
+                        if (sn == kStages) { sn = 0; phn ^= 1u; }
+                        ready = mbar_test_wait(&full_bar[sn], phn);   // probe the stage after the pair now
+                        const bool last_pair = ++pc == pairs_per_tap;
+                        if (last_pair) pc = 0;
+                        if (!last_pair) umma_stage_pair_elect<4>(acc, da0, db0, idesc, first ^ 1u, e0, da1, db1, e1);
+                        else switch (p.last_ksteps) {
+                            case 4: umma_stage_pair_elect<4>(acc, da0, db0, idesc, first ^ 1u, e0, da1, db1, e1); break;
+                            case 3: umma_stage_pair_elect<3>(acc, da0, db0, idesc, first ^ 1u, e0, da1, db1, e1); break;
+                            case 2: umma_stage_pair_elect<2>(acc, da0, db0, idesc, first ^ 1u, e0, da1, db1, e1); break;
+                            default: umma_stage_pair_elect<1>(acc, da0, db0, idesc, first ^ 1u, e0, da1, db1, e1); break;
+                        }
+                        first = 0u;
+                        s = sn; ph = phn;
+                    }
+                } else
                 for (int tap = 0; tap < 9 * p.taps_d; ++tap) {
                     for (int ck = 0; ck < p.nchunks; ++ck, ++it) {
                         // `ready` was probed one stage ahead (the probe's latency hides behind the MMA issue)
