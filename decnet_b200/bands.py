@@ -17,7 +17,12 @@ rows.  What crosses a band boundary:
   * the bilinear warps use GLOBAL row coordinates (the reference's y' = h*H/(H-1) - 1/2).
 
 Transports: `LocalTransport` runs all ranks in one process (single-GPU test of the decomposition),
-`DistTransport` is one process per GPU over torch.distributed (NCCL over NVLink).
+`DistTransport` is one process per GPU over torch.distributed send/recv (NCCL; eager only), and
+`PeerTransport` is one process per GPU over NVLink PEER MEMORY: the activation buffers of the aggregation and
+the per-level disparity maps live in symmetric allocations (torch symmetric memory = CUDA IPC-mapped peer
+buffers), every rank STORES its edge rows straight into its neighbours' halo rows and its band into every
+rank's full map, and device-side signals order the steps -- no host synchronisation, no collective library call
+on the path, so the whole banded step is captured in ONE CUDA graph per rank and replayed.
 """
 from __future__ import annotations
 
@@ -121,6 +126,84 @@ class DistTransport:
         return {self.rank: full}
 
 
+class PeerTransport:
+    """One process per GPU; halo rows and band gathers are plain device stores into peer memory over NVLink.
+
+    * `conv_buffer(name, shape)`: a symmetric [B, D, rows_max+2, W, C] bf16 allocation (zero-filled once); returns this
+      rank's view [B, D, rows+2, W, C].  The aggregation layers write their owned rows into it (decnet_conv3d_bf16_band
+      leaves the halo rows alone), `push_halo(name)` then stores the first / last owned row into the down / up halo row of
+      the two neighbours' buffers and exchanges one signal with each neighbour: a layer may start once both neighbours'
+      rows of the previous layer have landed.  Safe without a second signal: a neighbour can only be one layer ahead after
+      it received my rows of the layer before, i.e. after I finished reading the buffer it is about to write into.
+    * `all_gather_rows(bands, key)`: every rank stores its band into every rank's symmetric full map, then a device-side
+      barrier.
+    Everything is stream-ordered kernels / copies: capturable in a CUDA graph (bench.py does)."""
+
+    def __init__(self, h_coarse, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.dist, self.symm = dist, symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.ranks_here = [self.rank]
+        self.h_coarse = h_coarse
+        self.bands = shard.coarse_bands(h_coarse, self.world)
+        self._conv, self._full, self._chan = {}, {}, 0
+
+    def _alloc(self, shape, dtype, device):
+        t = self.symm.empty(*shape, dtype=dtype, device=device)
+        t.zero_()
+        hdl = self.symm.rendezvous(t, self.group)
+        torch.cuda.synchronize(device)
+        hdl.barrier(0)
+        return t, hdl
+
+    # ---- 3-D aggregation: per-layer halo rows ------------------------------------------------------------------
+    def conv_buffer(self, name, B, D, W, C, device):
+        if name not in self._conv:
+            rows_max = max(b - a for a, b in self.bands)
+            t, hdl = self._alloc((B, D, rows_max + 2, W, C), torch.bfloat16, device)
+            view = lambda r: hdl.get_buffer(r, (B, D, self.bands[r][1] - self.bands[r][0] + 2, W, C), torch.bfloat16)
+            mine = view(self.rank)
+            up = view(self.rank - 1) if self.rank > 0 else None
+            dn = view(self.rank + 1) if self.rank < self.world - 1 else None
+            self._chan += 1
+            self._conv[name] = (t, hdl, mine, up, dn, self._chan)
+        return self._conv[name][2]
+
+    def push_halo(self, name):
+        _, hdl, mine, up, dn, ch = self._conv[name]
+        if up is not None:
+            up[:, :, -1].copy_(mine[:, :, 1])            # my first owned row -> the up neighbour's bottom halo row
+            hdl.put_signal(self.rank - 1, ch)
+        if dn is not None:
+            dn[:, :, 0].copy_(mine[:, :, -2])            # my last owned row -> the down neighbour's top halo row
+            hdl.put_signal(self.rank + 1, ch)
+        if up is not None:
+            hdl.wait_signal(self.rank - 1, ch)
+        if dn is not None:
+            hdl.wait_signal(self.rank + 1, ch)
+
+    # ---- per-level disparity maps ---------------------------------------------------------------------------------
+    def all_gather_rows(self, bands, key=None):
+        mine = bands[self.rank]
+        B, rows, W = mine.shape
+        f = rows // (self.bands[self.rank][1] - self.bands[self.rank][0])
+        H = self.h_coarse * f
+        k = (key, B, H, W)
+        if k not in self._full:
+            t, hdl = self._alloc((B, H, W), torch.float32, mine.device)
+            self._chan += 1
+            self._full[k] = (t, hdl, [hdl.get_buffer(r, (B, H, W), torch.float32) for r in range(self.world)], self._chan)
+        t, hdl, views, ch = self._full[k]
+        r0 = self.bands[self.rank][0] * f
+        for r in range(self.world):
+            views[(self.rank + r) % self.world][:, r0:r0 + rows].copy_(mine)     # staggered: not everyone hits rank 0 first
+        hdl.barrier(ch)
+        return {self.rank: t}
+
+
 def _dense_stage_bands(model, left0, right0, D, tr):
     """a2-a4 on row bands with per-layer halo exchange.  Returns {rank: pred band [B, rows, W]}."""
     reg = model.cost_regularizer
@@ -137,6 +220,26 @@ def _dense_stage_bands(model, left0, right0, D, tr):
         ops._call("decnet_costvol_bf16_ndhwc_rows", left0, left0.data_ptr(), right0.data_ptr(), v.data_ptr(),
                   B, C, pk["cp"], H0, W, D, r0 - 1, r1 - r0 + 2)
         vol[r] = v                          # halo rows already exact (computed from the replicated features)
+
+    if isinstance(tr, PeerTransport):
+        # peer-memory transport: three symmetric ping-pong buffers; a layer stores its owned rows only, the neighbours store
+        # the halo rows (image-edge halo rows stay at their initial zero)
+        r = tr.rank
+        buf = {n: tr.conv_buffer(n, B, D, W, pk["cp"], left0.device) for n in ("t1", "t2", "o0")}
+
+        def player(i, xin, name, residual=None):
+            c3.conv3d_layer(xin, u[i][0], u[i][1], u[i][2], u[i][3], residual=residual, out=buf[name], band=True)
+            tr.push_halo(name)
+            return buf[name]
+        x = player(0, vol[r], "t1")
+        o0 = player(1, x, "o0")
+        x = player(2, o0, "t1")
+        x = player(3, x, "t2")
+        x = player(4, x, "t1", residual=o0)
+        x = player(5, x, "t2")
+        x = player(6, x, "t1")
+        cost = c3.conv3d_layer(x, u[7][0], u[7][1], u[7][2], False, out_f32=True)
+        return {r: ops.softargmin(cost[:, :, 1:-1].contiguous())}
 
     def layer(i, xin, residual=None):
         out = {r: c3.conv3d_layer(xin[r], u[i][0], u[i][1], u[i][2], u[i][3],
@@ -190,7 +293,8 @@ def forward_bands(model, left_feats, right_feats, transport, left_mask_list=None
     tr.h_coarse = H0
     pred = _dense_stage_bands(model, left_feats["stage0"].contiguous(), right_feats["stage0"].contiguous(),
                               model.max_disp // 27, tr)
-    full = tr.all_gather_rows(pred)
+    gather = (lambda bands, key: tr.all_gather_rows(bands, key)) if isinstance(tr, PeerTransport) else (lambda bands, key: tr.all_gather_rows(bands))
+    full = gather(pred, 0)
     for s in range(1, model.num_stage):
         Lf, Rf = left_feats[f"stage{s}"], right_feats[f"stage{s}"]
         if s >= model.skip_stage_id:
@@ -202,7 +306,7 @@ def forward_bands(model, left_feats, right_feats, transport, left_mask_list=None
                 up = F.interpolate(full[r][:, b.e0:b.e1].unsqueeze(1) * 3, [3 * (b.e1 - b.e0), Lf.shape[3]],
                                    mode="bicubic").squeeze(1)
                 out[r] = up[:, 3 * (b.r0 - b.e0): 3 * (b.r1 - b.e0)].contiguous()
-            full = tr.all_gather_rows(out)
+            full = gather(out, s)
             continue
         D = model.max_disp // 3 ** (model.num_stage - s - 1)
         out = {}
@@ -211,5 +315,5 @@ def forward_bands(model, left_feats, right_feats, transport, left_mask_list=None
             out[r] = _level_stage_band(model, s, s - 1, band, Lf, Rf, left_feats[f"stage{s - 1}"],
                                        right_feats[f"stage{s - 1}"], full[r],
                                        (left_mask_list, right_mask_list), D)
-        full = tr.all_gather_rows(out)
+        full = gather(out, s)
     return full

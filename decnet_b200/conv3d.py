@@ -35,12 +35,22 @@ def packed_stack(reg):
     return reg._cached("packed", build)
 
 
-def conv3d_layer(x, w, bias, np_, relu, residual=None, out=None, out_f32=False):
-    """x bf16 [B,D,H,W,CP] -> bf16 [B,D,H,W,NP] (or fp32 [B,D,H,W] of channel 0 when out_f32)."""
+def conv3d_layer(x, w, bias, np_, relu, residual=None, out=None, out_f32=False, band=False):
+    """x bf16 [B,D,H,W,CP] -> bf16 [B,D,H,W,NP] (or fp32 [B,D,H,W] of channel 0 when out_f32).
+    band: row-band mode -- rows 0 and H-1 of `out` are halo slots filled by the neighbouring ranks, not stored here."""
     B, D, H, W, cp = x.shape
     if out is None:
         out = (torch.empty((B, D, H, W), dtype=torch.float32, device=x.device) if out_f32
                else torch.empty((B, D, H, W, np_), dtype=torch.bfloat16, device=x.device))
+    if band:
+        assert not out_f32
+        with torch.cuda.device_of(x):
+            st = _lib.lib().decnet_conv3d_bf16_band(x.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                                    residual.data_ptr() if residual is not None else None, out.data_ptr(),
+                                                    B, D, H, W, cp, np_, 1 if relu else 0,
+                                                    torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(st, "decnet_conv3d_bf16_band")
+        return out
     with torch.cuda.device_of(x):
         st = _lib.lib().decnet_conv3d_bf16(x.data_ptr(), w.data_ptr(), bias.data_ptr(),
                                            residual.data_ptr() if residual is not None else None,

@@ -164,6 +164,8 @@ struct Params {
     // are the tail_tiles tiles of the last, partial round split in two along N (np/2 output channels each) when they then
     // still fit one round -- 360 tiles on 148 SMs become 2 full rounds + 128 half tiles instead of 3 rounds.
     int num_items, tail_first, tail_tiles;
+    int skip_h_edges;                  // row-band mode: rows h = 0 and h = H-1 are halo slots a NEIGHBOUR rank fills over NVLink
+                                       // (or that stay zero at the image edge); this launch must not store into them
     long long *dbg;                    // optional per-CTA timing (decnet_conv3d_debug_timing), else null
 };
 
@@ -347,7 +349,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int h = (t % p.th) * p.bh + dh; t /= p.th;
             const int d = (t % p.td) * p.bd + dd; t /= p.td;
             const int b = t;
-            const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
+            const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && !(p.skip_h_edges && (h == 0 || h == p.H - 1));
             const size_t m = (((size_t)b * p.D + d) * p.H + h) * p.W + w;
             const int slot = j & 1;
             mbar_wait(&tmem_full_bar[slot], (uint32_t)(j >> 1) & 1u);
@@ -728,7 +730,7 @@ void decnet_conv3d_debug_timing(void *dbg_buffer) { g_conv3d_dbg = static_cast<l
 //                  esize 4 -> fp32 operands read as tf32 (kind::tf32, K-step 8, 32 channels per row).
 static int launch_conv(const void *x, const void *w_packed, const float *bias, const void *residual, void *out,
                        int out_mode, int esize, int taps_d, int B, int D, int H, int W, int cp, int np, int relu,
-                       void *stream, int round_out = 0)
+                       void *stream, int round_out = 0, int skip_h_edges = 0)
 {
     DECNET_REQUIRE(x && w_packed && bias && out, "null pointer");
     DECNET_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "non-positive size");
@@ -753,7 +755,7 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
     p.last_ksteps = (cp - (p.nchunks - 1) * chunk_ch) / kstep;
     pick_tile(W, H, D, p.bw, p.bh, p.bd);
     p.tw = (W + p.bw - 1) / p.bw; p.th = (H + p.bh - 1) / p.bh; p.td = (D + p.bd - 1) / p.bd;
-    p.relu = relu; p.mode = out_mode; p.round_tf32 = round_out;
+    p.relu = relu; p.mode = out_mode; p.round_tf32 = round_out; p.skip_h_edges = skip_h_edges;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;   // 2 slots
 
     const long long tiles = (long long)B * p.tw * p.th * p.td;
@@ -764,7 +766,7 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
     const int sms = sm_count_cached();
     // The CTA-pair kernel is correct (same tests) but measured 2x slower than the single-CTA one in
     // round 1 (MMAs slow down 3x while TMA fills run): opt-in only.
-    const bool two_cta = (g_conv3d_variant % 10) == 2 && tiles >= 2 && sms >= 2 && out_mode != 2;
+    const bool two_cta = (g_conv3d_variant % 10) == 2 && tiles >= 2 && sms >= 2 && out_mode != 2 && !skip_h_edges;
     const size_t stage_bytes = kABytes + (size_t)(two_cta ? np / 2 : np) * kRowBytes;
     p.stages = (int)((226 * 1024 - 1024) / stage_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -839,6 +841,12 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
 {
     DECNET_REQUIRE(out_mode == 0 || out_mode == 1, "out_mode must be 0 (bf16 [M][np]) or 1 (fp32 [M], channel 0)");
     return launch_conv(x_ndhwc, w_packed, bias, residual, out, out_mode, 2, 3, B, D, H, W, cp, np, relu, stream);
+}
+
+int decnet_conv3d_bf16_band(const void *x_ndhwc, const void *w_packed, const float *bias, const void *residual,
+                            void *out, int B, int D, int H, int W, int cp, int np, int relu, void *stream)
+{
+    return launch_conv(x_ndhwc, w_packed, bias, residual, out, 0, 2, 3, B, D, H, W, cp, np, relu, stream, 0, 1);
 }
 
 int decnet_conv2d_tf32_nhwc(const float *x_nhwc, const float *w_packed, const float *bias, float *out,

@@ -175,6 +175,13 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
                        const void *residual, void *out, int out_mode,
                        int B, int D, int H, int W, int cp, int np, int relu, void *stream);
 
+/* Row-band form (one huge pair split across GPUs): the tensors are a band [B,D,rows+2,W,.] whose
+ * rows 0 and rows+1 are halo slots.  The layer computes every owned row from the band (halo rows are inputs) and does NOT
+ * store into the halo rows of `out`: they are filled by the neighbouring ranks over NVLink peer memory (decnet_b200/bands.py)
+ * or stay zero at the image edge.  out_mode 0 only. */
+int decnet_conv3d_bf16_band(const void *x_ndhwc, const void *w_packed, const float *bias, const void *residual,
+                            void *out, int B, int D, int H, int W, int cp, int np, int relu, void *stream);
+
 /* 3x3 Conv2d (pad 1, stride 1) + bias [+ ReLU] as a TF32 implicit GEMM on the same tcgen05 kernel
  * (kind::tf32, fp32 operands in shared memory, fp32 accumulation): the 81-channel convs of
  * DynamicUpsampling.weight_learning (modules/submodule.py:571-575), which are GEMM-sized.
