@@ -24,7 +24,7 @@ for r in rd:
     agg[name][1] += us
     total += us
     n += 1
-ours = sum(v[1] for k, v in agg.items() if any(t in k for t in ("conv2d::", "conv2dtc::", "conv2dnhwc::", "conv2drows::", "conv3d::", "glue::", "sparse::", "detail::", "codec::")))
+ours = sum(v[1] for k, v in agg.items() if any(t in k for t in ("conv2d::", "conv2dtc::", "conv2dnhwc::", "conv2drows::", "conv3d::", "glue::", "sparse::", "detail::", "codec::", "featext::")))
 print(f"# total {total:.1f} us over {n} launches; hand-written decnet kernels: {100 * ours / total:.1f} % of the device time")
 print("share%  launches  total_us  kernel")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
