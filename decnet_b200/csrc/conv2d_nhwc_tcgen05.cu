@@ -58,6 +58,7 @@ struct Params {
     int ldc;                                       // output row stride in floats (>= np: writes a channel slice of a wider tensor)
     int dst_h, dst_w;                              // > 0 (GEMM mode, border = 0): row p = (b, y, x) of a flat [B, dst_h, dst_w]
                                                    // grid is stored at the interior pixel (b, y+1, x+1) of a zero-bordered one
+    int na_slots;                                  // pair kernel: slots of the A ring (the B ring has two)
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -408,11 +409,253 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
 }
 
+
+// =============================================================================================================================
+// Pair kernel (3xTF32 mode, NP <= 96): TWO 128-pixel tiles per CTA share every weight stage.
+//
+// OPT-IN EXPERIMENT (decnet_conv2d_nhwc_set_variant(2)), exact but SLOWER than the kernel above: 81 -> 81 at 180x324, B = 8:
+// 497 us against 427 us.  It was built to test the hypothesis that the kernel above is bound by the L2 -> SM traffic of its weight
+// tiles (72 KB of hi + lo weights per 17 KB activation tile, re-fetched for every 128-pixel tile: 3 GB per launch at 6.5 TB/s).
+// Here the weights of a (row tap, channel chunk) stage are loaded ONCE for two consecutive tiles -- 106 KB instead of 178 KB per
+// 72 MMAs -- and the time per tile-stage does not move (4180 cycles either way): the bound is SHARED-MEMORY bandwidth, not L2.
+// Per stage the tensor core fetches 36 x 7 KB of operands, TMA writes 89 KB and the converters move 51 KB: 392 KB in 4180 cycles
+// = 94 B/clk of the 128 B/clk crossbar (TF32 mode: 83 B/clk; this kernel: 85 B/clk).  Kept as the record of that measurement.
+// Structure: a ring of two B slots (hi + lo taps) and a ring of A slots (hi + lo tile each).  TMEM holds four accumulators: per tile the current hi*hi
+// chain (drained into registers every kGroup stages by that tile's four epilogue warps while the OTHER tile's MMAs run -- so one
+// slot per tile is enough) and the small-term accumulator of the whole tile.
+// Warps: 0 TMA producer, 1 MMA issuer, 2-5 epilogue of tile 0, 6-9 epilogue of tile 1, 10-13 converters (448 threads).
+// =============================================================================================================================
+constexpr int kPairThreads = 448;
+constexpr int kPairChunks = 6;                     // NP <= 96: 96 accumulator registers per epilogue thread
+constexpr int kMaxASlots = 4;
+
+__global__ void __launch_bounds__(kPairThreads, 1)
+conv2d_nhwc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[kMaxASlots], a_ready[kMaxASlots], a_empty[kMaxASlots];
+    __shared__ __align__(8) uint64_t b_full[2], b_empty[2];
+    __shared__ __align__(8) uint64_t big_full[2], big_empty[2], small_full[2], small_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int T = p.taps;
+    const int a_rows = T == 3 ? kARows : kTileM;
+    const int b_tap_bytes = p.np * 128;
+    const int b_slot_bytes = 2 * T * b_tap_bytes;             // hi taps, then lo taps
+    const int a_slot_bytes = 2 * kABytes;                     // hi tile, lo tile
+    unsigned char *a_base = base + 2 * b_slot_bytes;
+    const int NA = p.na_slots;
+    const int acc_stride = p.tmem_cols >> 2;                  // big[0], big[1], small[0], small[1]
+    const int pitch = p.w + 2;
+    const int nst = T * p.nchunks;
+    const int num_pairs = (p.num_tiles + 1) >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_ready[s], kConvWarps); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
+            mbar_init(&big_full[s], 1); mbar_init(&big_empty[s], 4);
+            mbar_init(&small_full[s], 1); mbar_init(&small_empty[s], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x)
+                for (int kh = 0; kh < T; ++kh)
+                    for (int ck = 0; ck < p.nchunks; ++ck) {
+                        mbar_wait(&b_empty[sb], phb ^ 1u);
+                        unsigned char *bs = base + (size_t)sb * b_slot_bytes;
+                        mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_slot_bytes);
+                        tma_load_3d(bs, &tmB, ck * 32, 0, kh * T, &b_full[sb]);
+                        tma_load_3d(bs + T * b_tap_bytes, &tmB, ck * 32, 0, T * T + kh * T, &b_full[sb]);
+                        if (++sb == 2) { sb = 0; phb ^= 1u; }
+                        for (int m = 0; m < 2; ++m) {
+                            const int p0 = (2 * pair + m) * kTileM;      // beyond P for the odd tail: TMA zero-fills
+                            mbar_wait(&a_empty[sa], pha ^ 1u);
+                            mbar_arrive_expect_tx(&a_full[sa], (uint32_t)(a_rows * 128));
+                            tma_load_2d(a_base + (size_t)sa * a_slot_bytes, &tmA, ck * 32,
+                                        T == 3 ? p0 + (kh - 1) * pitch - 1 : p0, &a_full[sa]);
+                            if (++sa == NA) { sa = 0; pha ^= 1u; }
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.np >> 3) << 17) | (8u << 24);
+        const uint32_t b_base_u = smem_u32(base), a_base_u = smem_u32(a_base);
+        const uint32_t db_tap_step = (uint32_t)(b_tap_bytes >> 4);
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+        uint32_t chain[2] = {0u, 0u};
+        uint32_t j = 0;
+        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++j) {
+            mbar_wait(&small_empty[0], (j & 1u) ^ 1u);
+            mbar_wait(&small_empty[1], (j & 1u) ^ 1u);
+            uint32_t first_s[2] = {0u, 0u}, first_b[2] = {0u, 0u};
+            int st = 0;
+            for (int kh = 0; kh < T; ++kh)
+                for (int ck = 0; ck < p.nchunks; ++ck, ++st) {
+                    const int gpos = st % kGroup;
+                    const bool chain_end = gpos == kGroup - 1 || st == nst - 1;
+                    mbar_wait(&b_full[sb], phb);
+                    const uint32_t sbu = b_base_u + (uint32_t)(sb * b_slot_bytes);
+                    const uint64_t db = make_desc_sw128(sbu), db_lo = make_desc_sw128(sbu + (uint32_t)(T * b_tap_bytes));
+                    const int ks = ck == p.nchunks - 1 ? p.last_ksteps : 4;
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        if (gpos == 0) {
+                            mbar_wait(&big_empty[m], (chain[m] & 1u) ^ 1u);     // this tile's previous chain was drained
+                            first_b[m] = 0u;
+                        }
+                        mbar_wait(&a_ready[sa], pha);
+                        tc_fence_after();
+                        const uint32_t sau = a_base_u + (uint32_t)(sa * a_slot_bytes);
+                        const uint64_t da = make_desc_sw128(sau), da_lo = make_desc_sw128(sau + (uint32_t)kABytes);
+                        const uint32_t acc_b = tmem_base + (uint32_t)(m * acc_stride);
+                        const uint32_t acc_s = tmem_base + (uint32_t)((2 + m) * acc_stride);
+                        umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s[m], T);     // lo(x) * hi(w)
+                        umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u, T);            // hi(x) * lo(w)
+                        umma_taps3(ks, acc_b, da, db, db_tap_step, idesc, first_b[m], T);       // hi(x) * hi(w)
+                        first_s[m] = 1u; first_b[m] = 1u;
+                        umma_commit_elect(smem_u32(&a_empty[sa]));
+                        if (chain_end) { umma_commit_elect(smem_u32(&big_full[m])); ++chain[m]; }
+                        if (++sa == NA) { sa = 0; pha ^= 1u; }
+                    }
+                    umma_commit_elect(smem_u32(&b_empty[sb]));
+                    if (++sb == 2) { sb = 0; phb ^= 1u; }
+                }
+            umma_commit_elect(smem_u32(&small_full[0]));
+            umma_commit_elect(smem_u32(&small_full[1]));
+        }
+    } else if (warp >= 10) {
+        // ===================== converters (warps 10..13): hi in place, lo beside it =====================
+        const int ctid = threadIdx.x - 10 * 32;
+        const int n16 = a_rows * 128 / 16;
+        int sa = 0; uint32_t pha = 0;
+        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x)
+            for (int it = 0; it < 2 * nst; ++it) {
+                mbar_wait(&a_full[sa], pha);
+                uint4 *sh = reinterpret_cast<uint4 *>(a_base + (size_t)sa * a_slot_bytes);
+                uint4 *sl = reinterpret_cast<uint4 *>(a_base + (size_t)sa * a_slot_bytes + kABytes);
+#pragma unroll 4
+                for (int i = ctid; i < n16; i += kConvWarps * 32) {
+                    const uint4 v = sh[i];
+                    uint4 h, l;
+                    h.x = (v.x + 0x1000u) & 0xFFFFE000u; h.y = (v.y + 0x1000u) & 0xFFFFE000u;
+                    h.z = (v.z + 0x1000u) & 0xFFFFE000u; h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+                    l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + 0x1000u) & 0xFFFFE000u;
+                    l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + 0x1000u) & 0xFFFFE000u;
+                    l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + 0x1000u) & 0xFFFFE000u;
+                    l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + 0x1000u) & 0xFFFFE000u;
+                    sh[i] = h;
+                    sl[i] = l;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[sa]);
+                if (++sa == NA) { sa = 0; pha ^= 1u; }
+            }
+    } else {
+        // ===================== epilogue: warps 2-5 own tile 0 of the pair, warps 6-9 tile 1 =====================
+        const int m = warp >= 6 ? 1 : 0;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const long long per_img = (long long)(p.h + 2) * pitch;
+        const int ngroups = (nst + kGroup - 1) / kGroup;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        float acc[kPairChunks][16];
+        uint32_t chain = 0, j = 0;
+        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++j) {
+            const long long pix = (long long)(2 * pair + m) * kTileM + r;
+            const bool inside = pix < p.P;
+            long long dst = pix; bool interior = inside;
+            if (p.border) {
+                const long long rem = pix % per_img;
+                const int yy = (int)(rem / pitch), xx = (int)(rem - (long long)yy * pitch);
+                interior = inside && yy >= 1 && yy <= p.h && xx >= 1 && xx <= p.w;
+            } else if (p.dst_h > 0 && inside) {
+                const long long hw = (long long)p.dst_h * p.dst_w, b = pix / hw, rem = pix - b * hw;
+                const int yy = (int)(rem / p.dst_w), xx = (int)(rem - (long long)yy * p.dst_w);
+                dst = (b * (p.dst_h + 2) + yy + 1) * (p.dst_w + 2) + xx + 1;
+            }
+#pragma unroll
+            for (int c = 0; c < kPairChunks; ++c)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[c][i] = 0.f;
+            auto drain = [&](uint32_t trow) {
+#pragma unroll
+                for (int c = 0; c < kPairChunks; ++c)
+                    if (c * 16 < p.np) {
+                        float v[16];
+                        tmem_ld16(trow + (uint32_t)(c * 16), v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[c][i] += v[i];
+                    }
+                tc_fence_before();
+                __syncwarp();
+            };
+            for (int g = 0; g < ngroups; ++g, ++chain) {
+                mbar_wait(&big_full[m], chain & 1u);
+                tc_fence_after();
+                drain(lane_base + (uint32_t)(m * acc_stride));
+                if (lane == 0) mbar_arrive(&big_empty[m]);
+            }
+            mbar_wait(&small_full[m], j & 1u);
+            tc_fence_after();
+            drain(lane_base + (uint32_t)((2 + m) * acc_stride));
+            if (lane == 0) mbar_arrive(&small_empty[m]);
+            if (inside) {
+#pragma unroll
+                for (int c = 0; c < kPairChunks; ++c)
+                    if (c * 16 < p.np) {
+                        const int c0 = c * 16;
+                        const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0);
+                        float4 *op = reinterpret_cast<float4 *>(p.out + dst * p.ldc + c0);
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (interior) {
+                                const float4 bv = __ldg(bp + i4);
+                                o = make_float4(acc[c][4 * i4] + bv.x, acc[c][4 * i4 + 1] + bv.y, acc[c][4 * i4 + 2] + bv.z,
+                                                acc[c][4 * i4 + 3] + bv.w);
+                                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            }
+                            op[i4] = o;
+                        }
+                    }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 }  // namespace conv2dnhwc
 }  // namespace decnet
 
 using namespace decnet;
 using namespace decnet::conv2dnhwc;
+
+static thread_local int g_halo_variant = 0;
 
 extern "C" {
 
@@ -478,10 +721,38 @@ static int launch_nhwc(const float *x, const float *w_packed, const float *bias,
         }
     }
     const int sms = sm_count_cached();
+    // opt-in (variant 2): two tiles per CTA share each weight stage (pair kernel; exact, measured slower: see its header)
+    if (p.split && np <= 16 * kPairChunks && p.num_tiles >= 2 * sms && g_halo_variant == 2 && !round_out_tf32) {
+        const size_t b_slot = (size_t)2 * taps * np * 128, a_slot = (size_t)2 * kABytes;
+        int na = (int)((226 * 1024 - 1024 - 2 * b_slot) / a_slot);
+        if (na > kMaxASlots) na = kMaxASlots;
+        if (na >= 2) {
+            p.na_slots = na;
+            p.tmem_cols = np <= 8 ? 32 : np <= 16 ? 64 : np <= 32 ? 128 : np <= 64 ? 256 : 512;       // 4 accumulators
+            const size_t smem2 = 2 * b_slot + (size_t)na * a_slot + 1024;
+            static std::mutex mu2;
+            static size_t set_for2[64] = {0};
+            int dev = 0;
+            DECNET_CUDA(cudaGetDevice(&dev));
+            {
+                std::lock_guard<std::mutex> lk(mu2);
+                if (dev < 0 || dev >= 64 || set_for2[dev] < smem2) {
+                    DECNET_CUDA(cudaFuncSetAttribute(conv2d_nhwc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                    if (dev >= 0 && dev < 64) set_for2[dev] = smem2;
+                }
+            }
+            const int pairs = (p.num_tiles + 1) / 2;
+            conv2d_nhwc_pair_kernel<<<(unsigned)(pairs < sms ? pairs : sms), kPairThreads, smem2, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+            return after_launch("conv2d_nhwc_pair_kernel");
+        }
+    }
     const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
     conv2d_nhwc_halo_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
     return after_launch("conv2d_nhwc_halo_kernel");
 }
+
+// 0 / 1 = the one-tile-per-CTA kernel (default); 2 = pair kernel for 3xTF32 launches with >= 2 tiles per SM and np <= 96.  Per thread.
+void decnet_conv2d_nhwc_set_variant(int variant) { g_halo_variant = variant; }
 
 int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream)

@@ -257,6 +257,11 @@ int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, cons
 int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream);
 
+/* Tuning switch (per calling thread): 0 / 1 = one 128-pixel tile per CTA (default); 2 = 3xTF32 launches with at least two tiles
+ * per SM and np <= 96 run the pair kernel (two tiles per CTA share every weight stage: 1.7x fewer bytes from L2 per MMA; exact,
+ * measured slower -- the kernel is bound by shared-memory bandwidth, not by L2: DESIGN.md section 3.4). */
+void decnet_conv2d_nhwc_set_variant(int variant);
+
 /* The same kernel writing a channel slice of a wider bordered tensor (row stride ldc floats, np channels from out_pad). */
 int decnet_conv2d_tc_nhwc_halo_ldc(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                    int B, int h, int w, int cp, int np, int ldc, int relu, int split, void *stream);

@@ -154,3 +154,32 @@ def test_conv2d_3xtf32_nhwc_halo_is_fp32_class(B, H, W, Cin, Cout, relu):
     assert err <= 1e-5 * max(1.0, want.abs().max().item()), (err, want.abs().max().item())
     if np_ > Cout:
         assert got[..., Cout:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,relu", [(1, 180, 324, 73, 81, True), (3, 120, 107, 81, 81, False), (2, 200, 150, 145, 72, True),
+                                                  (6, 61, 109, 72, 36, True)])
+def test_pair_kernel_matches_one_tile_per_cta(B, H, W, Cin, Cout, relu):
+    """conv2d_nhwc_pair_kernel (opt-in variant 2: two tiles per CTA share each weight stage) against the default
+    one-tile-per-CTA kernel: same MMAs per accumulator, other drain points -> equal to fp32 rounding; odd tile counts and the
+    zero border included."""
+    from decnet_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    cp = (Cin + 7) // 8 * 8
+    xn = ops.nchw_cat_to_nhwc_pad([x], cp, round_tf32=False)
+    wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp, split=True)
+    assert B * (H + 2) * (W + 2) >= 2 * 148 * 128
+    want = ops.conv2d_tf32_nhwc_halo(xn, wp, bp, relu, split=True)
+    _lib.lib().decnet_conv2d_nhwc_set_variant(2)
+    try:
+        got = ops.conv2d_tf32_nhwc_halo(xn, wp, bp, relu, split=True)
+    finally:
+        _lib.lib().decnet_conv2d_nhwc_set_variant(0)
+    scale = max(1.0, float(want.abs().max()))
+    assert float((got - want).abs().max()) <= 2e-6 * scale
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
+    ref = (torch.relu(ref) if relu else ref).float()
+    assert float((got[:, 1:-1, 1:-1, :Cout].permute(0, 3, 1, 2) - ref).abs().max()) <= 1e-5 * scale
+    assert float(got[:, 0].abs().max()) == 0 and float(got[:, :, -1].abs().max()) == 0
