@@ -16,7 +16,7 @@
 // boundaries inside the flattened index are covered by the borders, the ends of the tensor by TMA's zero fill.
 //
 // split = 1 ("3xTF32", fp32-class results: the mode the parity gates run on): the activations arrive as plain fp32, four
-// converter warps write hi = rna_tf32(x) in place and lo = rna_tf32(x - hi) beside it, the weights arrive as hi and lo
+// converter warps write lo = rna_tf32(x - trunc_tf32(x)) beside the raw tile (whose truncation by the MMA is the hi part), the weights arrive as hi and lo
 // parts ([18][NP][cp]: taps 0-8 hi, 9-17 lo), and every column tap issues lo*hi + hi*lo + hi*hi into the same accumulator
 // (36 MMAs per stage).  A stage is then 2 x 17 KB of A and 2 x 3 x NP x 128 B of B.
 // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the accumulation
@@ -277,15 +277,13 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     uint4 *sl = reinterpret_cast<uint4 *>(base + (size_t)s * stage_bytes + kABytes);
 #pragma unroll 4
                     for (int i = ctid; i < n16; i += kConvWarps * 32) {
+                        // hi = trunc_tf32(x): what the MMA reads from the raw tile (no store); lo = rna(x - hi) beside it
                         const uint4 v = st[i];
-                        uint4 h, l;
-                        h.x = (v.x + 0x1000u) & 0xFFFFE000u; h.y = (v.y + 0x1000u) & 0xFFFFE000u;
-                        h.z = (v.z + 0x1000u) & 0xFFFFE000u; h.w = (v.w + 0x1000u) & 0xFFFFE000u;
-                        l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) + 0x1000u) & 0xFFFFE000u;
-                        l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) + 0x1000u) & 0xFFFFE000u;
-                        l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) + 0x1000u) & 0xFFFFE000u;
-                        l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) + 0x1000u) & 0xFFFFE000u;
-                        st[i] = h;
+                        uint4 l;
+                        l.x = (__float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u)) + 0x1000u) & 0xFFFFE000u;
+                        l.y = (__float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u)) + 0x1000u) & 0xFFFFE000u;
+                        l.z = (__float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u)) + 0x1000u) & 0xFFFFE000u;
+                        l.w = (__float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u)) + 0x1000u) & 0xFFFFE000u;
                         sl[i] = l;
                     }
                     fence_proxy_async_smem();                     // generic-proxy writes -> visible to the MMA's async proxy

@@ -28,8 +28,8 @@
 //     (cvt.rna, what cuDNN's TF32 path does) in place before the MMA warp reads it.  Weights are
 //     rounded on the host.
 //
-//   * split = 1 ("3xTF32"): the converters write hi = rna_tf32(x) in place and lo = rna_tf32(x - hi) into the second
-//     half of the stage, the weights arrive as hi and lo parts, and every (row group, row tap) issues three MMAs into
+//   * split = 1 ("3xTF32"): hi = trunc_tf32(x) is what the MMA reads from the raw tile; the converters write
+//     lo = rna_tf32(x - hi) into the second half of the stage, the weights arrive as hi and lo parts, and every (row group, row tap) issues three MMAs into
 //     the same accumulator: lo*hi + hi*lo + hi*hi.  The dropped lo*lo term and the rounding of the lo parts are
 //     ~2^-22 relative, so the result is fp32-class (the parity gates of tests/test_glue_gpu.py run on this mode);
 //     the kernel is bound by its epilogue, so the extra MMAs on K = 8 are nearly free.
@@ -388,14 +388,14 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     uint4 *sl = reinterpret_cast<uint4 *>(ring + (size_t)s * stage_bytes + p.lo_off);
 #pragma unroll 4
                     for (int i = ctid; i < n16; i += kConvWarps * 32) {
+                        // hi = the raw tile as the MMA reads it (kind::tf32 drops the low 13 mantissa bits: hi = trunc(x), no
+                        // store needed); lo = rna(x - trunc(x)), exact difference, stored beside it
                         const uint4 v = st[i];
-                        uint4 h, l;
-                        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-                        l.x = rna_tf32(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)));
-                        l.y = rna_tf32(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)));
-                        l.z = rna_tf32(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)));
-                        l.w = rna_tf32(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
-                        st[i] = h;
+                        uint4 l;
+                        l.x = rna_tf32(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u)));
+                        l.y = rna_tf32(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u)));
+                        l.z = rna_tf32(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u)));
+                        l.w = rna_tf32(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u)));
                         sl[i] = l;
                     }
                 } else {
