@@ -39,7 +39,7 @@ namespace conv2dnhwc {
 constexpr int kMaxStages = 6;
 constexpr int kThreads = 320;
 constexpr int kConvWarps = 4;
-constexpr int kGroup = 2;                          // split mode: stages per hi*hi accumulation chain
+constexpr int kGroup = 4;                          // split mode: stages per hi*hi accumulation chain
 constexpr int kTileM = 128;
 constexpr int kARows = 130;                        // 128 pixels + one halo pixel on each side
 constexpr int kABytes = 17 * 1024;                 // 130 rows x 128 B rounded up to the 1 KB swizzle period

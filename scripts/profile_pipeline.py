@@ -1,5 +1,5 @@
 """Per-kernel time breakdown of one hot-path step (torch.profiler / CUPTI), to see Amdahl.
-Usage: python scripts/profile_pipeline.py [--conv3d cudnn|tcgen05] [--batch 8]"""
+Usage: python scripts/profile_pipeline.py [--precision fp32|tf32] [--batch 8]"""
 import argparse
 import sys
 from pathlib import Path
@@ -11,12 +11,12 @@ sys.path.insert(0, str(ROOT))
 from decnet_b200.synthetic import build_workload  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--conv3d", default="tcgen05")
+ap.add_argument("--precision", default="fp32")
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--workload", default="sceneflow")
 args = ap.parse_args()
 torch.backends.cudnn.benchmark = True
-model, left, right, info = build_workload(args.workload, args.batch, conv3d_impl=args.conv3d)
+model, left, right, info = build_workload(args.workload, args.batch, precision=args.precision)
 print(info)
 for _ in range(3):
     model(left, right)
