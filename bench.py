@@ -785,13 +785,6 @@ def run_ours(args):
             except Exception as e:
                 gpu_ref = {"error": f"{type(e).__name__}: {e}"}
 
-    bands = None
-    if extras and world > 1 and not bands_mode:
-        try:
-            bands = leg_bands(args, env)
-        except Exception as e:
-            bands = {"error": f"{type(e).__name__}: {e}"}
-
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # a fresh process: this one is bound to its GPU's NUMA node and its OpenMP pool was created under that mask
@@ -803,6 +796,7 @@ def run_ours(args):
         except Exception as e:
             cpu = {"error": f"{type(e).__name__}: {e}"}
 
+    line = bands = None
     if rank == 0:
         conv_dtype = "3xTF32 (hi/lo split, fp32-class) in / f32 acc" if args.precision == "fp32" else "tf32 in / f32 acc"
         line = {"metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -819,17 +813,42 @@ def run_ours(args):
                            "streams": "masks + sparse ops on a forked second stream (two graph branches)" if not args.no_overlap else "one stream",
                            "l2": "inputs (400 MB of feature pyramids per step) exceed the 126 MB L2; no flush",
                            "host_numa": env.numa,
-                           "parallelism": (f"row bands of one batch over {world} rank(s): per-layer halo send/recv in the "
-                                           "3-D aggregation, all-gather of the per-level disparity") if bands_mode
+                           "parallelism": (f"row bands of one batch over {world} rank(s): per-layer halo rows and per-level disparity "
+                                           "bands stored into peer memory over NVLink") if bands_mode
                            else f"by stereo pair, {world} rank(s), no collective"},
                 "e2e": e2e, "e2e_pyramids": e2e_pyr,
                 "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tensor, "roofline_conv2d": roof_conv2d,
-                "cpu_baseline": cpu, "from_images": from_images, "tf32": tf32, "gpu_reference": gpu_ref, "bands": bands}
+                "cpu_baseline": cpu, "from_images": from_images, "tf32": tf32, "gpu_reference": gpu_ref, "bands": None}
+
+    # ---- the last leg talks to the other ranks through peer memory: a watchdog guarantees that the line above is printed
+    # (without the `bands` object) and that every rank exits even if a peer fails inside it
+    if extras and world > 1 and not bands_mode:
+        def bail():
+            if rank == 0:
+                line["bands"] = {"error": "the row-band leg did not finish within 240 s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(240.0, bail)
+        dog.daemon = True
+        dog.start()
+        try:
+            bands = leg_bands(args, env)
+        except Exception as e:
+            bands = {"error": f"{type(e).__name__}: {e}"}
+        dog.cancel()
+        if rank == 0:
+            line["bands"] = bands
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        if isinstance(bands, dict) and "error" in bands:
+            os._exit(0)                      # a rank failed inside the peer-memory leg: the group cannot be torn down cleanly
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def run_cpu_leg(args):
