@@ -33,6 +33,7 @@ SIGNATURES = {
     "decnet_costvol_bf16_ndhwc": (_i, [_f32p] * 3 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv3d_bf16": (_i, [_f32p] * 5 + [_i] * 8 + [C.c_void_p]),
     "decnet_conv3d_bf16_band": (_i, [_f32p] * 5 + [_i] * 7 + [C.c_void_p]),
+    "decnet_conv3d_bf16_softargmin": (_i, [_f32p] * 5 + [_i] * 7 + [C.c_void_p]),
     "decnet_costvol_bf16_ndhwc_rows": (_i, [_f32p] * 3 + [_i] * 8 + [C.c_void_p]),
     "decnet_refine_pack_rows": (_i, [_f32p] * 4 + [_i] * 6 + [C.c_void_p]),
     "decnet_conv2d_tf32_nhwc": (_i, [_f32p] * 4 + [_i] * 7 + [C.c_void_p]),

@@ -60,7 +60,7 @@ def conv3d_layer(x, w, bias, np_, relu, residual=None, out=None, out_f32=False, 
     return out
 
 
-def run_stack(reg, vol):
+def run_stack(reg, vol, with_pred=False):
     """vol bf16 [B,D,H,W,CP] -> regularised cost fp32 [B,D,H,W]; o = conv1(conv0(x)) + conv0(x)."""
     pk = packed_stack(reg)
     u = pk["units"]
@@ -72,7 +72,25 @@ def run_stack(reg, vol):
     conv3d_layer(t2, u[4][0], u[4][1], u[4][2], True, residual=o0, out=t1)
     conv3d_layer(t1, u[5][0], u[5][1], u[5][2], True, out=t2)
     conv3d_layer(t2, u[6][0], u[6][1], u[6][2], True, out=t1)
-    return conv3d_layer(t1, u[7][0], u[7][1], u[7][2], False, out_f32=True)
+    if not with_pred:
+        return conv3d_layer(t1, u[7][0], u[7][1], u[7][2], False, out_f32=True)
+    # last layer + soft-argmin (a4) in one launch
+    B, D, H, W, cp = t1.shape
+    cost = torch.empty((B, D, H, W), dtype=torch.float32, device=t1.device)
+    pred = torch.empty((B, H, W), dtype=torch.float32, device=t1.device)
+    with torch.cuda.device_of(t1):
+        st = _lib.lib().decnet_conv3d_bf16_softargmin(t1.data_ptr(), u[7][0].data_ptr(), u[7][1].data_ptr(), cost.data_ptr(),
+                                                      pred.data_ptr(), B, D, H, W, cp, u[7][2], 0,
+                                                      torch.cuda.current_stream(t1.device).cuda_stream)
+    _lib.check(st, "decnet_conv3d_bf16_softargmin")
+    return pred, cost
+
+
+def dense_pred(reg, Lf, Rf, D):
+    """a2 + a3 + a4: cost volume -> tcgen05 stack -> soft-argmin (in the last layer's epilogue).  (pred [B,H,W], cost)."""
+    pk = packed_stack(reg)
+    vol = ops.cost_volume_bf16_ndhwc(Lf, Rf, D, pk["cp"])
+    return run_stack(reg, vol, with_pred=True)
 
 
 def dense_cost(reg, Lf, Rf, D):

@@ -167,6 +167,8 @@ struct Params {
     int skip_h_edges;                  // row-band mode: rows h = 0 and h = H-1 are halo slots a NEIGHBOUR rank fills over NVLink
                                        // (or that stay zero at the image edge); this launch must not store into them
     long long *dbg;                    // optional per-CTA timing (decnet_conv3d_debug_timing), else null
+    float *pred;                       // mode 1, td == 1: soft-argmin over the tile's disparities fused into the epilogue
+                                       // ([B][H][W]; submodule.py:766-777), else null
 };
 
 // work item -> (tile, first output channel, number of output channels)
@@ -189,6 +191,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float cost_s[2][128];   // fused soft-argmin: the tile's costs, double-buffered over tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *base = reinterpret_cast<unsigned char *>(
@@ -358,7 +361,28 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (p.mode == 1) {
                 float v[16];
                 tmem_ld16(trow, v);
-                if (valid) { float x = v[0] + p.bias[0]; if (p.relu) x = fmaxf(x, 0.f); p.out_f32[m] = x; }
+                float x = v[0] + p.bias[0];
+                if (p.relu) x = fmaxf(x, 0.f);
+                if (valid) p.out_f32[m] = x;
+                if (p.pred) {
+                    // a4 in the epilogue: the tile box spans all D disparities (td == 1), so the 128 accumulator rows hold
+                    // the whole cost column of bw*bh pixels.  Same arithmetic as softargmin_kernel (max-shifted expf, sums
+                    // in disparity order), so the fused and the two-launch routes agree bit for bit.
+                    float *cs = cost_s[j & 1];
+                    cs[r] = d < p.D ? x : -INFINITY;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+                    const int npix = p.bw * p.bh;
+                    if (r < npix && w < p.W && h < p.H) {                   // r < npix: dd == 0, (h, w) is the pixel
+                        float mx = -INFINITY;
+                        for (int e = 0; e < p.D; ++e) mx = fmaxf(mx, cs[e * npix + r]);
+                        float s0 = 0.f, s1 = 0.f;
+                        for (int e = 0; e < p.D; ++e) {
+                            const float ex = expf(cs[e * npix + r] - mx);
+                            s0 += ex; s1 += ex * (float)e;
+                        }
+                        p.pred[((size_t)b * p.H + h) * p.W + w] = s1 / s0;
+                    }
+                }
             } else if (p.mode == 2) {
                 for (int cc = 0; cc < nlen; cc += 16) {
                     const int c0 = n0 + cc;
@@ -730,7 +754,7 @@ void decnet_conv3d_debug_timing(void *dbg_buffer) { g_conv3d_dbg = static_cast<l
 //                  esize 4 -> fp32 operands read as tf32 (kind::tf32, K-step 8, 32 channels per row).
 static int launch_conv(const void *x, const void *w_packed, const float *bias, const void *residual, void *out,
                        int out_mode, int esize, int taps_d, int B, int D, int H, int W, int cp, int np, int relu,
-                       void *stream, int round_out = 0, int skip_h_edges = 0)
+                       void *stream, int round_out = 0, int skip_h_edges = 0, float *pred = nullptr, int *pred_fused = nullptr)
 {
     DECNET_REQUIRE(x && w_packed && bias && out, "null pointer");
     DECNET_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "non-positive size");
@@ -757,6 +781,9 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
     p.tw = (W + p.bw - 1) / p.bw; p.th = (H + p.bh - 1) / p.bh; p.td = (D + p.bd - 1) / p.bd;
     p.relu = relu; p.mode = out_mode; p.round_tf32 = round_out; p.skip_h_edges = skip_h_edges;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;   // 2 slots
+    // fused soft-argmin: needs the whole disparity axis inside one tile box (single-CTA kernel, mode 1)
+    p.pred = (pred && out_mode == 1 && p.td == 1 && (g_conv3d_variant % 10) != 2) ? pred : nullptr;
+    if (pred_fused) *pred_fused = p.pred != nullptr;
 
     const long long tiles = (long long)B * p.tw * p.th * p.td;
     DECNET_REQUIRE(tiles < (1ll << 31), "too many tiles");
@@ -841,6 +868,19 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
 {
     DECNET_REQUIRE(out_mode == 0 || out_mode == 1, "out_mode must be 0 (bf16 [M][np]) or 1 (fp32 [M], channel 0)");
     return launch_conv(x_ndhwc, w_packed, bias, residual, out, out_mode, 2, 3, B, D, H, W, cp, np, relu, stream);
+}
+
+// a3 (last layer) + a4 in one launch: cost fp32 [B,D,H,W] (channel 0) and pred [B,H,W] = soft-argmin_d(cost).  The
+// soft-argmin runs in the conv epilogue when one tile box spans the D axis (D <= 8 at every published stage-0 size);
+// otherwise the standalone kernel follows on the same stream.  Same result either way.
+int decnet_conv3d_bf16_softargmin(const void *x_ndhwc, const void *w_packed, const float *bias, float *cost, float *pred,
+                                  int B, int D, int H, int W, int cp, int np, int relu, void *stream)
+{
+    DECNET_REQUIRE(pred, "null pointer");
+    int fused = 0;
+    const int st = launch_conv(x_ndhwc, w_packed, bias, nullptr, cost, 1, 2, 3, B, D, H, W, cp, np, relu, stream, 0, 0, pred, &fused);
+    if (st != 0 || fused) return st;
+    return decnet_softargmin(cost, pred, B, D, H, W, stream);
 }
 
 int decnet_conv3d_bf16_band(const void *x_ndhwc, const void *w_packed, const float *bias, const void *residual,

@@ -727,8 +727,7 @@ class DecompMatching(nn.Module):
         """a1-a4: cost volume -> 3-D aggregation -> soft-argmin.  Returns (pred [B,H,W], cost [B,D,H,W])."""
         from . import conv3d
         self.cost_regularizer._check_inference()
-        cost = conv3d.dense_cost(self.cost_regularizer, Lf, Rf, D)
-        return ops.softargmin(cost), cost
+        return conv3d.dense_pred(self.cost_regularizer, Lf, Rf, D)
 
 
 def set_precision(module, precision):

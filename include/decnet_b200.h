@@ -175,6 +175,14 @@ int decnet_conv3d_bf16(const void *x_ndhwc, const void *w_packed, const float *b
                        const void *residual, void *out, int out_mode,
                        int B, int D, int H, int W, int cp, int np, int relu, void *stream);
 
+/* Last layer of the aggregation stack (the 216->1 Conv3d, modules/submodule.py:659-662) together with the soft-argmin that
+ * follows it (disparity_regression, modules/submodule.py:766-777, called at SparseDenseNetRefinementMask.py:237-239):
+ *   cost fp32 [B,D,H,W] = channel 0 of the layer,  pred fp32 [B,H,W] = sum_d softmax_d(cost) * d.
+ * When one 128-voxel tile box spans the whole D axis (D <= 8 at every published stage-0 size) the soft-argmin runs in the
+ * conv epilogue of the same launch; otherwise decnet_softargmin follows on the same stream.  Both routes give the same bits. */
+int decnet_conv3d_bf16_softargmin(const void *x_ndhwc, const void *w_packed, const float *bias, float *cost, float *pred,
+                                  int B, int D, int H, int W, int cp, int np, int relu, void *stream);
+
 /* Row-band form (one huge pair split across GPUs): the tensors are a band [B,D,rows+2,W,.] whose
  * rows 0 and rows+1 are halo slots.  The layer computes every owned row from the band (halo rows are inputs) and does NOT
  * store into the halo rows of `out`: they are filled by the neighbouring ranks over NVLink peer memory (decnet_b200/bands.py)

@@ -57,6 +57,31 @@ def test_single_layer_vs_fp32_conv(B, D, H, W, C, Cout, relu, use_res):
             assert got[..., Cout:].abs().max().item() == 0          # padded channels stay exactly zero
 
 
+@pytest.mark.parametrize("B,D,H,W,C", [(8, 8, 20, 36, 216), (2, 8, 14, 47, 216), (1, 5, 7, 9, 64), (1, 8, 1, 3, 32),
+                                        (1, 29, 9, 11, 64), (1, 16, 6, 10, 48), (1, 1, 4, 4, 16)])
+def test_last_layer_with_fused_softargmin(B, D, H, W, C):
+    """The 216->1 layer + soft-argmin in one launch (in the epilogue when one tile box spans D, else the second kernel):
+    cost identical to the plain mode-1 layer and pred identical, bit for bit, to decnet_softargmin of that cost."""
+    from decnet_b200 import _lib, conv3d as c3, ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cp = c3._pad16(C)
+    x = torch.zeros(B, D, H, W, cp, device="cuda", dtype=torch.bfloat16)
+    x[..., :C] = torch.randn(B, D, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.zeros(27, 16, cp, device="cuda", dtype=torch.bfloat16)
+    w[:, :1, :C] = (torch.randn(27, 1, C, device="cuda", generator=g) * (8.0 / (27 * C)) ** 0.5).to(torch.bfloat16)
+    bias = torch.zeros(16, device="cuda"); bias[0] = 0.3
+    cost_ref = c3.conv3d_layer(x, w, bias, 16, False, out_f32=True)
+    pred_ref = ops.softargmin(cost_ref)
+    cost = torch.full((B, D, H, W), float("nan"), device="cuda")
+    pred = torch.full((B, H, W), float("nan"), device="cuda")
+    st = _lib.lib().decnet_conv3d_bf16_softargmin(x.data_ptr(), w.data_ptr(), bias.data_ptr(), cost.data_ptr(), pred.data_ptr(),
+                                                  B, D, H, W, cp, 16, 0, torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "decnet_conv3d_bf16_softargmin")
+    assert torch.equal(cost, cost_ref)
+    assert torch.equal(pred, pred_ref)
+    assert 0 <= pred.min().item() and pred.max().item() <= D - 1
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_stack_vs_reference_golden(name):
     """Full a2+a3+a4 with the bf16 tcgen05 stack against the reference's fp32 golden coarse disparity."""
