@@ -59,6 +59,11 @@ struct Params {
     int dst_h, dst_w;                              // > 0 (GEMM mode, border = 0): row p = (b, y, x) of a flat [B, dst_h, dst_w]
                                                    // grid is stored at the interior pixel (b, y+1, x+1) of a zero-bordered one
     int na_slots;                                  // pair kernel: slots of the A ring (the B ring has two)
+    long long *trace;                              // tuning only (decnet_conv2d_nhwc_debug_trace): clock64 timeline of CTA 0,
+                                                   // [256 stages][8]: 0 slot free (TMA issued), 1 landed, 2 converted, 3 issuer saw it,
+                                                   // 4 MMAs + commit issued; then [256 drains][2]: chain finished, drained
+    int dbg;                                       // tuning only (variant 100 + mask): 1 converters idle, 2 no correction MMAs,
+                                                   // 4 no hi*hi MMAs, 8 no weight TMA after the first ring fill, 16 no drains
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -105,6 +110,96 @@ __device__ __forceinline__ void umma_taps3(int ksteps, uint32_t acc, uint64_t da
         }
     }
 }
+// The same column-tap block for kind::f16 operands (K-steps of 16 halves = the same 32 bytes): the correction terms of split = 2.
+#define DH_NEXT(OFF)                                                               \
+        "add.u64 a, %1, " #OFF ";\n\t"                                              \
+        "add.u64 b, %2, " #OFF ";\n\t"                                              \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+#define DH_HEAD                                                                    \
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b;\n\t"                            \
+        "elect.sync _|e, 0xffffffff;\n\t"                                           \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                 \
+        "setp.eq.b32 t, 0, 0;\n\t"                                                  \
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+template <int KSTEPS>
+__device__ __forceinline__ void umma_tap_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate_first) {
+    if constexpr (KSTEPS == 4)
+        asm volatile(DH_HEAD DH_NEXT(2) DH_NEXT(4) DH_NEXT(6) "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+    else if constexpr (KSTEPS == 3)
+        asm volatile(DH_HEAD DH_NEXT(2) DH_NEXT(4) "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+    else if constexpr (KSTEPS == 2)
+        asm volatile(DH_HEAD DH_NEXT(2) "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+    else
+        asm volatile(DH_HEAD "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+__device__ __forceinline__ void umma_taps3_f16(int ksteps, uint32_t acc, uint64_t da, uint64_t db, uint32_t db_tap_step,
+                                               uint32_t idesc, uint32_t first, int ntaps = 3) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+        if (kw >= ntaps) break;
+        const uint64_t a = da + (uint64_t)(8 * kw), b = db + (uint64_t)(kw * db_tap_step);
+        const uint32_t acc_first = (kw == 0) ? first : 1u;
+        switch (ksteps) {
+            case 4: umma_tap_f16<4>(acc, a, b, idesc, acc_first); break;
+            case 3: umma_tap_f16<3>(acc, a, b, idesc, acc_first); break;
+            case 2: umma_tap_f16<2>(acc, a, b, idesc, acc_first); break;
+            default: umma_tap_f16<1>(acc, a, b, idesc, acc_first); break;
+        }
+    }
+}
+// split = 2 converter arithmetic for two neighbouring channels (c, c+1) -> packed halves, c in the low half:
+//   lo16 = fp16(2^11 * (x - trunc_tf32(x)))   (the residual has <= 13 significant bits; fp16 keeps 11, like the TF32 lo part)
+//   hi16 = fp16(x)                            (multiplies the 2^-11-sized lo part of the weights: its 2^-11 rounding is 2^-22 overall)
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float hi_half, float lo_half) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_half), "f"(lo_half));
+    return d;
+}
+__device__ __forceinline__ uint32_t lo16x2(uint32_t a, uint32_t b) {
+    const float fa = (__uint_as_float(a) - __uint_as_float(a & 0xFFFFE000u)) * 2048.f;
+    const float fb = (__uint_as_float(b) - __uint_as_float(b & 0xFFFFE000u)) * 2048.f;
+    return cvt_f16x2_sat(fb, fa);
+}
+__device__ __forceinline__ uint32_t hi16x2(uint32_t a, uint32_t b) { return cvt_f16x2_sat(__uint_as_float(b), __uint_as_float(a)); }
+
+// split = 2 converter: the fp16 correction operand of one landed activation tile.  Row r of the second tile =
+// [lo16 of the chunk's channels | fp16 of the same channels], 4 bytes per channel, K-major SWIZZLE_128B like the raw tile (16-byte
+// unit j of row r sits at unit j ^ (r & 7)).  A thread converts 8 channels of one row: two 16-byte reads, two 16-byte writes; a
+// quarter warp covers rows (q, q ^ 5) of an 8-row group, which keeps the four reads and the four writes of both rows on distinct
+// bank groups.  cl8 = 8-channel groups in this chunk (4, or last_ksteps in the last chunk); cw = converter warp 0..kConvWarps-1.
+__device__ __forceinline__ void convert_tile_f16(const unsigned char *raw, unsigned char *a2, int a_rows, int cl8, int cw, int lane)
+{
+    const int qw = lane >> 3, u = lane & 7, c8 = u & 3;
+    const int rsub = u < 4 ? qw : (qw ^ 5);
+    if (c8 >= cl8) return;
+    // all reads of the thread first (the stores could alias them for the compiler, and a shared-memory round trip is long while
+    // the MMAs of the other stage stream their operands): one latency, not five
+    constexpr int kPass = (kARows + kConvWarps * 8 - 1) / (kConvWarps * 8);
+    const int r0 = cw * 8 + rsub, x7 = r0 & 7;                        // r & 7 is the same in every pass
+    const unsigned char *src = raw + r0 * 128;
+    unsigned char *dst = a2 + r0 * 128;
+    const int o0 = ((2 * c8) ^ x7) << 4, o1 = ((2 * c8 + 1) ^ x7) << 4;
+    const int ol = (c8 ^ x7) << 4, oh = ((cl8 + c8) ^ x7) << 4;
+    uint4 v0[kPass], v1[kPass];
+#pragma unroll
+    for (int k = 0; k < kPass; ++k)
+        if (r0 + k * (kConvWarps * 8) < a_rows) {
+            v0[k] = *reinterpret_cast<const uint4 *>(src + k * (kConvWarps * 8 * 128) + o0);
+            v1[k] = *reinterpret_cast<const uint4 *>(src + k * (kConvWarps * 8 * 128) + o1);
+        }
+#pragma unroll
+    for (int k = 0; k < kPass; ++k)
+        if (r0 + k * (kConvWarps * 8) < a_rows) {
+            uint4 l, h;
+            l.x = lo16x2(v0[k].x, v0[k].y); l.y = lo16x2(v0[k].z, v0[k].w);
+            l.z = lo16x2(v1[k].x, v1[k].y); l.w = lo16x2(v1[k].z, v1[k].w);
+            h.x = hi16x2(v0[k].x, v0[k].y); h.y = hi16x2(v0[k].z, v0[k].w);
+            h.z = hi16x2(v1[k].x, v1[k].y); h.w = hi16x2(v1[k].z, v1[k].w);
+            *reinterpret_cast<uint4 *>(dst + k * (kConvWarps * 8 * 128) + ol) = l;
+            *reinterpret_cast<uint4 *>(dst + k * (kConvWarps * 8 * 128) + oh) = h;
+        }
+}
+
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -131,6 +226,8 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t ready_bar[kMaxStages];   // split mode: hi/lo tiles written by the converters
+    __shared__ __align__(8) uint64_t afull_bar[kMaxStages];   // split mode: the activation tile landed (the converters start
+                                                              // while the 4x larger weight part of the stage is still in flight)
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ __align__(8) uint64_t small_full_bar[2];       // split mode: the per-tile accumulator of the small terms
@@ -153,7 +250,9 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps); }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], kConvWarps); mbar_init(&afull_bar[s], 1);
+        }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4);
             mbar_init(&small_full_bar[a], 1); mbar_init(&small_empty_bar[a], 4);
@@ -174,16 +273,30 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
+            int nfill = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int p0 = tile * kTileM;
                 for (int kh = 0; kh < T; ++kh)
                     for (int ck = 0; ck < p.nchunks; ++ck) {
                         mbar_wait(&empty_bar[s], ph ^ 1u);
                         unsigned char *sa = base + (size_t)s * stage_bytes;
-                        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)tx_bytes);
-                        tma_load_2d(sa, &tmA, ck * 32, T == 3 ? p0 + (kh - 1) * pitch - 1 : p0, &full_bar[s]);
+                        const bool skip_b = (p.dbg & 8) && nfill >= kStages;
+                        if (p.trace && blockIdx.x == 0 && nfill < 256) p.trace[nfill * 8 + 0] = clock64();
+                        ++nfill;
+                        // split mode: the activation tile completes its own barrier, which is all the converters wait for
+                        uint64_t *abar = p.split ? &afull_bar[s] : &full_bar[s];
+                        if (p.split) {
+                            mbar_arrive_expect_tx(abar, (uint32_t)(a_rows * 128));
+                            if (skip_b) mbar_arrive(&full_bar[s]);
+                            else mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(tx_bytes - a_rows * 128));
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(skip_b ? a_rows * 128 : tx_bytes));
+                        }
+                        tma_load_2d(sa, &tmA, ck * 32, T == 3 ? p0 + (kh - 1) * pitch - 1 : p0, abar);
+                        if (!skip_b) {
                         tma_load_3d(sa + b_off, &tmB, ck * 32, 0, kh * T, &full_bar[s]);
                         if (p.split) tma_load_3d(sa + b_off + T * b_tap_bytes, &tmB, ck * 32, 0, T * T + kh * T, &full_bar[s]);
+                        }
                         if (++s == kStages) { s = 0; ph ^= 1u; }
                     }
             }
@@ -192,6 +305,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         // ===================== MMA issuer =====================
         // c_format F32, a/b TF32, both K-major, N = np, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.np >> 3) << 17) | (8u << 24);
+        const uint32_t idesc16 = (1u << 4) | ((uint32_t)(p.np >> 3) << 17) | (8u << 24);     // a/b format F16 (0)
         const uint32_t smem_base = smem_u32(base);
         const uint32_t empty_base = smem_u32(&empty_bar[0]);
         const uint32_t db_tap_step = (uint32_t)(b_tap_bytes >> 4);
@@ -203,6 +317,7 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const uint32_t full_base = smem_u32(&tmem_full_bar[0]);
             const int nst = T * p.nchunks;
             uint32_t it = 0, j = 0;
+            int nmma = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
                 const uint32_t sj = j & 1u;
                 mbar_wait(&small_empty_bar[sj], ((j >> 1) & 1u) ^ 1u);
@@ -219,6 +334,9 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                             first_b = 0u;
                         }
                         if (!ready) mbar_wait(&ready_bar[s], ph);
+                        mbar_wait(&full_bar[s], ph);                      // the weights of the stage
+                        const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && nmma < 256;
+                        if (tr) p.trace[nmma * 8 + 3] = clock64();
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)(s * stage_bytes);
                         const uint64_t da = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + (uint32_t)kABytes);
@@ -228,12 +346,21 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         if (sn == kStages) { sn = 0; phn ^= 1u; }
                         ready = mbar_test_wait(&ready_bar[sn], phn);
                         const int ks = ck == p.nchunks - 1 ? p.last_ksteps : 4;
-                        umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s, T);     // lo(x) * hi(w)
-                        umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u, T);          // hi(x) * lo(w)
+                        if (p.dbg & 2) {
+                        } else if (p.split == 2) {
+                            // [lo16(x) | fp16(x)] * [hi16(w) ; lo16(w)]: both correction terms, K-concatenated fp16
+                            umma_taps3_f16(ks, acc_s, da_lo, db_lo, db_tap_step, idesc16, first_s, T);
+                        } else {
+                            umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s, T); // lo(x) * hi(w)
+                            umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u, T);      // hi(x) * lo(w)
+                        }
+                        if (!(p.dbg & 4))
                         umma_taps3(ks, acc_b, da, db, db_tap_step, idesc, first_b, T);        // hi(x) * hi(w)
                         first_s = 1u; first_b = 1u;
                         umma_commit_elect(empty_base + (uint32_t)(s * 8));
                         if (gpos == kGroup - 1 || st == nst - 1) { umma_commit_elect(full_base + slot * 8u); ++it; }
+                        if (tr) p.trace[nmma * 8 + 4] = clock64();
+                        ++nmma;
                         s = sn; ph = phn;
                     }
                 umma_commit_elect(smem_u32(&small_full_bar[sj]));
@@ -270,11 +397,19 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const int ctid = threadIdx.x - 6 * 32;
             const int n16 = a_rows * 128 / 16;                    // 16-byte words TMA delivered for A
             int s = 0; uint32_t ph = 0;
+            int nconv = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
                 for (int it = 0; it < T * p.nchunks; ++it) {
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait(&afull_bar[s], ph);
+                    const bool tr = p.trace && blockIdx.x == 0 && warp == 6 && lane == 0 && nconv < 256;
+                    if (tr) p.trace[nconv * 8 + 1] = clock64();
                     uint4 *st = reinterpret_cast<uint4 *>(base + (size_t)s * stage_bytes);
                     uint4 *sl = reinterpret_cast<uint4 *>(base + (size_t)s * stage_bytes + kABytes);
+                    if (p.dbg & 1) {
+                    } else if (p.split == 2) {
+                        convert_tile_f16(reinterpret_cast<const unsigned char *>(st), reinterpret_cast<unsigned char *>(sl), a_rows,
+                                         (it % p.nchunks == p.nchunks - 1) ? p.last_ksteps : 4, warp - 6, lane);
+                    } else
 #pragma unroll 4
                     for (int i = ctid; i < n16; i += kConvWarps * 32) {
                         // hi = trunc_tf32(x): what the MMA reads from the raw tile (no store); lo = rna(x - hi) beside it
@@ -288,6 +423,8 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     }
                     fence_proxy_async_smem();                     // generic-proxy writes -> visible to the MMA's async proxy
                     __syncwarp();
+                    if (tr) p.trace[nconv * 8 + 2] = clock64();
+                    ++nconv;
                     if (lane == 0) mbar_arrive(&ready_bar[s]);
                     if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
@@ -338,18 +475,20 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             float acc[kMaxChunks][16];
             const int ngroups = (T * p.nchunks + kGroup - 1) / kGroup;
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-            auto drain = [&](uint32_t trow) {
+            auto drain = [&](uint32_t trow, float scale) {
 #pragma unroll
                 for (int c = 0; c < kMaxChunks; ++c)
                     if (c * 16 < p.np) {
                         float v[16];
                         tmem_ld16(trow + (uint32_t)(c * 16), v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[c][i] += v[i];
+                        for (int i = 0; i < 16; ++i) acc[c][i] = fmaf(v[i], scale, acc[c][i]);
                     }
                 tc_fence_before();
                 __syncwarp();
             };
+            // split = 2: the correction accumulator holds 2^(11+sw) x the value (see the weight packer); bias[np] = 2^-(11+sw)
+            const float small_scale = p.split == 2 ? __ldg(p.bias + p.np) : 1.f;
             uint32_t it = 0, j = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
                 const long long pix = (long long)tile * kTileM + r;
@@ -363,14 +502,17 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 for (int g = 0; g < ngroups; ++g, ++it) {
                     const uint32_t slot = it & 1u;
                     mbar_wait(&tmem_full_bar[slot], (it >> 1) & 1u);
+                    const bool tr = p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 256;
+                    if (tr) p.trace[2048 + it * 2] = clock64();
                     tc_fence_after();
-                    drain(lane_base + slot * (uint32_t)acc_stride);
+                    drain(lane_base + slot * (uint32_t)acc_stride, 1.f);
+                    if (tr) p.trace[2048 + it * 2 + 1] = clock64();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
                 }
                 const uint32_t sj = j & 1u;
                 mbar_wait(&small_full_bar[sj], (j >> 1) & 1u);
                 tc_fence_after();
-                drain(lane_base + (2u + sj) * (uint32_t)acc_stride);
+                drain(lane_base + (2u + sj) * (uint32_t)acc_stride, small_scale);
                 if (lane == 0) mbar_arrive(&small_empty_bar[sj]);
                 if (inside) {
 #pragma unroll
@@ -497,6 +639,7 @@ conv2d_nhwc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.np >> 3) << 17) | (8u << 24);
+        const uint32_t idesc16 = (1u << 4) | ((uint32_t)(p.np >> 3) << 17) | (8u << 24);
         const uint32_t b_base_u = smem_u32(base), a_base_u = smem_u32(a_base);
         const uint32_t db_tap_step = (uint32_t)(b_tap_bytes >> 4);
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
@@ -527,8 +670,12 @@ conv2d_nhwc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         const uint64_t da = make_desc_sw128(sau), da_lo = make_desc_sw128(sau + (uint32_t)kABytes);
                         const uint32_t acc_b = tmem_base + (uint32_t)(m * acc_stride);
                         const uint32_t acc_s = tmem_base + (uint32_t)((2 + m) * acc_stride);
-                        umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s[m], T);     // lo(x) * hi(w)
-                        umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u, T);            // hi(x) * lo(w)
+                        if (p.split == 2) {
+                            umma_taps3_f16(ks, acc_s, da_lo, db_lo, db_tap_step, idesc16, first_s[m], T);  // both corrections, fp16
+                        } else {
+                            umma_taps3(ks, acc_s, da_lo, db, db_tap_step, idesc, first_s[m], T); // lo(x) * hi(w)
+                            umma_taps3(ks, acc_s, da, db_lo, db_tap_step, idesc, 1u, T);        // hi(x) * lo(w)
+                        }
                         umma_taps3(ks, acc_b, da, db, db_tap_step, idesc, first_b[m], T);       // hi(x) * hi(w)
                         first_s[m] = 1u; first_b[m] = 1u;
                         umma_commit_elect(smem_u32(&a_empty[sa]));
@@ -551,6 +698,10 @@ conv2d_nhwc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 mbar_wait(&a_full[sa], pha);
                 uint4 *sh = reinterpret_cast<uint4 *>(a_base + (size_t)sa * a_slot_bytes);
                 uint4 *sl = reinterpret_cast<uint4 *>(a_base + (size_t)sa * a_slot_bytes + kABytes);
+                if (p.split == 2) {
+                    convert_tile_f16(reinterpret_cast<const unsigned char *>(sh), reinterpret_cast<unsigned char *>(sl), a_rows,
+                                     ((it >> 1) % p.nchunks == p.nchunks - 1) ? p.last_ksteps : 4, warp - 10, lane);
+                } else
 #pragma unroll 4
                 for (int i = ctid; i < n16; i += kConvWarps * 32) {
                     const uint4 v = sh[i];
@@ -596,14 +747,14 @@ conv2d_nhwc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int c = 0; c < kPairChunks; ++c)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[c][i] = 0.f;
-            auto drain = [&](uint32_t trow) {
+            auto drain = [&](uint32_t trow, float scale) {
 #pragma unroll
                 for (int c = 0; c < kPairChunks; ++c)
                     if (c * 16 < p.np) {
                         float v[16];
                         tmem_ld16(trow + (uint32_t)(c * 16), v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[c][i] += v[i];
+                        for (int i = 0; i < 16; ++i) acc[c][i] = fmaf(v[i], scale, acc[c][i]);
                     }
                 tc_fence_before();
                 __syncwarp();
@@ -611,12 +762,12 @@ conv2d_nhwc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int g = 0; g < ngroups; ++g, ++chain) {
                 mbar_wait(&big_full[m], chain & 1u);
                 tc_fence_after();
-                drain(lane_base + (uint32_t)(m * acc_stride));
+                drain(lane_base + (uint32_t)(m * acc_stride), 1.f);
                 if (lane == 0) mbar_arrive(&big_empty[m]);
             }
             mbar_wait(&small_full[m], j & 1u);
             tc_fence_after();
-            drain(lane_base + (uint32_t)((2 + m) * acc_stride));
+            drain(lane_base + (uint32_t)((2 + m) * acc_stride), p.split == 2 ? __ldg(p.bias + p.np) : 1.f);
             if (lane == 0) mbar_arrive(&small_empty[m]);
             if (inside) {
 #pragma unroll
@@ -654,6 +805,7 @@ using namespace decnet;
 using namespace decnet::conv2dnhwc;
 
 static thread_local int g_halo_variant = 0;
+static thread_local long long *g_halo_trace = nullptr;
 
 extern "C" {
 
@@ -669,6 +821,7 @@ static int launch_nhwc(const float *x, const float *w_packed, const float *bias,
     DECNET_REQUIRE(P > 0, "non-positive size");
     DECNET_REQUIRE(cp % 8 == 0 && cp >= 8 && cp <= 8192, "cp=%d must be a multiple of 8", cp);
     DECNET_REQUIRE(np % 16 == 0 && np >= 16 && np <= 256, "np=%d must be a multiple of 16 in [16,256]", np);
+    DECNET_REQUIRE(split >= 0 && split <= 2, "split must be 0 (TF32), 1 (3xTF32) or 2 (TF32 + fp16 corrections)");
     DECNET_REQUIRE(!split || np <= 128, "split (3xTF32) mode accumulates in registers: np=%d must be <= 128", np);
     DECNET_REQUIRE(ldc >= np && ldc % 4 == 0, "ldc=%d must be a multiple of 4 and >= np=%d", ldc, np);
     DECNET_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15u) == 0 &&
@@ -677,11 +830,13 @@ static int launch_nhwc(const float *x, const float *w_packed, const float *bias,
     Params p{};
     p.bias = bias; p.out = out; p.B = B; p.h = h; p.w = w; p.cp = cp; p.np = np;
     p.taps = taps; p.border = border; p.ldc = ldc; p.dst_h = dst_h; p.dst_w = dst_w;
+    p.dbg = g_halo_variant >= 100 ? g_halo_variant - 100 : 0;
+    p.trace = g_halo_trace;
     p.nchunks = (cp + 31) / 32;
     p.last_ksteps = (cp - (p.nchunks - 1) * 32) / 8;
     p.P = P;
     DECNET_REQUIRE(p.P + 2ll * (w + 3) < (1ll << 31), "tensor too large for 32-bit TMA coordinates");
-    p.relu = relu; p.round_tf32 = round_out_tf32; p.split = split ? 1 : 0;
+    p.relu = relu; p.round_tf32 = round_out_tf32; p.split = split;
     p.tmem_cols = np <= 16 ? 32 : np <= 32 ? 64 : np <= 64 ? 128 : np <= 128 ? 256 : 512;
     if (p.split) p.tmem_cols *= 2;                                  // two chain slots + two small-term slots
     p.num_tiles = (int)((p.P + kTileM - 1) / kTileM);
@@ -751,6 +906,8 @@ static int launch_nhwc(const float *x, const float *w_packed, const float *bias,
 
 // 0 / 1 = the one-tile-per-CTA kernel (default); 2 = pair kernel for 3xTF32 launches with >= 2 tiles per SM and np <= 96.  Per thread.
 void decnet_conv2d_nhwc_set_variant(int variant) { g_halo_variant = variant; }
+// tuning only: device buffer of 2560 int64 that CTA 0 of the following launches fills with its clock64 timeline, or null.  Per thread.
+void decnet_conv2d_nhwc_debug_trace(void *buffer) { g_halo_trace = static_cast<long long *>(buffer); }
 
 int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream)

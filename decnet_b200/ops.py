@@ -3,6 +3,9 @@ the current CUDA stream.  PyTorch is plumbing here (memory + streams), not the p
 """
 from __future__ import annotations
 
+import math
+import os
+
 import torch
 
 from . import _lib
@@ -480,17 +483,59 @@ def split_tf32(t):
     return hi, rna_tf32(t - hi)
 
 
+# How the channels-last tensor-core kernel (conv2d_nhwc_tcgen05.cu) builds an fp32-class product, the `split` argument of
+# its entry points: 1 = 3xTF32 (hi*hi + lo*hi + hi*lo, all kind::tf32), 2 = hi*hi in TF32 + both correction terms as ONE
+# K-concatenated fp16 MMA ([lo16(x) | fp16(x)] * [hi16(w) ; lo16(w)]): a third fewer operand bytes through shared memory.
+# The TF32 hi / lo parts have 11 significant bits, so fp16 holds them exactly once a per-layer power of two brings the weights
+# into its exponent range; DECNET_SPLIT_KIND=1 selects the all-TF32 form (A/B measurements).
+SPLIT_KIND = int(os.environ.get("DECNET_SPLIT_KIND", "2"))
+if SPLIT_KIND not in (1, 2):
+    raise ValueError("DECNET_SPLIT_KIND must be 1 or 2")
+
+
+def _split_arg(split):
+    return SPLIT_KIND if split else 0
+
+
+def _pack_split_weights(out, bias_np):
+    """out fp32 [T][NP][cp] -> ([2T][NP][cp] for the split modes of the channels-last kernel, bias [NP + 4]).
+    Taps 0..T-1: the TF32 hi parts.  Taps T..2T-1, SPLIT_KIND 1: the TF32 lo parts; SPLIT_KIND 2: per 32-channel chunk of cl
+    channels the 4*cl bytes [fp16(hi * 2^sw) x cl | fp16(lo * 2^(11+sw)) x cl] -- the B operand of the fp16 correction MMA,
+    whose A operand is [fp16(2^11 * lo(x)) | fp16(x)]; both products carry the factor 2^(11+sw), and bias[NP] = 2^-(11+sw) is
+    what the epilogue multiplies the correction accumulator with.  sw puts the largest weight just below 2^13."""
+    hi, lo = split_tf32(out)
+    b = torch.zeros(bias_np.numel() + 4, dtype=torch.float32, device=out.device)
+    b[:bias_np.numel()] = bias_np
+    if SPLIT_KIND == 1:
+        b[bias_np.numel()] = 1.0
+        return torch.cat((hi, lo), 0).contiguous(), b
+    T, np_, cp = out.shape
+    m = float(hi.abs().max())
+    sw = max(-40, min(40, 13 - math.frexp(m)[1])) if m > 0 and math.isfinite(m) else 0
+    wh = (hi * 2.0 ** sw).clamp(-65504.0, 65504.0).to(torch.float16)
+    wl = (lo * 2.0 ** (11 + sw)).clamp(-65504.0, 65504.0).to(torch.float16)
+    b2 = torch.zeros((T, np_, 2 * cp), dtype=torch.float16, device=out.device)
+    for c0 in range(0, cp, 32):
+        cl = min(32, cp - c0)
+        b2[:, :, 2 * c0:2 * c0 + cl] = wh[:, :, c0:c0 + cl]
+        b2[:, :, 2 * c0 + cl:2 * c0 + 2 * cl] = wl[:, :, c0:c0 + cl]
+    b[bias_np.numel()] = 2.0 ** -(11 + sw)
+    return torch.cat((hi, b2.view(torch.float32)), 0).contiguous(), b
+
+
 def pack_conv2d_tf32_weights(w, bias, cp, split=False):
     """[Cout,Cin,3,3] (+ bias [Cout]) -> ([9][NP][cp] fp32, bias [NP]); NP = Cout rounded up to 16.
-    split: [18][NP][cp] -- taps 0-8 the TF32 hi parts, 9-17 the lo parts (3xTF32 mode of the halo kernel)."""
+    split: [18][NP][cp] -- taps 0-8 the TF32 hi parts, 9-17 the correction operand (_pack_split_weights), bias [NP + 4]."""
     cout, cin = w.shape[:2]
     np_ = (cout + 15) // 16 * 16
     out = torch.zeros((9, np_, cp), dtype=torch.float32, device=w.device)
     out[:, :cout, :cin] = w.float().permute(2, 3, 0, 1).reshape(9, cout, cin)
-    out = torch.cat(split_tf32(out), 0) if split else rna_tf32(out)
     b = torch.zeros(np_, dtype=torch.float32, device=w.device)
     b[:cout] = bias.float()
-    return out.contiguous(), b.contiguous(), np_
+    if split:
+        out, b = _pack_split_weights(out, b)
+        return out, b, np_
+    return rna_tf32(out).contiguous(), b.contiguous(), np_
 
 
 def conv2d_tf32_nhwc(x_nhwc, w_packed, bias, relu, round_out=False):
@@ -635,7 +680,7 @@ def conv2d_tf32_nhwc_halo(x_pad, w_packed, bias, relu, round_out=False, split=Fa
         raise ValueError(f"w_packed {tuple(w_packed.shape)} does not match cp={cp}, split={split}")
     out = torch.empty((B, hp, wp, np_), dtype=torch.float32, device=x_pad.device)
     _call("decnet_conv2d_tc_nhwc_halo", x_pad, x_pad.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(),
-          B, hp - 2, wp - 2, cp, np_, 1 if relu else 0, 1 if round_out else 0, 1 if split else 0)
+          B, hp - 2, wp - 2, cp, np_, 1 if relu else 0, 1 if round_out else 0, _split_arg(split))
     return out
 
 
@@ -726,10 +771,12 @@ def pack_gemm_weights(w2d, bias, cp, split=False, n0=0, n1=None):
     np_ = (n + 15) // 16 * 16
     out = torch.zeros((1, np_, cp), dtype=torch.float32, device=w2d.device)
     out[0, :n, :k] = w2d[n0:n1].float()
-    out = torch.cat(split_tf32(out), 0) if split else rna_tf32(out)
     b = torch.zeros(np_, dtype=torch.float32, device=w2d.device)
     b[:n] = bias[n0:n1].float()
-    return out.contiguous(), b.contiguous(), np_
+    if split:
+        out, b = _pack_split_weights(out, b)
+        return out, b, np_
+    return rna_tf32(out).contiguous(), b.contiguous(), np_
 
 
 def gemm_tc(x, w_packed, bias, out, relu, split=False, col=0, border=None, dst_hw=None):
@@ -751,7 +798,7 @@ def gemm_tc(x, w_packed, bias, out, relu, split=False, col=0, border=None, dst_h
     if rows_out != want:
         raise ValueError(f"out has {rows_out} rows, expected {want}")
     _call("decnet_gemm_tc_nhwc", x, x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr() + 4 * col, P, cp, np_, ldc,
-          1 if relu else 0, 1 if split else 0, bB, bh, bw, dh, dw)
+          1 if relu else 0, _split_arg(split), bB, bh, bw, dh, dw)
     return out
 
 
@@ -764,7 +811,7 @@ def conv2d_nhwc_halo_into(x_pad, w_packed, bias, out_pad, relu, split=False, col
     if tuple(out_pad.shape[:3]) != (B, hp, wp) or col % 4 or col + np_ > ldc:
         raise ValueError(f"out_pad {tuple(out_pad.shape)} / col {col} do not fit x_pad {tuple(x_pad.shape)}, NP {np_}")
     _call("decnet_conv2d_tc_nhwc_halo_ldc", x_pad, x_pad.data_ptr(), w_packed.data_ptr(), bias.data_ptr(),
-          out_pad.data_ptr() + 4 * col, B, hp - 2, wp - 2, cp, np_, ldc, 1 if relu else 0, 1 if split else 0)
+          out_pad.data_ptr() + 4 * col, B, hp - 2, wp - 2, cp, np_, ldc, 1 if relu else 0, _split_arg(split))
     return out_pad
 
 

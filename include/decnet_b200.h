@@ -314,6 +314,7 @@ int decnet_nhwc_pad_to_nchw(const float *in_pad, float *out, int B, int C, int N
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */
+void decnet_conv2d_nhwc_debug_trace(void *buffer);   /* tuning only: clock64 timeline of CTA 0 of conv2d_nhwc_halo_kernel (2560 int64), or NULL */
 void decnet_conv3d_debug_timing(void *dbg_buffer);
 /* 0 = auto (single-CTA kernel), 1 = force single-CTA, 2 = CTA-pair kernel (tcgen05 cta_group::2,
  * correct but slower in round 1; kept for tuning).  Per calling thread. */
