@@ -147,6 +147,44 @@ __device__ __forceinline__ void umma_tf32_kh3_split(uint32_t tmem_d, uint64_t da
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first)
         : "memory");
 }
+// split = 2: per row tap ONE kind::f16 MMA [lo16(x) | fp16(x)] * [hi16(w) ; lo16(w)] (both correction terms, K = 16) and the
+// kind::tf32 hi(x)*hi(w).  The fp16 operands sit where the TF32 lo parts would (same 1 KB blocks, same LBO / SBO), in the
+// MN-major SWIZZLE_64B layout (scripts/micro/umma_f16_mn.cu): their descriptors are the lo descriptors with the layout type
+// 1 -> 4 (+3 at bit 61).  idesc16: the kind::f16 instruction descriptor.
+__device__ __forceinline__ void umma_kh3_split16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t a_step, uint32_t b_step,
+                                                 uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t idesc16,
+                                                 uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a, b, al, bl, sa, sb, la, lb;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %9, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "cvt.u64.u32 sa, %3;\n\t"
+        "cvt.u64.u32 sb, %4;\n\t"
+        "cvt.u64.u32 la, %5;\n\t"
+        "cvt.u64.u32 lb, %6;\n\t"
+        "add.u64 al, %1, la;\n\t"
+        "add.u64 bl, %2, lb;\n\t"
+        "add.u64 al, al, 0x6000000000000000;\n\t"
+        "add.u64 bl, bl, 0x6000000000000000;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bl, %8, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %7, t;\n\t"
+        "add.u64 a, %1, sa;\n\t"
+        "add.u64 b, %2, sb;\n\t"
+        "add.u64 al, al, sa;\n\t"
+        "add.u64 bl, bl, sb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bl, %8, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %7, t;\n\t"
+        "add.u64 a, a, sa;\n\t"
+        "add.u64 b, b, sb;\n\t"
+        "add.u64 al, al, sa;\n\t"
+        "add.u64 bl, bl, sb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al, bl, %8, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %7, t;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(idesc16),
+          "r"(accumulate_first)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -192,6 +230,10 @@ __device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, u
     const int G = (p.dbg & 2) ? 0 : p.G, CP = p.CP, N = p.N;
     const size_t gstride = (size_t)4 * p.W;
     const float floor_ = p.relu ? 0.f : -INFINITY;            // ReLU as an unconditional max
+    // split = 2: every product carries the weights' power-of-two scale 2^(11+sw) (ops.pack_conv2d_tf32_nchw_weights); its inverse
+    // sits behind the bias
+    const bool scaled = p.split == 2;
+    const float inv_s = scaled ? bias_s[p.CP] : 1.f;
     // tile cursor without divisions: (tx, ty, b) advance by gridDim.x tiles
     int tx, ty, tb;
     { int t = blockIdx.x; tx = t % p.tw; t /= p.tw; ty = t % p.th; tb = t / p.th; }
@@ -227,7 +269,9 @@ __device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, u
                 for (int i = 0; i < 4; ++i) {
                     const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[0][i4 + i]), d);
                     const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v[2][i4 + i]), d);
-                    x[i4 + i] = keep ? fmaxf((left + __uint_as_float(v[1][i4 + i])) + (right + bb[i]), floor_) : 0.f;
+                    const float mid = __uint_as_float(v[1][i4 + i]);
+                    const float y = scaled ? fmaf((left + mid) + right, inv_s, bb[i]) : (left + mid) + (right + bb[i]);
+                    x[i4 + i] = keep ? fmaxf(y, floor_) : 0.f;
                 }
             }
             if (col_ok && 4 * g < rows_left) {
@@ -269,12 +313,12 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float bias_s[96];
+    __shared__ __align__(16) float bias_s[100];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *base = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    if (threadIdx.x < p.CP) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+    if (threadIdx.x < p.CP + (p.split == 2 ? 1 : 0)) bias_s[threadIdx.x] = p.bias[threadIdx.x];
     unsigned char *wsm = base;                                   // resident weights
     unsigned char *ring = base + p.w_bytes;                      // stages
     const int tile_bytes = p.RH * kRowBlock;                     // what TMA delivers per stage
@@ -330,6 +374,8 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_tf32_mn(p.N);
+        // kind::f16: a/b format F16 (0), both MN-major, fp32 accumulate
+        const uint32_t idesc16 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.N >> 3) << 17) | (8u << 24);
         const uint32_t ring_base = smem_u32(ring);
         const uint32_t w_base = smem_u32(wsm);
         const uint32_t empty_base = smem_u32(&empty_bar[0]);
@@ -356,7 +402,12 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 const uint64_t db0 = make_desc_mn(w_base + (uint32_t)(ck * p.natoms * kRowBlock));
                 const uint32_t accum = ck != 0 ? 1u : 0u;
                 const int Gn = (p.dbg & 4) ? 0 : p.G;
-                if (p.split) {
+                if (p.split == 2) {
+#pragma unroll 1
+                    for (int g = 0; g < Gn; ++g)
+                        umma_kh3_split16(acc + (uint32_t)(g * p.N), da0 + (uint64_t)(g * (4 * kRowBlock >> 4)), db0, a_step, b_step,
+                                         a_lo, b_lo, idesc, idesc16, accum);
+                } else if (p.split) {
 #pragma unroll 1
                     for (int g = 0; g < Gn; ++g)
                         umma_tf32_kh3_split(acc + (uint32_t)(g * p.N), da0 + (uint64_t)(g * (4 * kRowBlock >> 4)), db0, a_step, b_step,
@@ -383,7 +434,37 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 mbar_wait(&full_bar[s], ph);
                 prof_acc[0] += clock64() - tq0;
                 uint4 *st = reinterpret_cast<uint4 *>(ring + (size_t)s * stage_bytes);
-                if (p.split) {
+                if (p.split == 2) {
+                    // fp16 correction operand beside the raw tile, one image row (1 KB) per warp instruction: lane = (channel c,
+                    // pixel octet u).  Raw row: [8 ch][32 px] fp32, the 32-byte unit u of channel c at unit u ^ (c & 3)
+                    // (TMA's SWIZZLE_128B_ATOM_32B); fp16 row: K atom 0 = 2^11 * lo(x), K atom 1 = fp16(x), each [8 ch][32 px]
+                    // halves, the 16-byte unit u of channel c at unit u ^ ((c >> 1) & 3) (SWIZZLE_64B).  The two 16-byte
+                    // halves of the 32-byte read are taken in the order (c & 1, c & 1 ^ 1), which keeps a quarter warp's
+                    // two channels on different banks; batches of three rows, loads before stores.
+                    const int c = lane >> 2, u = lane & 3, h0 = (c & 1) << 4;
+                    const unsigned char *raw = reinterpret_cast<const unsigned char *>(st) + c * 128 + ((u ^ (c & 3)) << 5);
+                    unsigned char *a2 = reinterpret_cast<unsigned char *>(st) + p.lo_off + c * 64 + ((u ^ ((c >> 1) & 3)) << 4);
+                    const int cw = warp - 2;
+                    for (int r0 = cw; r0 < p.RH; r0 += 3 * kConvWarps) {
+                        uint4 va[3], vb[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (r0 + k * kConvWarps < p.RH) {
+                                va[k] = *reinterpret_cast<const uint4 *>(raw + (r0 + k * kConvWarps) * kRowBlock + h0);
+                                vb[k] = *reinterpret_cast<const uint4 *>(raw + (r0 + k * kConvWarps) * kRowBlock + (h0 ^ 16));
+                            }
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (r0 + k * kConvWarps < p.RH) {
+                                const uint4 v0 = h0 ? vb[k] : va[k], v1 = h0 ? va[k] : vb[k];    // pixels 0-3, 4-7 of the octet
+                                uint4 l, h;
+                                l.x = lo16x2(v0.x, v0.y); l.y = lo16x2(v0.z, v0.w); l.z = lo16x2(v1.x, v1.y); l.w = lo16x2(v1.z, v1.w);
+                                h.x = hi16x2(v0.x, v0.y); h.y = hi16x2(v0.z, v0.w); h.z = hi16x2(v1.x, v1.y); h.w = hi16x2(v1.z, v1.w);
+                                *reinterpret_cast<uint4 *>(a2 + (r0 + k * kConvWarps) * kRowBlock) = l;
+                                *reinterpret_cast<uint4 *>(a2 + (r0 + k * kConvWarps) * kRowBlock + 512) = h;
+                            }
+                    }
+                } else if (p.split) {
                     // hi in place, lo = rna(x - hi) (the difference is exact in fp32) at the same swizzled offset of the lo tile
                     uint4 *sl = reinterpret_cast<uint4 *>(ring + (size_t)s * stage_bytes + p.lo_off);
 #pragma unroll 4
@@ -434,7 +515,8 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // Shape support and tile plan (host).  Returns false when the layer does not fit this kernel.
 static bool plan(int Cin, int Cout, int H, int W, int dil, int B, int split, Params &p, size_t &smem)
 {
-    p.split = split ? 1 : 0;
+    if (split < 0 || split > 2) return false;
+    p.split = split;
     if (Cin < 1 || Cout < 1 || dil < 1 || dil > 12 || (W & 3) != 0) return false;   // TMA strides: multiples of 16 B
     p.nck = (Cin + 7) / 8;
     p.CP = Cout <= 4 ? 4 : (Cout + 7) / 8 * 8;

@@ -510,8 +510,7 @@ def _pack_split_weights(out, bias_np):
         b[bias_np.numel()] = 1.0
         return torch.cat((hi, lo), 0).contiguous(), b
     T, np_, cp = out.shape
-    m = float(hi.abs().max())
-    sw = max(-40, min(40, 13 - math.frexp(m)[1])) if m > 0 and math.isfinite(m) else 0
+    sw = _weight_scale_exp(hi)
     wh = (hi * 2.0 ** sw).clamp(-65504.0, 65504.0).to(torch.float16)
     wl = (lo * 2.0 ** (11 + sw)).clamp(-65504.0, 65504.0).to(torch.float16)
     b2 = torch.zeros((T, np_, 2 * cp), dtype=torch.float16, device=out.device)
@@ -553,7 +552,7 @@ def conv2d_tf32_nhwc(x_nhwc, w_packed, bias, relu, round_out=False):
 # small 3x3 Conv2d on NCHW fp32 tensors, TF32 tensor cores with pixels as the MN-major M dimension
 # --------------------------------------------------------------------------------------
 def conv2d_tf32_supported(cin, cout, H, W, dilation=1, split=False):
-    return bool(_lib.lib().decnet_conv2d_tc_supported(int(cin), int(cout), int(H), int(W), int(dilation), 1 if split else 0))
+    return bool(_lib.lib().decnet_conv2d_tc_supported(int(cin), int(cout), int(H), int(W), int(dilation), _split_arg(split)))
 
 
 def padded_cat_channels(src_channels):
@@ -584,11 +583,44 @@ def pack_conv2d_tf32_nchw_weights(w, bias, src_channels=None, split=False):
         bm[:, :cin, kw * cp: kw * cp + cout] = wf[:, :, :, kw].permute(2, 1, 0)       # [kh][ci][co]
     # -> [kh][chunk][atom][k][n]
     out = bm.view(3, nck, 8, natoms, 32).permute(0, 1, 3, 2, 4).contiguous()
-    out = torch.cat(split_tf32(out), 0) if split else rna_tf32(out)                   # cvt.rna to TF32
-    assert out.numel() == _lib.lib().decnet_conv2d_tc_packed_floats(int(cin), int(cout), 1 if split else 0)
-    b = torch.zeros(cp, dtype=torch.float32, device=w.device)
+    b = torch.zeros(cp + (4 if split else 0), dtype=torch.float32, device=w.device)
     b[:cout] = bias.float()
+    if not split:
+        out = rna_tf32(out)                                                            # cvt.rna to TF32
+    elif SPLIT_KIND == 1:
+        out = torch.cat(split_tf32(out), 0)
+        b[cp] = 1.0
+    else:
+        out, b[cp] = _pack_nchw_split16(out)
+    assert out.numel() == _lib.lib().decnet_conv2d_tc_packed_floats(int(cin), int(cout), _split_arg(split))
     return out.contiguous(), b.contiguous()
+
+
+def _weight_scale_exp(hi):
+    """sw with max|hi| * 2^sw just below 2^13: brings the weights into fp16's exponent range with room on both sides."""
+    m = float(hi.abs().max())
+    return max(-40, min(40, 13 - math.frexp(m)[1])) if m > 0 and math.isfinite(m) else 0
+
+
+def _pack_nchw_split16(blocks):
+    """blocks fp32 [kh][chunk][atom][8 k][32 n] -> (hi rows then fp16 correction rows, 2^-(11+sw)): split kind 2 of the thin
+    NCHW kernel.  All three products of a pixel carry the factor S = 2^(11+sw): the TF32 hi rows hold hi(w) * S, and each 1 KB
+    block of the second half is the MN-major SWIZZLE_64B fp16 operand [K atom 0: fp16(hi(w) * 2^sw) | K atom 1: fp16(lo(w) * S)],
+    8 k x 32 n halves each, that meets [fp16(2^11 * lo(x)) | fp16(x)].  The rows are loaded by the same TMA map as the fp32
+    rows (SWIZZLE_128B_ATOM_32B: 32-byte unit ^= bits 7-8 of the address), so the 16-byte units of a block are stored
+    pre-permuted: unit g of the global block holds logical unit s64(s128a32(g)), s64 = 16-byte unit ^= bits 7-8."""
+    hi, lo = split_tf32(blocks)
+    sw = _weight_scale_exp(hi)
+    wh = (hi * 2.0 ** sw).clamp(-65504.0, 65504.0).to(torch.float16)
+    wl = (lo * 2.0 ** (11 + sw)).clamp(-65504.0, 65504.0).to(torch.float16)
+    kh, nck, natoms = blocks.shape[:3]
+    logical = torch.stack((wh, wl), 3).contiguous()                                    # [kh][chunk][atom][2][8 k][32 n] halves
+    units = logical.view(kh, nck, natoms, 64, 8)                                       # 64 sixteen-byte units per 1 KB block
+    g = torch.arange(64, device=blocks.device)
+    s1 = g ^ (((g >> 3) & 3) << 1)                                                     # s128a32: unit bits 1-2 ^= bits 3-4
+    perm = s1 ^ ((s1 >> 3) & 3)                                                        # s64: unit bits 0-1 ^= bits 3-4
+    packed = units[:, :, :, perm, :].contiguous().view(torch.float32).view(kh, nck, natoms, 8, 32)
+    return torch.cat((hi * 2.0 ** (11 + sw), packed), 0), 2.0 ** -(11 + sw)
 
 
 def conv2d_tf32_nchw(x, w_packed, bias_padded, cout, dilation=1, relu=False):
@@ -620,7 +652,7 @@ def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=Fal
     out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x0.device)
     _call("decnet_conv2d_tc_nchw_cat", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
           w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(), B, int(cout), H, W, int(dilation), 1 if relu else 0,
-          int(w_valid), 1 if split else 0)
+          int(w_valid), _split_arg(split))
     return out
 
 
