@@ -510,7 +510,7 @@ def leg_conv2d_roofline(args, env, left, pk):
         e1.record(); torch.cuda.synchronize()
         t_c = e0.elapsed_time(e1) * 1e-3 / 20
         alg_c = 4.0 * Bq * Hq * Wq * (Cq + 8)
-        out = {"bound": "hbm", "kernel": f"conv2d_tcgen05_kernel (3x3, 8->8 channels, finest level, {'3xTF32' if split else 'TF32'})",
+        out = {"bound": "hbm", "kernel": f"conv2d_tcgen05_kernel (3x3, 8->8 channels, finest level, {'hi/lo split, fp32-class' if split else 'TF32'})",
                "achieved": alg_c / t_c / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg_c / t_c / 1e9 / pk["hbm_gbs"],
                "traffic": None, "algorithmic_bytes": alg_c, "us_per_launch": t_c * 1e6}
         tr = ROOT / "profiles" / "traffic.json"
@@ -798,7 +798,8 @@ def run_ours(args):
 
     line = bands = None
     if rank == 0:
-        conv_dtype = "3xTF32 (hi/lo split, fp32-class) in / f32 acc" if args.precision == "fp32" else "tf32 in / f32 acc"
+        conv_dtype = ("hi/lo operand split (TF32 hi*hi + fp16 corrections, fp32-class) in / f32 acc" if args.precision == "fp32"
+                      else "tf32 in / f32 acc")
         line = {"metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if bands_mode else "weak", "vs_baseline": None,

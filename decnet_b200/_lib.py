@@ -59,6 +59,7 @@ SIGNATURES = {
     "decnet_nhwc_pad_to_nchw": (_i, [_f32p] * 2 + [_i] * 5 + [C.c_void_p]),
     "decnet_conv3d_debug_timing": (None, [C.c_void_p]),
     "decnet_conv2d_nhwc_debug_trace": (None, [C.c_void_p]),
+    "decnet_conv2d_tf32_debug": (None, [_i, C.c_void_p]),
     "decnet_conv3d_set_variant": (None, [_i]),
     "decnet_softargmin": (_i, [_f32p] * 2 + [_i] * 4 + [C.c_void_p]),
     "decnet_mask_threshold": (_i, [_f32p] * 2 + [C.c_float] + [_f32p] * 4 + [_i] * 3 + [C.c_void_p]),

@@ -27,6 +27,13 @@
 // (its values, and so its truncation steps, are 2^-11 of the big one's) and is added last; the registers are biased,
 // activated and stored once per tile.  NP <= 128 (4 x NP TMEM columns).
 //
+// split = 2 (the default of the Python side): the two small terms as ONE kind::f16 MMA per column tap and K-step: the converters
+// write [fp16(2^11 * lo(x)) x cl | fp16(x) x cl] (cl = channels of the chunk, 4 bytes per channel like the fp32 tile) beside the
+// raw tile, taps 9-17 of the weights hold [fp16(hi(w) * 2^sw) x cl | fp16(lo(w) * 2^(11+sw)) x cl] per row, and the small-term
+// accumulator is drained with the factor 2^-(11+sw) (bias[np]).  24 MMAs per stage instead of 36.  In the split modes the
+// activation tile completes its own mbarrier, so the converters start while the (4x larger) weight part of the stage is still in
+// flight.
+//
 // Warp roles as in conv3d_tcgen05.cu: 0 TMA producer, 1 MMA issuer, 2-5 epilogue, 6-9 converters (split mode only);
 // persistent CTAs, two TMEM slots.
 #include "common.cuh"

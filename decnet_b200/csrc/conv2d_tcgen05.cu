@@ -33,6 +33,11 @@
 //     the same accumulator: lo*hi + hi*lo + hi*hi.  The dropped lo*lo term and the rounding of the lo parts are
 //     ~2^-22 relative, so the result is fp32-class (the parity gates of tests/test_glue_gpu.py run on this mode);
 //     the kernel is bound by its epilogue, so the extra MMAs on K = 8 are nearly free.
+//   * split = 2 (the default of the Python side): the two correction products as ONE kind::f16 MMA per tap.  The converters
+//     write the fp16 operand [fp16(2^11 * lo(x)) | fp16(x)] (K = 16: 8 + 8 channels) into the second half of the stage in the
+//     MN-major SWIZZLE_64B layout, the second half of the weights holds [fp16(hi(w) * 2^sw) ; fp16(lo(w) * 2^(11+sw))], the TF32
+//     weights are hi(w) * 2^(11+sw), and the epilogue multiplies the accumulator by 2^-(11+sw) (bias[CP]): two MMAs per tap, a
+//     third fewer operand bytes through shared memory, the same error budget.
 //
 // Warp roles (704 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-5 = converters,
 // 6-21 = epilogue.  Persistent CTAs, smem ring of RH-KB stages, two TMEM accumulator slots, the
@@ -445,7 +450,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     const unsigned char *raw = reinterpret_cast<const unsigned char *>(st) + c * 128 + ((u ^ (c & 3)) << 5);
                     unsigned char *a2 = reinterpret_cast<unsigned char *>(st) + p.lo_off + c * 64 + ((u ^ ((c >> 1) & 3)) << 4);
                     const int cw = warp - 2;
-                    for (int r0 = cw; r0 < p.RH; r0 += 3 * kConvWarps) {
+                    for (int r0 = cw; r0 < ((p.dbg & 1) ? 0 : p.RH); r0 += 3 * kConvWarps) {
                         uint4 va[3], vb[3];
 #pragma unroll
                         for (int k = 0; k < 3; ++k)

@@ -233,8 +233,17 @@ int decnet_conv2d_tf32_nchw_cat(const float *const *srcs, const int *src_channel
  *   split = 1: error-compensated "3xTF32": both operands are split into TF32 hi + lo parts (x: in the kernel; weights:
  *              by the caller, w_packed = the hi rows followed by the lo rows, 2x decnet_conv2d_tf32_packed_floats values)
  *              and every tap issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator.  The result is fp32-class
- *              (~2^-22 relative per product): the mode on which the 1e-3 parity gates against the reference's fp32
- *              execution run (the layers the reference computes with F.conv2d: modules/submodule.py:15-49). */
+ *              (~2^-22 relative per product).
+ *   split = 2: the same hi/lo decomposition with the two correction products as ONE kind::f16 MMA per tap (the default of
+ *              the Python side): the kernel writes [fp16(2^11 * lo(x)) | fp16(x)] (8 + 8 channels) beside the raw tile, the
+ *              second half of w_packed holds, per 1 KB block [kh][chunk][n-atom], the MN-major SWIZZLE_64B fp16 operand
+ *              [K atom 0: fp16(hi(w) * 2^sw) | K atom 1: fp16(lo(w) * 2^(11+sw))] (8 k x 32 n halves each; its 16-byte units
+ *              pre-permuted for the 128B_ATOM_32B TMA map: unit g holds logical unit s64(s128a32(g))), the first half holds
+ *              hi(w) * 2^(11+sw), and bias_padded[CP] = 2^-(11+sw) (bias_padded has CP + 4 floats).  sw: any integer that keeps
+ *              |w| * 2^sw below 2^15 (decnet_b200/ops.py: _pack_nchw_split16).  Same error budget as split = 1, two MMAs per
+ *              tap instead of three.
+ * The split modes are those on which the 1e-3 parity gates against the reference's fp32 execution run (the layers the
+ * reference computes with F.conv2d: modules/submodule.py:15-49). */
 int decnet_conv2d_tc_supported(int Cin, int Cout, int H, int W, int dilation, int split);
 int decnet_conv2d_tc_packed_floats(int Cin, int Cout, int split);
 int decnet_conv2d_tc_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
@@ -261,13 +270,19 @@ int decnet_conv2d_tf32_nhwc_halo(const float *x_pad, const float *w_packed, cons
 
 /* split = 1: 3xTF32 mode of the same kernel (see decnet_conv2d_tc_nchw_cat): x_pad is plain fp32 (NOT pre-rounded; four
  * converter warps split it into hi + lo tiles in shared memory), w_packed is [18][np][cp] (taps 0-8 the TF32 hi parts of
- * the weights, 9-17 the lo parts), round_out_tf32 should be 0. */
+ * the weights, 9-17 the lo parts), round_out_tf32 should be 0.
+ * split = 2 (default of the Python side): the corrections as one K-concatenated kind::f16 MMA per column tap.  Taps 9-17 of
+ * w_packed hold, per output channel row and 32-channel chunk of cl channels, the 4*cl bytes
+ * [fp16(hi(w) * 2^sw) x cl | fp16(lo(w) * 2^(11+sw)) x cl]; the kernel builds [fp16(2^11 * lo(x)) x cl | fp16(x) x cl]; taps
+ * 0-8 are the plain TF32 hi parts; bias has np + 4 floats and bias[np] = 2^-(11+sw), the factor of the correction accumulator
+ * (decnet_b200/ops.py: _pack_split_weights).  np <= 96 for the 3x3 form in the split modes (two stages must fit in shared memory).
+ * The same holds for the _ldc form and for decnet_gemm_tc_nhwc (taps 0 / 1 instead of 0-8 / 9-17). */
 int decnet_conv2d_tc_nhwc_halo(const float *x_pad, const float *w_packed, const float *bias, float *out_pad,
                                int B, int h, int w, int cp, int np, int relu, int round_out_tf32, int split, void *stream);
 
-/* Tuning switch (per calling thread): 0 / 1 = one 128-pixel tile per CTA (default); 2 = 3xTF32 launches with at least two tiles
- * per SM and np <= 96 run the pair kernel (two tiles per CTA share every weight stage: 1.7x fewer bytes from L2 per MMA; exact,
- * measured slower -- the kernel is bound by shared-memory bandwidth, not by L2: DESIGN.md section 3.4). */
+/* Tuning switch (per calling thread): 0 / 1 = one 128-pixel tile per CTA (default); 2 = split-mode launches with at least two
+ * tiles per SM and np <= 96 run the pair kernel (two tiles per CTA share every weight stage: 1.7x fewer bytes from L2 per MMA;
+ * bit-identical, not faster at the product shapes: DESIGN.md section 3.4); 100 + mask = knock-out timing (results wrong). */
 void decnet_conv2d_nhwc_set_variant(int variant);
 
 /* The same kernel writing a channel slice of a wider bordered tensor (row stride ldc floats, np channels from out_pad). */
@@ -277,7 +292,8 @@ int decnet_conv2d_tc_nhwc_halo_ldc(const float *x_pad, const float *w_packed, co
 /* GEMM mode of the same kernel (one tap): out[p, 0..np) = act(bias + sum_k x[p, k] * w[n, k]) over P rows of cp channels --
  * the 1x1 convs of the feature extractor, and (behind decnet_im2col3x3) its stride-3, dilated and 1/27-resolution 3x3 convs
  * and the GEMM form of its 216 -> 72 transposed conv (modules/submodule.py:225-241, 272-286, 162-177).
- *   x fp32 [P, cp] (cp multiple of 8, rows 16-byte aligned), w_packed fp32 [1 or 2 (split: hi, lo)][np][cp], bias [np],
+ *   x fp32 [P, cp] (cp multiple of 8, rows 16-byte aligned), w_packed fp32 [1 or 2 (split: hi, then lo / fp16 rows)][np][cp],
+ *   bias [np] (split = 2: [np + 4], see decnet_conv2d_tc_nhwc_halo),
  *   out rows of ldc floats (np <= ldc: writes a channel slice of a wider tensor; np <= 128 in split mode).
  *   border_B > 0: the rows are the pixels of a zero-bordered [border_B, border_h+2, border_w+2] tensor; border rows are
  *                 stored as zeros (same pixel index in and out).
@@ -314,6 +330,7 @@ int decnet_nhwc_pad_to_nchw(const float *in_pad, float *out, int B, int C, int N
 /* Profiling hook: when set to a device buffer of 4*SMs int64, every conv3d launch on this thread
  * records per CTA {issuer cycles, cycles blocked on operand barriers, elapsed ns, k-iterations};
  * pass NULL to disable (default). */
+void decnet_conv2d_tf32_debug(int flags, void *prof16);   /* tuning only: knock-out mask (1 converters idle, 2 no epilogue, 4 no MMAs) and per-role wait cycles of CTA 0 of conv2d_tcgen05_kernel (16 int64), or NULL */
 void decnet_conv2d_nhwc_debug_trace(void *buffer);   /* tuning only: clock64 timeline of CTA 0 of conv2d_nhwc_halo_kernel (2560 int64), or NULL */
 void decnet_conv3d_debug_timing(void *dbg_buffer);
 /* 0 = auto (single-CTA kernel), 1 = force single-CTA, 2 = CTA-pair kernel (tcgen05 cta_group::2,

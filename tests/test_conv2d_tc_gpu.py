@@ -87,6 +87,45 @@ def test_conv2d_3xtf32_nchw_is_fp32_class(B, Cin, Cout, H, W, dil, relu):
     assert err <= 1e-5 * max(1.0, want.abs().max().item()), ("3xTF32", err, want.abs().max().item())
 
 
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("xs,ws", [(1.0, 1.0), (300.0, 1e-3), (1e-3, 30.0), (3e3, 1e-4), (1e-5, 1.0)])
+def test_conv2d_split_kinds_and_operand_ranges(kind, xs, ws, monkeypatch):
+    """Both fp32-class forms of the thin kernel (1: three TF32 MMAs per tap; 2, the default: TF32 hi*hi + one fp16 correction MMA)
+    on operands of very different magnitudes, and weights whose channels differ by 2^12: the fp16 correction operand is scaled by a
+    per-layer power of two, so large / small weights and activations keep the fp32-class error (relative to the output scale)."""
+    from decnet_b200 import ops
+    monkeypatch.setattr(ops, "SPLIT_KIND", kind)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    B, srcs, Cout, H, W, dil = 2, [8, 8, 1], 8, 64, 96, 2
+    x = [torch.randn(B, c, H, W, device="cuda", generator=g) * xs for c in srcs]
+    w = torch.randn(Cout, sum(srcs), 3, 3, device="cuda", generator=g) * (2.0 / (9 * sum(srcs))) ** 0.5 * ws
+    w[::2] *= 2.0 ** -12                                              # wide dynamic range between output channels
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1 * xs * ws
+    b[::2] *= 2.0 ** -12
+    wp, bp = ops.pack_conv2d_tf32_nchw_weights(w, b, srcs, split=True)
+    assert bp.numel() == 8 + 4
+    got = ops.conv2d_tf32_nchw_cat(x, wp, bp, Cout, dil, False, split=True)
+    want = F.conv2d(torch.cat(x, 1).double(), w.double(), b.double(), padding=dil, dilation=dil).float()
+    for sl in (slice(0, None, 2), slice(1, None, 2)):                 # the small and the large channels, each against its own scale
+        err = (got[:, sl] - want[:, sl]).abs().max().item()
+        assert err <= 1e-5 * want[:, sl].abs().max().item(), (kind, xs, ws, sl, err, want[:, sl].abs().max().item())
+
+
+def test_conv2d_split16_beyond_fp16_range_degrades_to_tf32_class():
+    """split kind 2 keeps fp32-class accuracy for |x| < 32752 (2^11 * lo(x) must fit fp16); beyond that the correction operand
+    saturates (cvt.rn.satfinite) and the affected products fall back to the TF32 class -- finite, never inf / NaN."""
+    from decnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(78)
+    x = torch.randn(1, 8, 32, 64, device="cuda", generator=g) * 2e5
+    w = torch.randn(8, 8, 3, 3, device="cuda", generator=g) * 0.1
+    b = torch.zeros(8, device="cuda")
+    wp, bp = ops.pack_conv2d_tf32_nchw_weights(w, b, split=True)
+    got = ops.conv2d_tf32_nchw_cat([x], wp, bp, 8, 1, False, split=True)
+    want = F.conv2d(x.double(), w.double(), None, padding=1).float()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 4 * 2 ** -11 * want.abs().max().item()
+
+
 def test_conv2d_tf32_unsupported_shapes_are_refused():
     from decnet_b200 import ops
     assert not ops.conv2d_tf32_supported(8, 8, 64, 97, 1)         # W*4 not a multiple of 16 (TMA stride rule)

@@ -181,6 +181,38 @@ def test_conv2d_3xtf32_nhwc_halo_is_fp32_class(B, H, W, Cin, Cout, relu):
         assert got[..., Cout:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("xs,ws", [(1.0, 1.0), (300.0, 1e-3), (1e-3, 30.0), (3e3, 1e-4)])
+def test_halo_split_kinds_and_operand_ranges(kind, xs, ws, monkeypatch):
+    """Both fp32-class forms of the channels-last kernel (1: 3xTF32; 2, the default: TF32 hi*hi + fp16 K-concatenated corrections)
+    across operand magnitudes, conv and GEMM mode, a ragged last channel chunk (cp = 88 -> chunks of 32, 32, 24)."""
+    import torch.nn.functional as F
+    from decnet_b200 import ops
+    monkeypatch.setattr(ops, "SPLIT_KIND", kind)
+    g = torch.Generator(device="cuda").manual_seed(91)
+    B, Cin, Cout, H, W = 2, 81, 81, 40, 52
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g) * xs
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5 * ws
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1 * xs * ws
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1).float()
+    cp = (Cin + 7) // 8 * 8
+    xn = ops.nchw_cat_to_nhwc_pad([x], cp, round_tf32=False)
+    wp, bp, np_ = ops.pack_conv2d_tf32_weights(w, b, cp, split=True)
+    assert bp.numel() == np_ + 4
+    got = ops.conv2d_tf32_nhwc_halo(xn, wp, bp, False, split=True)
+    err = (got[:, 1:-1, 1:-1, :Cout].permute(0, 3, 1, 2) - want).abs().max().item()
+    assert err <= 1e-5 * want.abs().max().item(), (kind, xs, ws, err, want.abs().max().item())
+    # GEMM mode (taps = 1) on the same operands: the centre tap as a 1x1 conv
+    w1 = w[:, :, 1, 1].contiguous()
+    wg, bg, npg = ops.pack_gemm_weights(w1, b, cp, split=True)
+    rows = xn[:, 1:-1, 1:-1].reshape(-1, cp).contiguous()
+    out = torch.empty(rows.shape[0], npg, device="cuda")
+    ops.gemm_tc(rows, wg, bg, out, False, split=True)
+    want1 = (rows[:, :Cin].double() @ w1.double().t() + b.double()).float()
+    err1 = (out[:, :Cout] - want1).abs().max().item()
+    assert err1 <= 1e-5 * want1.abs().max().item(), (kind, xs, ws, err1)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,relu", [(1, 180, 324, 73, 81, True), (3, 120, 107, 81, 81, False), (2, 200, 150, 145, 72, True),
                                                   (6, 61, 109, 72, 36, True)])
 def test_pair_kernel_matches_one_tile_per_cta(B, H, W, Cin, Cout, relu):
