@@ -511,14 +511,14 @@ def _pack_split_weights(out, bias_np):
         return torch.cat((hi, lo), 0).contiguous(), b
     T, np_, cp = out.shape
     sw = _weight_scale_exp(hi)
-    wh = (hi * 2.0 ** sw).clamp(-65504.0, 65504.0).to(torch.float16)
-    wl = (lo * 2.0 ** (11 + sw)).clamp(-65504.0, 65504.0).to(torch.float16)
+    wh = torch.ldexp(hi, sw).clamp(-65504.0, 65504.0).to(torch.float16)
+    wl = torch.ldexp(lo, sw + 11).clamp(-65504.0, 65504.0).to(torch.float16)
     b2 = torch.zeros((T, np_, 2 * cp), dtype=torch.float16, device=out.device)
     for c0 in range(0, cp, 32):
         cl = min(32, cp - c0)
         b2[:, :, 2 * c0:2 * c0 + cl] = wh[:, :, c0:c0 + cl]
         b2[:, :, 2 * c0 + cl:2 * c0 + 2 * cl] = wl[:, :, c0:c0 + cl]
-    b[bias_np.numel()] = 2.0 ** -(11 + sw)
+    b[bias_np.numel()] = torch.ldexp(torch.ones((), device=out.device), -(sw + 11))
     return torch.cat((hi, b2.view(torch.float32)), 0).contiguous(), b
 
 
@@ -597,9 +597,11 @@ def pack_conv2d_tf32_nchw_weights(w, bias, src_channels=None, split=False):
 
 
 def _weight_scale_exp(hi):
-    """sw with max|hi| * 2^sw just below 2^13: brings the weights into fp16's exponent range with room on both sides."""
-    m = float(hi.abs().max())
-    return max(-40, min(40, 13 - math.frexp(m)[1])) if m > 0 and math.isfinite(m) else 0
+    """sw (0-dim int32 tensor on hi's device, no host sync: packing may run under stream capture) with max|hi| * 2^sw just below
+    2^13: brings the weights into fp16's exponent range with room on both sides."""
+    m = hi.abs().max()
+    e = torch.frexp(torch.where(torch.isfinite(m) & (m > 0), m, torch.ones_like(m)))[1]
+    return (13 - e).clamp(-40, 40).to(torch.int32)
 
 
 def _pack_nchw_split16(blocks):
@@ -611,8 +613,8 @@ def _pack_nchw_split16(blocks):
     pre-permuted: unit g of the global block holds logical unit s64(s128a32(g)), s64 = 16-byte unit ^= bits 7-8."""
     hi, lo = split_tf32(blocks)
     sw = _weight_scale_exp(hi)
-    wh = (hi * 2.0 ** sw).clamp(-65504.0, 65504.0).to(torch.float16)
-    wl = (lo * 2.0 ** (11 + sw)).clamp(-65504.0, 65504.0).to(torch.float16)
+    wh = torch.ldexp(hi, sw).clamp(-65504.0, 65504.0).to(torch.float16)
+    wl = torch.ldexp(lo, sw + 11).clamp(-65504.0, 65504.0).to(torch.float16)
     kh, nck, natoms = blocks.shape[:3]
     logical = torch.stack((wh, wl), 3).contiguous()                                    # [kh][chunk][atom][2][8 k][32 n] halves
     units = logical.view(kh, nck, natoms, 64, 8)                                       # 64 sixteen-byte units per 1 KB block
@@ -620,7 +622,7 @@ def _pack_nchw_split16(blocks):
     s1 = g ^ (((g >> 3) & 3) << 1)                                                     # s128a32: unit bits 1-2 ^= bits 3-4
     perm = s1 ^ ((s1 >> 3) & 3)                                                        # s64: unit bits 0-1 ^= bits 3-4
     packed = units[:, :, :, perm, :].contiguous().view(torch.float32).view(kh, nck, natoms, 8, 32)
-    return torch.cat((hi * 2.0 ** (11 + sw), packed), 0), 2.0 ** -(11 + sw)
+    return torch.cat((torch.ldexp(hi, sw + 11), packed), 0), torch.ldexp(torch.ones((), device=blocks.device), -(sw + 11))
 
 
 def conv2d_tf32_nchw(x, w_packed, bias_padded, cout, dilation=1, relu=False):
