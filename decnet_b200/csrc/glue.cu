@@ -570,7 +570,7 @@ blend_kernel(const float *__restrict__ logit, const float *__restrict__ dense, c
 // grid.y = (b, group of CG channels): one thread = one pixel x CG channels, all 5*CG loads independent and
 // issued before the first use (the kernel is HBM/L2-latency bound: memory-level parallelism is what matters).
 template <int CG>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const float *__restrict__ disp,
             float *__restrict__ warped, float *__restrict__ packed, int B, int C, int H, int W,
             int H_total, int row0)
@@ -592,15 +592,20 @@ warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const fl
     const size_t o00 = (size_t)y0 * W + x0, o01 = (size_t)y0 * W + x1, o10 = (size_t)y1 * W + x0, o11 = (size_t)y1 * W + x1;
     const float *Rb = Rf + ((size_t)b * C + c0) * plane;
     float v00[CG], v01[CG], v10[CG], v11[CG], lv[CG];
+    // four tap pointers stepped by one channel plane: the address arithmetic per load is one 64-bit add (the indexed form cost
+    // ~370 of the kernel's 614 instructions per warp: profiles/r02_warp_kernel_ncu.txt)
+    const float *q00 = Rb + o00, *q01 = Rb + o01, *q10 = Rb + o10, *q11 = Rb + o11;
+    const float *ql = Lf + ((size_t)b * C + c0) * plane + pix;
+    const int nch = min(CG, C - c0);
 #pragma unroll
     for (int i = 0; i < CG; ++i) {
-        const bool ok = c0 + i < C;
-        const float *rp = Rb + (size_t)i * plane;
-        v00[i] = ok ? __ldg(rp + o00) : 0.f;
-        v01[i] = ok ? __ldg(rp + o01) : 0.f;
-        v10[i] = ok ? __ldg(rp + o10) : 0.f;
-        v11[i] = ok ? __ldg(rp + o11) : 0.f;
-        lv[i] = (packed && ok) ? __ldg(Lf + ((size_t)b * C + c0 + i) * plane + pix) : 0.f;
+        const bool ok = i < nch;
+        v00[i] = ok ? __ldg(q00) : 0.f;
+        v01[i] = ok ? __ldg(q01) : 0.f;
+        v10[i] = ok ? __ldg(q10) : 0.f;
+        v11[i] = ok ? __ldg(q11) : 0.f;
+        lv[i] = (packed && ok) ? __ldg(ql) : 0.f;
+        q00 += plane; q01 += plane; q10 += plane; q11 += plane; ql += plane;
     }
     if (packed) {
         float *pb = packed + (size_t)b * (2 * C + 1) * plane + pix;
@@ -616,12 +621,14 @@ warp_kernel(const float *__restrict__ Lf, const float *__restrict__ Rf, const fl
     } else {
         float *wb = warped + ((size_t)b * C + c0) * plane + pix;
 #pragma unroll
-        for (int i = 0; i < CG; ++i)
-            if (c0 + i < C) {
+        for (int i = 0; i < CG; ++i) {
+            if (i < nch) {
                 float v = 0.f;
                 v += v00[i] * t.w00; v += v01[i] * t.w01; v += v10[i] * t.w10; v += v11[i] * t.w11;
-                wb[(size_t)i * plane] = v;
+                *wb = v;
             }
+            wb += plane;
+        }
     }
 }
 
