@@ -138,12 +138,35 @@ costvol_bf16_rows_kernel(const float *__restrict__ L, const float *__restrict__ 
         // channel padding of the tile
         for (int i = threadIdx.x; i < wt * (Cpad - C); i += kBlock) tile[(i / (Cpad - C)) * ts + C + i % (Cpad - C)] = __float2bfloat16(0.f);
         __syncthreads();
-        for (int i = threadIdx.x; i < C * wt; i += kBlock) {
-            const int c = i / wt, wl = i - c * wt, w = w0 + wl;
-            float val = 0.f;
-            if (in_img && w >= d) val = __ldg(Lb + (size_t)c * plane + w) * sample_plane(Rb + (size_t)c * plane, taps[wl], H, W);
-            else if (in_img) val = 0.f * sample_plane(Rb + (size_t)c * plane, taps[wl], H, W);   // keeps NaN/Inf of R like l * r with l = 0
-            tile[wl * ts + c] = __float2bfloat16(val);
+        // a thread keeps ONE pixel of the tile and walks channels cg, cg + ngrp, ...: the four tap offsets and weights are
+        // set up once, every load address is a pointer stepped by ngrp planes (the item-indexed form spent ~180 instructions
+        // per sample on divisions, tap clamps and 64-bit address arithmetic); lanes of a warp are neighbouring pixels
+        {
+            const int ngrp = kBlock / wt;                                        // channel groups (>= 4: wt <= 64)
+            const int cg = threadIdx.x / wt, wl = threadIdx.x - cg * wt, w = w0 + wl;
+            if (cg < ngrp) {
+                const Taps t = taps[wl];
+                const int x0 = min(max(t.x0, 0), W - 1), x1 = min(max(t.x0 + 1, 0), W - 1);
+                const int y0 = min(max(t.y0, 0), H - 1), y1 = min(max(t.y0 + 1, 0), H - 1);
+                const size_t step = (size_t)ngrp * plane;
+                const float *q00 = Rb + (size_t)cg * plane + (size_t)y0 * W + x0, *q01 = Rb + (size_t)cg * plane + (size_t)y0 * W + x1;
+                const float *q10 = Rb + (size_t)cg * plane + (size_t)y1 * W + x0, *q11 = Rb + (size_t)cg * plane + (size_t)y1 * W + x1;
+                const float *ql = Lb + (size_t)cg * plane + w;
+                __nv_bfloat16 *tp = tile + wl * ts + cg;
+                const bool use_l = w >= d;
+                if (in_img) {
+#pragma unroll 4
+                    for (int c = cg; c < C; c += ngrp) {
+                        float v = 0.f;                                          // same summation order as sample_plane()
+                        v += __ldg(q00) * t.w00; v += __ldg(q01) * t.w01; v += __ldg(q10) * t.w10; v += __ldg(q11) * t.w11;
+                        const float l = use_l ? __ldg(ql) : 0.f;               // l = 0 left of the candidate: keeps NaN/Inf of R
+                        *tp = __float2bfloat16(l * v);
+                        q00 += step; q01 += step; q10 += step; q11 += step; ql += step; tp += ngrp;
+                    }
+                } else {
+                    for (int c = cg; c < C; c += ngrp) { *tp = __float2bfloat16(0.f); tp += ngrp; }
+                }
+            }
         }
         __syncthreads();
         uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((((size_t)b * D + d) * nrows + hl) * W + w0) * Cpad);
