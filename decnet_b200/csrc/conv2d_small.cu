@@ -245,7 +245,7 @@ static int launch_tiled_dil(int dil, const float *x, const float *wpk, const flo
 }
 
 // ConvTranspose2d k=3 s=3 (+bias, ReLU): out[b,co,3y+i,3x+j] = relu(bias[co] + sum_ci in[b,ci,y,x] * w[ci,co,i,j])
-template <int COUT>
+template <int COUT, int UNROLL>
 __global__ void __launch_bounds__(128)
 deconv3x3s3_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
                    float *__restrict__ out, int Cin, int h, int wd, int relu)
@@ -255,9 +255,20 @@ deconv3x3s3_kernel(const float *__restrict__ x, const float *__restrict__ w, con
     // reads from shared memory (6 LDS.128 per 24 FMAs).
     extern __shared__ __align__(16) float ws[];          // [Cin][3 j][COUT] for this block's row phase i
     const int Y = blockIdx.y, yy = Y / 3, i = Y - 3 * yy;
-    for (int t = threadIdx.x; t < Cin * 3 * COUT; t += 128) {
-        const int ci = t / (3 * COUT), r = t - ci * 3 * COUT, j = r / COUT, co = r - j * COUT;
-        ws[t] = w[(ci * COUT + co) * 9 + i * 3 + j];     // PyTorch ConvTranspose2d layout [Cin][Cout][3][3]
+    {
+        // thread -> fixed (j, co), input channels ci0, ci0 + nci, ...: no division inside the loop
+        constexpr int kPer = 3 * COUT, kCiStep = 128 / kPer > 0 ? 128 / kPer : 1;
+        if (kPer <= 128) {
+            const int ci0 = threadIdx.x / kPer, r = threadIdx.x - ci0 * kPer, j = r / COUT, co = r - j * COUT;
+            if (ci0 < kCiStep)
+                for (int ci = ci0; ci < Cin; ci += kCiStep)
+                    ws[ci * kPer + r] = __ldg(w + (ci * COUT + co) * 9 + i * 3 + j);   // PyTorch ConvTranspose2d layout [Cin][Cout][3][3]
+        } else {
+            for (int t = threadIdx.x; t < Cin * kPer; t += 128) {
+                const int ci = t / kPer, r = t - ci * kPer, j = r / COUT, co = r - j * COUT;
+                ws[t] = __ldg(w + (ci * COUT + co) * 9 + i * 3 + j);
+            }
+        }
     }
     __syncthreads();
     const int b = blockIdx.z;
@@ -268,8 +279,7 @@ deconv3x3s3_kernel(const float *__restrict__ x, const float *__restrict__ w, con
     for (int k = 0; k < 3 * COUT; ++k) acc[k] = __ldg(bias + (k % COUT));
     const size_t cplane = (size_t)h * wd;
     const float *xp = x + (size_t)b * Cin * cplane + (size_t)yy * wd + xx;
-#pragma unroll 4
-    for (int ci = 0; ci < Cin; ++ci) {
+    auto step = [&](int ci) {
         const float v = __ldg(xp + (size_t)ci * cplane);
         const float4 *wr = reinterpret_cast<const float4 *>(ws + ci * 3 * COUT);
 #pragma unroll
@@ -280,7 +290,11 @@ deconv3x3s3_kernel(const float *__restrict__ x, const float *__restrict__ w, con
             acc[4 * k4 + 2] = fmaf(v, wv.z, acc[4 * k4 + 2]);
             acc[4 * k4 + 3] = fmaf(v, wv.w, acc[4 * k4 + 3]);
         }
-    }
+    };
+    // UNROLL = 8 for the coarse levels (few threads, long channel loops: bound by the latency of the loads, keep 8 in flight),
+    // 4 where the grid fills the machine (fewer registers, more resident blocks)
+#pragma unroll UNROLL
+    for (int ci = 0; ci < Cin; ++ci) step(ci);
     const int W = 3 * wd;
     const size_t plane = (size_t)(3 * h) * W;
     float *ob = out + (size_t)b * COUT * plane + (size_t)Y * W + 3 * xx;
@@ -372,12 +386,16 @@ int decnet_deconv3x3s3(const float *x, const float *w, const float *bias, float 
     DECNET_REQUIRE(smem <= 200 * 1024, "Cin too large");
     DECNET_REQUIRE(3 * h <= 65535, "too many rows");
     dim3 grid((w_in + 127) / 128, 3 * h, B);
-    if (Cout == 8) {
-        auto kern = deconv3x3s3_kernel<8>;
+    if (Cout == 8 && Cin >= 48) {
+        auto kern = deconv3x3s3_kernel<8, 8>;
+        if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
+    } else if (Cout == 8) {
+        auto kern = deconv3x3s3_kernel<8, 4>;
         if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
     } else {
-        auto kern = deconv3x3s3_kernel<24>;
+        auto kern = deconv3x3s3_kernel<24, 4>;
         if (smem > 48 * 1024) DECNET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, out, Cin, h, w_in, relu);
     }
