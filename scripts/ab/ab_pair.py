@@ -6,7 +6,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 from decnet_b200 import _lib, ops
 
 g = torch.Generator(device="cuda").manual_seed(0)
-for (B, h, w, cin, cout) in [(8, 180, 324, 81, 81), (8, 180, 324, 73, 81), (8, 60, 108, 649, 81), (16, 180, 324, 24, 96)]:
+for (B, h, w, cin, cout) in [(8, 180, 324, 81, 81), (8, 180, 324, 81, 64), (8, 180, 324, 81, 48), (8, 180, 324, 145, 64), (16, 180, 324, 24, 96)]:
     cp = (cin + 7) // 8 * 8
     x = torch.zeros(B, h + 2, w + 2, cp, device="cuda")
     x[:, 1:-1, 1:-1, :cin] = torch.randn(B, h, w, cin, device="cuda", generator=g)
