@@ -44,6 +44,7 @@ SIGNATURES = {
     "decnet_conv2d_tc_supported": (_i, [_i] * 6),
     "decnet_conv2d_tc_packed_floats": (_i, [_i] * 3),
     "decnet_conv2d_tc_nchw_cat": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 3 + [_i] * 8 + [C.c_void_p]),
+    "decnet_conv2d_tc_nchw_cat_add": (_i, [C.c_void_p, C.c_void_p, _i] + [_f32p] * 4 + [_i] * 8 + [C.c_void_p]),
     "decnet_conv2d_tc_nhwc_halo": (_i, [_f32p] * 4 + [_i] * 8 + [C.c_void_p]),
     "decnet_conv2d_nhwc_set_variant": (None, [_i]),
     "decnet_conv2d_tc_nhwc_halo_ldc": (_i, [_f32p] * 4 + [_i] * 8 + [C.c_void_p]),

@@ -279,7 +279,7 @@ def _level_stage_band(model, s, l, band, Lf, Rf, prevL, prevR, pred_prev_full, m
     packed = torch.empty((B, 2 * C + 1, Hb, W), dtype=torch.float32, device=Lb.device)
     ops._call("decnet_refine_pack_rows", Lb, Lb.data_ptr(), Rb.data_ptr(), fused.data_ptr(), packed.data_ptr(),
               B, C, Hb, W, Lf.shape[2], e0)
-    pred, _ = model.refinement[l].forward_packed(packed, fused)
+    pred, _ = model.refinement[l].forward_packed(packed, fused, want_residual=False)
     return pred[:, band.r0 - e0: band.r1 - e0].contiguous()
 
 

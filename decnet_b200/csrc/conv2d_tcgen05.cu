@@ -58,6 +58,8 @@ constexpr int kWBox = 64;                  // weight rows (128 B each) per TMA b
 
 struct Params {
     const float *bias;                     // [CP]
+    const float *addend;                   // [B][H][W] added to output channel 0 after the activation (Cout == 1: the
+                                           // refinement's disp + residual, submodule.py:761), or null
     float *out;                            // [B][Cout][H][W]
     int B, Cout, H, W;
     int w_valid;                           // columns >= w_valid (<= W) are written as zeros: row-pitch padding of a W % 4 != 0 image
@@ -281,6 +283,8 @@ __device__ __forceinline__ void epilogue(const Params &p, const float *bias_s, u
             }
             if (col_ok && 4 * g < rows_left) {
                 float *op = orow0 + (size_t)g * gstride + (size_t)c0 * plane;
+                if (p.addend && c0 == 0 && keep)
+                    x[0] += __ldg(p.addend + (size_t)tb * plane + (size_t)(h0 + q) * p.W + col + (size_t)g * gstride);
                 if (c0 + NC <= p.Cout) {                      // full chunk: straight-line stores
 #pragma unroll
                     for (int i = 0; i < NC; ++i) { *op = x[i]; op += plane; }
@@ -602,6 +606,15 @@ int decnet_conv2d_tc_nchw_cat(const float *const *srcs, const int *src_channels,
                               const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
                               int relu, int w_valid, int split, void *stream)
 {
+    return decnet_conv2d_tc_nchw_cat_add(srcs, src_channels, nsrc, w_packed, bias_padded, nullptr, out, B, Cout, H, W, dilation,
+                                         relu, w_valid, split, stream);
+}
+
+int decnet_conv2d_tc_nchw_cat_add(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
+                                  const float *bias_padded, const float *addend, float *out, int B, int Cout, int H, int W,
+                                  int dilation, int relu, int w_valid, int split, void *stream)
+{
+    DECNET_REQUIRE(!addend || Cout == 1, "addend only for single-channel outputs");
     DECNET_REQUIRE(w_valid >= 0 && w_valid <= W, "w_valid=%d outside [0, W=%d]", w_valid, W);
     DECNET_REQUIRE(srcs && src_channels && w_packed && bias_padded && out, "null pointer");
     DECNET_REQUIRE(nsrc >= 1 && nsrc <= 3, "1..3 concatenated sources, got %d", nsrc);
@@ -621,7 +634,7 @@ int decnet_conv2d_tc_nchw_cat(const float *const *srcs, const int *src_channels,
                    "(see decnet_conv2d_tc_supported)", cin_pad, Cout, H, W, dilation, split);
     p.ck1 = cks[0]; p.ck2 = cks[0] + cks[1];
     p.dbg = g_conv2dtc_dbg; p.prof = g_conv2dtc_prof;
-    p.bias = bias_padded; p.out = out; p.B = B; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu;
+    p.bias = bias_padded; p.addend = addend; p.out = out; p.B = B; p.Cout = Cout; p.H = H; p.W = W; p.relu = relu;
     p.w_valid = w_valid > 0 ? w_valid : W;
     CUtensorMap tmX[3], tmW;
     for (int i = 0; i < 3; ++i) {

@@ -17,7 +17,7 @@ fits it:
     transposed conv) runs channels-last on `conv2d_nhwc_halo_kernel`: 3x3 stride-1 layers of the 1/9 level in its conv mode
     on zero-bordered tensors, all the rest in its GEMM mode -- behind `im2col3x3` for strided / dilated / 1/27-level 3x3
     windows, with concatenations written as channel slices of one buffer and the transposed conv as a GEMM + pixel shuffle.
-  No layer runs on a library any more (`library_ok` stays False everywhere).
+  No layer runs on a library: the units have no library branch (a layer no kernel covers raises DecnetError).
 The module refuses CPU tensors like the rest of the package; `oracle/features.py` is the CPU
 restatement used by the tests.
 """

@@ -65,10 +65,13 @@ class _Cached:
                                "into the conv weights and no gradient reaches them); call .eval() first")
 
 
-def _split(unit) -> bool:
+def _split(unit) -> int:
+    """0 for the plain-TF32 mode, else the form of the fp32-class operand split (ops.SPLIT_KIND: 2 = TF32 hi*hi + fp16
+    correction MMA, 1 = three TF32 MMAs).  The value is part of every packed-weight cache key, so packs made under one kind are
+    never handed to the other."""
     if unit.precision not in PRECISIONS:
         raise ValueError(f"precision must be one of {PRECISIONS}, got {unit.precision!r}")
-    return unit.precision == "fp32"
+    return ops.SPLIT_KIND if unit.precision == "fp32" else 0
 
 
 # --------------------------------------------------------------------------------------
@@ -78,9 +81,6 @@ class Conv2dUnit(_Cached, nn.Module):
     """Conv2d [+ BN(eval)] [+ ReLU]; keys as modules/submodule.py:15-49."""
 
     precision = "fp32"
-    # True only for the feature-extractor layers no kernel of ours covers yet (strided / 1x1 wide / ASPP convs at 1/9
-    # and 1/27 resolution, SURVEY.md 8f rank 2): those may run on the library.  Hot-path units never set it.
-    library_ok = False
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, dilation=1, relu=True, bn=True,
                  padding=0):
@@ -178,10 +178,11 @@ class Conv2dUnit(_Cached, nn.Module):
             xp, wv = pad_pitch(x)                      # see forward_cat: pitch-padded copy, cropped result
             return unpad_pitch(self.forward(xp, w_valid=wv), wv)
         nat_first = c.kernel_size == (1, 1) and self.native() is not None      # tiny 1x1 layers: the direct kernel
-        tc = self.tensor_core(x) if (addend is None and not nat_first) else None
+        tc = self.tensor_core(x) if ((addend is None or c.out_channels == 1) and not nat_first) else None
         if tc is not None:
             return ops.conv2d_tf32_nchw_cat([x.contiguous()], tc[0], tc[1], c.out_channels, c.dilation[0], self.relu,
-                                            w_valid or 0, split=_split(self))
+                                            w_valid or 0, split=_split(self),
+                                            addend=None if addend is None else addend.contiguous())
         if w_valid:
             out = self.forward(x, addend)
             out[..., w_valid:] = 0                       # keep the pitch padding at zero behind a non-tensor-core layer
@@ -190,18 +191,8 @@ class Conv2dUnit(_Cached, nn.Module):
         if nat is not None:
             return ops.conv2d_small(x.contiguous(), nat[0], nat[1], c.out_channels, c.kernel_size[0], c.dilation[0],
                                     self.relu, addend)
-        if not self.library_ok:
-            raise _lib.DecnetError(f"Conv2dUnit {c.in_channels}->{c.out_channels} k{c.kernel_size} s{c.stride} d{c.dilation} on "
-                                   f"{tuple(x.shape)}: no decnet_b200 kernel covers this layer (and there is no library fallback)")
-        # feature-extractor layers outside the hot path (library_ok): cuDNN on the folded weights, in this unit's precision
-        w, b = self.folded()
-        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
-                                        deterministic=torch.backends.cudnn.deterministic, allow_tf32=not _split(self)):
-            if self.relu and addend is None:
-                return torch.cudnn_convolution_relu(x, w, b, c.stride, c.padding, c.dilation, 1)
-            x = F.conv2d(x, w, b, stride=c.stride, padding=c.padding, dilation=c.dilation)
-        x = F.relu_(x) if self.relu else x
-        return x if addend is None else x + addend.unsqueeze(1)
+        raise _lib.DecnetError(f"Conv2dUnit {c.in_channels}->{c.out_channels} k{c.kernel_size} s{c.stride} d{c.dilation} on "
+                               f"{tuple(x.shape)}: no decnet_b200 kernel covers this layer (and there is no library fallback)")
 
 
 class Deconv2dUnit(_Cached, nn.Module):
@@ -210,7 +201,6 @@ class Deconv2dUnit(_Cached, nn.Module):
     Kernel 3, stride 3 (the only shape the model uses): deconv3x3s3_kernel, exact fp32."""
 
     precision = "fp32"
-    library_ok = False
 
     def __init__(self, in_channels, out_channels, kernel_size, stride, bn=False):
         super().__init__()
@@ -237,11 +227,8 @@ class Deconv2dUnit(_Cached, nn.Module):
         w, b = self.folded()
         if c.kernel_size == (3, 3) and c.stride == (3, 3) and c.padding == (0, 0) and ops.deconv3x3s3_supported(c.out_channels):
             return ops.deconv3x3s3(x.contiguous(), w, b, True)
-        if not self.library_ok:
-            raise _lib.DecnetError(f"Deconv2dUnit {c.in_channels}->{c.out_channels}: no decnet_b200 kernel covers this layer")
-        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
-                                        deterministic=torch.backends.cudnn.deterministic, allow_tf32=not _split(self)):
-            return F.relu_(F.conv_transpose2d(x, w, b, stride=c.stride))
+        raise _lib.DecnetError(f"Deconv2dUnit {c.in_channels}->{c.out_channels} k{c.kernel_size} s{c.stride}: no decnet_b200 kernel "
+                               f"covers this layer (and there is no library fallback)")
 
 
 class Conv3dUnit(nn.Module):
@@ -514,23 +501,29 @@ class Refinement(_Cached, nn.Module):
             x = ops.conv2d_tf32_nhwc_halo(x, wp, bp, relu, round_out=(not split) and i + 1 < len(packed), split=split)
         return ops.nhwc_pad_to_nchw(x, self.conv[3].conv.out_channels)
 
-    def _tail(self, x, disp_map, start, wv):
+    def _tail(self, x, disp_map, start, wv, want_residual=True):
         for unit in list(self.conv)[start:-1]:
             x = unit(x, w_valid=wv)
-        residual = unpad_pitch(self.conv[-1](x, w_valid=wv), wv).squeeze(1)
-        return disp_map + residual, residual
+        if want_residual:
+            residual = unpad_pitch(self.conv[-1](x, w_valid=wv), wv).squeeze(1)
+            return disp_map + residual, residual
+        # inference: `disp + residual` (submodule.py:761) in the last conv's epilogue, the residual itself is not materialised
+        add = disp_map if wv is None else pad_pitch(disp_map)[0]
+        return unpad_pitch(self.conv[-1](x, addend=add, w_valid=wv), wv).squeeze(1), None
 
-    def forward_packed(self, packed, disp_map):
+    def forward_packed(self, packed, disp_map, want_residual=True):
         """The conv stack on an already packed input cat(left, warped right, disp) [B,2C+1,H,W] (row-band mode: the
         warp needs global row coordinates, decnet_refine_pack_rows) -> (disp + residual, residual)."""
         disp_map = disp_map.contiguous()
         if self._is_wide():
             x, wv = pad_pitch(self._wide_head([packed.contiguous()]))
-            return self._tail(x, disp_map, 4, wv)
+            return self._tail(x, disp_map, 4, wv, want_residual)
         x, wv = pad_pitch(packed.contiguous())
-        return self._tail(x, disp_map, 0, wv)
+        return self._tail(x, disp_map, 0, wv, want_residual)
 
-    def forward(self, left_fea, right_fea, disp_map):
+    def forward(self, left_fea, right_fea, disp_map, want_residual=True):
+        """-> (disp + residual, residual) like the reference (submodule.py:747-762); want_residual=False (the model's inference
+        path) adds the disparity in the last conv's epilogue and returns (disp + residual, None)."""
         disp_map = disp_map.contiguous()
         units = list(self.conv)
         c0 = units[0].conv
@@ -539,7 +532,7 @@ class Refinement(_Cached, nn.Module):
         if self._is_wide():
             warped = ops.warp_bilinear(right_fea.contiguous(), disp_map)
             x, wv = pad_pitch(self._wide_head([left_fea.contiguous(), warped, disp_map]))
-            return self._tail(x, disp_map, 4, wv)
+            return self._tail(x, disp_map, 4, wv, want_residual)
         Wp = (left_fea.shape[3] + 3) // 4 * 4
         if ops.conv2d_tf32_supported(ops.padded_cat_channels((C, C, 1)), c0.out_channels, left_fea.shape[2], Wp,
                                      c0.dilation[0], split):
@@ -547,8 +540,8 @@ class Refinement(_Cached, nn.Module):
             warped = ops.warp_bilinear(right_fea.contiguous(), disp_map)
             lp, wv = pad_pitch(left_fea.contiguous())
             x = units[0].forward_cat([lp, pad_pitch(warped)[0], pad_pitch(disp_map)[0]], w_valid=wv)
-            return self._tail(x, disp_map, 1, wv)
-        return self.forward_packed(ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map), disp_map)
+            return self._tail(x, disp_map, 1, wv, want_residual)
+        return self.forward_packed(ops.refine_pack(left_fea.contiguous(), right_fea.contiguous(), disp_map), disp_map, want_residual)
 
 
 # --------------------------------------------------------------------------------------
@@ -712,7 +705,7 @@ class DecompMatching(nn.Module):
                 aux = ops.attn_pack(None, dense, sparse, lm, var)                  # [dense, sparse, mask, -var]
                 logit = self.soft_attention[l].logits_cat(Lf, aux).squeeze(1).contiguous()
                 soft, fused = ops.blend(logit, dense, sparse, want_mask=is_check)
-                pred, residual = self.refinement[l](Lf, Rf, fused)
+                pred, residual = self.refinement[l](Lf, Rf, fused, want_residual=is_check)
                 if is_check:
                     for k, v in (("dense", dense), ("sparse", sparse), ("var", var), ("soft_mask", soft),
                                  ("fusion", fused), ("residual", residual), ("left_mask", lm), ("right_mask", rm)):

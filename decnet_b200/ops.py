@@ -634,9 +634,10 @@ def conv2d_tf32_nchw(x, w_packed, bias_padded, cout, dilation=1, relu=False):
     return out
 
 
-def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=False, w_valid=0, split=False):
+def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=False, w_valid=0, split=False, addend=None):
     """Conv over torch.cat(srcs, 1) without building it; srcs: 1..3 tensors [B,Ci,H,W] or [B,H,W] (one channel).
-    split: 3xTF32 (w_packed from pack_conv2d_tf32_nchw_weights(split=True))."""
+    split: fp32-class operand split (w_packed from pack_conv2d_tf32_nchw_weights(split=True)).
+    addend [B,H,W] (cout == 1): added after the activation in the epilogue."""
     import ctypes
     x0 = srcs[0]
     _chk("srcs[0]", x0)
@@ -652,9 +653,13 @@ def conv2d_tf32_nchw_cat(srcs, w_packed, bias_padded, cout, dilation=1, relu=Fal
     ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
     cs = (ctypes.c_int * n)(*chans)
     out = torch.empty((B, int(cout), H, W), dtype=torch.float32, device=x0.device)
-    _call("decnet_conv2d_tc_nchw_cat", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
-          w_packed.data_ptr(), bias_padded.data_ptr(), out.data_ptr(), B, int(cout), H, W, int(dilation), 1 if relu else 0,
-          int(w_valid), _split_arg(split))
+    if addend is not None:
+        _chk("addend", addend, x0, (B, H, W))
+        if int(cout) != 1:
+            raise ValueError("addend only for single-channel outputs")
+    _call("decnet_conv2d_tc_nchw_cat_add", x0, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(cs, ctypes.c_void_p), n,
+          w_packed.data_ptr(), bias_padded.data_ptr(), addend.data_ptr() if addend is not None else None, out.data_ptr(),
+          B, int(cout), H, W, int(dilation), 1 if relu else 0, int(w_valid), _split_arg(split))
     return out
 
 

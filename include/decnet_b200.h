@@ -249,6 +249,11 @@ int decnet_conv2d_tc_packed_floats(int Cin, int Cout, int split);
 int decnet_conv2d_tc_nchw_cat(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
                               const float *bias_padded, float *out, int B, int Cout, int H, int W, int dilation,
                               int relu, int w_valid, int split, void *stream);
+/* The same with a single-channel addend [B,H,W] (Cout == 1) added after the activation: the refinement's
+ * `disp_map + residual` (modules/submodule.py:761) in the epilogue of its last conv.  addend NULL = the call above. */
+int decnet_conv2d_tc_nchw_cat_add(const float *const *srcs, const int *src_channels, int nsrc, const float *w_packed,
+                                  const float *bias_padded, const float *addend, float *out, int B, int Cout, int H, int W,
+                                  int dilation, int relu, int w_valid, int split, void *stream);
 
 /* Second formulation of the same convolution for C_out <= 8, dilation <= 4 (conv2d_rows_tcgen05.cu): pixels on the
  * GEMM N dimension, block-Toeplitz weights on M, column taps as accumulator column offsets -- the epilogue needs no

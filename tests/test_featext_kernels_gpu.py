@@ -116,4 +116,4 @@ def test_feature_extractor_has_no_library_layer():
     from decnet_b200.features import FeatExtNetChannelPlus
     from decnet_b200.model import Conv2dUnit, Deconv2dUnit
     fe = FeatExtNetChannelPlus(8)
-    assert not any(m.library_ok for m in fe.modules() if isinstance(m, (Conv2dUnit, Deconv2dUnit)))
+    assert not any(hasattr(m, "library_ok") for m in fe.modules() if isinstance(m, (Conv2dUnit, Deconv2dUnit)))   # no library branch

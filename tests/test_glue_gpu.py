@@ -64,6 +64,9 @@ def test_ops_teacher_forced_vs_reference_golden(name):
         p_, r_ = model.refinement[l](Lf, Rf, fusion[l])
         assert float((r_ - resid[l]).abs().max()) <= tol, ("residual", l, (r_ - resid[l]).abs().max())
         assert float((p_ - pred[s]).abs().max()) <= tol, ("pred", l)
+        # inference form: the disparity is added in the last conv's epilogue, the residual is not materialised -- same bits
+        p2, r2 = model.refinement[l](Lf, Rf, fusion[l], want_residual=False)
+        assert r2 is None and torch.equal(p2, p_), ("pred without residual", l)
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -68,7 +68,7 @@ def test_units_are_inference_only_and_have_no_cpu_route():
     assert all(c.precision == "tf32" for c in m.modules() if isinstance(c, Conv2dUnit))
     with pytest.raises(ValueError):
         set_precision(m, "bf16")
-    assert not any(c.library_ok for c in m.modules() if isinstance(c, Conv2dUnit))   # hot path: our kernels only
+    assert not any(hasattr(c, "library_ok") for c in m.modules() if isinstance(c, Conv2dUnit))   # no library branch exists
 
 
 def test_3xtf32_operand_split_is_fp32_class():
