@@ -1,4 +1,5 @@
 // decnet_b200/csrc/common.cu -- error reporting, launch accounting, device info.
+#include <cstdlib>
 #include "common.cuh"
 #include <cstdarg>
 #include <cstdio>
@@ -25,6 +26,11 @@ int cuda_status(cudaError_t err, const char *what) {
 int after_launch(const char *kernel_name) {
     ++g_launches;
     return cuda_status(cudaGetLastError(), kernel_name);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char *e = std::getenv("DECNET_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 int sm_count_cached() {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
+#include <utility>
 #include "../../include/decnet_b200.h"
 
 namespace decnet {
@@ -34,6 +35,29 @@ inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+// Programmatic dependent launch (the persistent tensor-core kernels follow one another dozens of times per step): a kernel
+// launched with launch_pdl() may start while its predecessor in the stream is still running -- it sets up barriers, allocates
+// TMEM, loads its weights -- and must call pdl_wait() before its first access to anything the predecessor wrote or still reads.
+// pdl_wait() returns once the predecessor grid has completed and its memory operations are visible to this grid; every access
+// that is ordered after the waiting thread's loads (through mbarriers) is ordered after it too.  pdl_trigger() lets the NEXT kernel
+// be scheduled as soon as every CTA of this one has started.  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// true unless DECNET_PDL=0 (read once)
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

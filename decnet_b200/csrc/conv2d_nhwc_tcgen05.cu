@@ -259,11 +259,13 @@ conv2d_nhwc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();                                            // see common.cuh: the next kernel may be scheduled from here on
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            pdl_wait();                                       // first access to the previous kernel's output: the activation tiles
             int s = 0; uint32_t ph = 0;
             int nfill = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -892,7 +894,7 @@ static int launch_nhwc(const float *x, const float *w_packed, const float *bias,
         }
     }
     const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
-    conv2d_nhwc_halo_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+    DECNET_CUDA(launch_pdl(conv2d_nhwc_halo_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tmA, tmB, p));
     return after_launch("conv2d_nhwc_halo_kernel");
 }
 

@@ -350,6 +350,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();                                               // the next kernel of the stream may be scheduled from here on
     const uint32_t tmem_base = tmem_base_slot;
     long long prof_acc[4] = {0, 0, 0, 0};
     const long long prof_t0 = clock64();
@@ -361,6 +362,10 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const int nbox = (p.w_rows + kWBox - 1) / kWBox;
             mbar_arrive_expect_tx(&w_bar, (uint32_t)(nbox * kWBox * 128));
             for (int i = 0; i < nbox; ++i) tma_load_2d(wsm + (size_t)i * kWBox * 128, &tmW, 0, i * kWBox, &w_bar);
+            // everything above (barriers, TMEM, bias, the layer's weights) is independent of the previous kernel; the
+            // activations are not.  All other roles touch global memory only after data this thread loads below has
+            // arrived (epilogue stores, the addend), so this one wait orders the whole CTA behind the predecessor.
+            pdl_wait();
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int t = tile;
@@ -668,7 +673,8 @@ int decnet_conv2d_tc_nchw_cat_add(const float *const *srcs, const int *src_chann
     }
     const int sms = sm_count_cached();
     const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
-    conv2d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX[0], tmX[1], tmX[2], tmW, p);
+    DECNET_CUDA(launch_pdl(conv2d_tcgen05_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream),
+                           tmX[0], tmX[1], tmX[2], tmW, p));
     return after_launch("conv2d_tcgen05_kernel");
 }
 

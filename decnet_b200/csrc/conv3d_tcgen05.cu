@@ -215,6 +215,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();                                        // see common.cuh: the next kernel may be scheduled from here on
     const uint32_t tmem_base = tmem_base_slot;
 
     // Persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and the
@@ -223,6 +224,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            pdl_wait();                                   // first access to the previous kernel's output: the activation tiles
             int s = 0; uint32_t ph = 0;                   // ring slot / phase, advanced without divisions
             for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
                 int tile, n0, nlen;
@@ -859,7 +861,7 @@ static int launch_conv(const void *x, const void *w_packed, const float *bias, c
         }
     }
     const unsigned grid = (unsigned)(p.num_items < sms ? p.num_items : sms);       // persistent: one CTA per SM
-    conv3d_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmBh, p);
+    DECNET_CUDA(launch_pdl(conv3d_tcgen05_kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), tmA, tmB, tmBh, p));
     return after_launch("conv3d_tcgen05_kernel");
 }
 

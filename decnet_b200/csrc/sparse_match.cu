@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(NT, NB)
 sparse_row_gather_kernel(const __grid_constant__ RowArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
     gather_row<MODE, NT>(a, blockIdx.x, smem_raw);
 }
 
@@ -309,6 +311,8 @@ __global__ void __launch_bounds__(NT, NB)
 sparse_row_gather_multi_kernel(const __grid_constant__ MultiArgs m)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();                            // masks and features come from the kernels before this one
     int lvl = 0;
 #pragma unroll
     for (int i = 1; i < kMaxLevels; ++i) lvl += (i < m.nlev && (int)blockIdx.x >= m.first_row[i]) ? 1 : 0;
@@ -699,7 +703,7 @@ static int launch_gather(const float *L, const float *R, const float *ml, const 
     a.C = C; a.H = H; a.W = W; a.D = D; a.nrows = B * H;
     a.vec_ok = (W % 4 == 0) && aligned16(out_a) && aligned16(ssim) && aligned16(mx) &&
                (MODE != MODE_FUSED || aligned16(out_b));
-    kern<<<a.nrows, NT, smem, st>>>(a);
+    DECNET_CUDA(launch_pdl(kern, dim3(a.nrows), dim3(NT), smem, st, a));
     return after_launch("sparse_row_gather_kernel");
 }
 
@@ -738,7 +742,7 @@ static int launch_gather_multi(int nlev, const float *const *L, const float *con
             if (dev >= 0 && dev < 64) set_for[dev] = smem;
         }
     }
-    kern<<<rows, NT, smem, st>>>(m);
+    DECNET_CUDA(launch_pdl(kern, dim3(rows), dim3(NT), smem, st, m));
     return after_launch("sparse_row_gather_multi_kernel");
 }
 
