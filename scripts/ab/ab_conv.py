@@ -7,6 +7,11 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from decnet_b200 import ops  # noqa
 
+# A/B of two builds of the library: put the older build at scripts/ab/libdecnet_old.so first, e.g.
+#   git stash; python -m decnet_b200.build; cp decnet_b200/libdecnet_b200.so scripts/ab/libdecnet_old.so; git stash pop; python -m decnet_b200.build
+# (git-ignored; it travels to the GPU box with the snapshot).  The packed-weight formats must match the old build's.
+if not (ROOT / "scripts/ab/libdecnet_old.so").exists():
+    sys.exit("scripts/ab/libdecnet_old.so is missing: build the revision to compare against first (see the comment above)")
 old = C.CDLL(str(ROOT / "scripts/ab/libdecnet_old.so"))
 new = C.CDLL(str(ROOT / "decnet_b200/libdecnet_b200.so"))
 dev = "cuda"
