@@ -82,7 +82,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons during the timed region: NVML polled every 5 ms from a thread (the region is ~0.1 s long, so
+    nvidia-smi's 200 ms loop yields one or two samples); nvidia-smi -lms 200 when pynvml is missing."""
+
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -91,7 +94,33 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.nvml_index)
+        self.nvml_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.nvml_stop:
+            try:
+                self.nvml_rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def start(self):
+        self.nvml_rows, self.nvml_stop, self.nvml_thread, self.nvml_max = [], False, None, None
+        try:
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through its PCI bus id
+            pr = torch.cuda.get_device_properties(self.index)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            self.nvml_index = nv.nvmlDeviceGetIndex(nv.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+            self.nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.nvml_thread.start()
+            return
+        except Exception:
+            self.nvml_thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -104,6 +133,14 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if getattr(self, "nvml_thread", None) is not None:
+            self.nvml_stop = True
+            self.nvml_thread.join(timeout=1.0)
+            sm = sorted(r[0] for r in self.nvml_rows)
+            reasons = sorted({name for r in self.nvml_rows for bit, name in self.NVML_REASONS.items() if r[1] & bit})
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_min_mhz": float(sm[0]) if sm else None,
+                    "sm_max_mhz": float(self.nvml_max) if self.nvml_max else None, "reasons": reasons, "samples": len(sm),
+                    "source": "NVML, 5 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
