@@ -477,9 +477,11 @@ def leg_sparse_roofline(args, env, left, right, info, pk, extras):
             "peak_source": pk["source"] + " (burst copy)", "algorithmic_bytes": alg,
             "us_per_launch": t_us, "mask_density": args.rho}
     tr = ROOT / "profiles" / "traffic.json"
+    traffic = {}
     if tr.exists():
         try:
-            roof["traffic"] = json.loads(tr.read_text()).get("sparse_row_gather_kernel_bytes_per_launch")
+            traffic = json.loads(tr.read_text())
+            roof["traffic"] = traffic.get("sparse_row_gather_kernel_bytes_per_launch")
         except Exception:
             pass
     # all levels of the step: what the model launches (ONE kernel over the rows of every level, finest first: the aggregate
@@ -494,7 +496,9 @@ def leg_sparse_roofline(args, env, left, right, info, pk, extras):
     roof["all_levels"] = {"kernel": "sparse_row_gather_multi_kernel<FUSED>: the rows of all levels in one launch (the product path)",
                           "algorithmic_bytes": tot_alg, "us": round(tot_us, 2),
                           "frac": round(tot_alg / (tot_us * 1e-6) / 1e9 / pk["hbm_gbs"], 4),
-                          "us_as_separate_launches": round(sum(v["us_alone"] for v in per.values()), 2), "per_level": per}
+                          "us_as_separate_launches": round(sum(v["us_alone"] for v in per.values()), 2), "per_level": per,
+                          # DRAM bytes of one launch at the SceneFlow shapes (same ncu capture as `traffic`); null elsewhere
+                          "traffic": traffic.get("sparse_row_gather_multi_kernel_bytes_per_launch") if args.workload == "sceneflow" else None}
     if extras:
         sweep = {}
         g = torch.Generator(device=dev).manual_seed(5 + top)
