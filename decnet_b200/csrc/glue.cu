@@ -531,6 +531,46 @@ nchw_cat_to_nhwc_pad_kernel(const float *__restrict__ s0, const float *__restric
     out[i] = v;
 }
 
+// Tiled form of the kernel above for CP % 4 == 0 (the product shapes): a block owns 32 padded pixels of one row; warps read one
+// source channel each (32 consecutive pixels: one 128-byte line) into a [32][CP + 1] shared tile, then the block writes the
+// 32 x CP floats of the segment, which are contiguous in the channels-last tensor, as float4.  The element-per-thread form read
+// 32 different planes per warp load (52 us for 33 MB at the 1/9 level).
+__global__ void __launch_bounds__(kBlock)
+nchw_cat_to_nhwc_pad_tiled_kernel(const float *__restrict__ s0, const float *__restrict__ s1, const float *__restrict__ s2,
+                                  int c0, int c1, int c2, float *__restrict__ out, int h, int w, int CP, int round_tf32)
+{
+    extern __shared__ float tile[];                        // [32][CP + 1]
+    const int xp0 = blockIdx.x * 32, yp = blockIdx.y, b = blockIdx.z;
+    const int npx = min(32, w + 2 - xp0), ts = CP + 1, csum = c0 + c1 + c2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool row_in = yp >= 1 && yp <= h;
+    const int xp = xp0 + lane;
+    const bool px_in = row_in && lane < npx && xp >= 1 && xp <= w;
+    const size_t plane = (size_t)h * w, pix = row_in ? (size_t)(yp - 1) * w + (size_t)max(xp - 1, 0) : 0;
+    for (int c = warp; c < CP; c += kBlock / 32) {
+        float v = 0.f;
+        if (px_in && c < csum) {
+            const float *src = c < c0 ? s0 + ((size_t)b * c0 + c) * plane
+                             : c < c0 + c1 ? s1 + ((size_t)b * c1 + (c - c0)) * plane
+                                           : s2 + ((size_t)b * c2 + (c - c0 - c1)) * plane;
+            v = __ldg(src + pix);
+            if (round_tf32) v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        }
+        tile[lane * ts + c] = v;
+    }
+    __syncthreads();
+    float4 *ob = reinterpret_cast<float4 *>(out + (((size_t)b * (h + 2) + yp) * (w + 2) + xp0) * CP);
+    const int cp4 = CP >> 2, total4 = npx * cp4;
+    int px = threadIdx.x / cp4, c4 = threadIdx.x - px * cp4;                  // one division per thread
+    const int dpx = kBlock / cp4, dc4 = kBlock - dpx * cp4;
+    for (int i = threadIdx.x; i < total4; i += kBlock) {
+        const float *t = tile + px * ts + 4 * c4;
+        ob[i] = make_float4(t[0], t[1], t[2], t[3]);
+        px += dpx; c4 += dc4;
+        if (c4 >= cp4) { c4 -= cp4; ++px; }
+    }
+}
+
 __global__ void __launch_bounds__(kBlock)
 nhwc_pad_to_nchw_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int NP, int h, int w, long long n)
 {
@@ -857,6 +897,13 @@ int decnet_nchw_cat_to_nhwc_pad(const float *const *srcs, const int *src_channel
     int sum = 0;
     for (int i = 0; i < nsrc; ++i) { DECNET_REQUIRE(srcs[i] && src_channels[i] > 0, "source %d", i); c[i] = src_channels[i]; s[i] = srcs[i]; sum += c[i]; }
     DECNET_REQUIRE(CP >= sum, "CP=%d < %d channels", CP, sum);
+    const size_t tile_bytes = (size_t)32 * (CP + 1) * sizeof(float);
+    if ((CP & 3) == 0 && tile_bytes <= 48 * 1024 && h + 2 <= 65535 && B <= 65535 &&
+        (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        nchw_cat_to_nhwc_pad_tiled_kernel<<<dim3((w + 2 + 31) / 32, h + 2, B), kBlock, tile_bytes, (cudaStream_t)stream>>>(
+            s[0], s[1], s[2], c[0], c[1], c[2], out, h, w, CP, round_tf32);
+        return after_launch("nchw_cat_to_nhwc_pad_tiled_kernel");
+    }
     const long long n = (long long)B * (h + 2) * (w + 2) * CP;
     nchw_cat_to_nhwc_pad_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(s[0], s[1], s[2], c[0], c[1], c[2],
                                                                                                      out, h, w, CP, round_tf32, n);
