@@ -478,19 +478,22 @@ dynup_glue_nhwc_kernel(const float *__restrict__ logits, const float *__restrict
             lg_s[px * stride + c] = __ldg(src + t);
         }
     }
+    // the 3 x (32 + 2) coarse disparities the block's pixels need (replicate padding), once per block
+    __shared__ float nb_s[3][kGluePx + 2];
+    if (threadIdx.x < 3 * (kGluePx + 2)) {
+        const int ky = threadIdx.x / (kGluePx + 2), kxp = threadIdx.x - ky * (kGluePx + 2);
+        const int yy = min(max(y + ky - 1, 0), h - 1), xx = min(max(x0 + kxp - 1, 0), w - 1);
+        nb_s[ky][kxp] = __ldg(disp + (size_t)b * plane + (size_t)yy * w + xx);
+    }
     __syncthreads();
     const int i = threadIdx.x / (3 * kGluePx), r = threadIdx.x - i * 3 * kGluePx, px = r / 3, j = r - 3 * px;
     if (px >= nx) return;
     const int x = x0 + px;
-    const float *db = disp + (size_t)b * plane;
     float nb[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int yy = min(max(y + ky - 1, 0), h - 1), xx = min(max(x + kx - 1, 0), w - 1);
-            nb[ky * 3 + kx] = __ldg(db + (size_t)yy * w + xx);
-        }
+        for (int kx = 0; kx < 3; ++kx) nb[ky * 3 + kx] = nb_s[ky][px + kx];
     const float *lg = lg_s + px * stride + (i * 3 + j) * 9;
     float v[9], mx = -INFINITY;
 #pragma unroll
